@@ -1,0 +1,361 @@
+#!/usr/bin/env python
+"""bench.py -- decoded depth frames/s of the fused structured-light kernel on B200.
+
+    python bench.py --gpus N --steps K --warmup W            (N == 1)
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+    python bench.py --impl reference ...                     (the CPU path, host cores)
+
+Workload: BASELINE.json configs[1] -- 1920x1200 camera, 9 Gray pairs (8 bits +
+the complementary half-period bit) + 4-step phase shift, projector width 2560.
+A "step" is one pass of the hot path (one fused kernel launch) over a batch of
+`--batch` independent frame sets that are already resident in HBM; the batch is
+far larger than L2 (126 MB), so no input byte is served from cache.  Frame sets
+are sharded across ranks with no data-path collective (scaling: weak -- every
+rank processes its own `--batch` frame sets per step).
+
+`value`  = frame sets decoded per second, whole job, inputs resident in HBM.
+`e2e`    = the same metric through the public host call
+           (capi.Reconstructor.reconstruct_into -> slc_reconstruct_host) with
+           pinned HOST buffers: H2D upload of every stack and D2H download of
+           every XYZ map and mask inside the timed region, pipelined over
+           stream slots.
+`roofline` = algorithmic bytes (39 B/px: 22 u8 planes read + float4 XYZ + u8
+           mask written) per launch / mean launch duration (CUDA events on the
+           launching stream), against the measured HBM copy bandwidth.
+`cpu_baseline` = the CPU oracle (a line-by-line port of the reference's loops)
+           timed on this box's host cores on a bounded sample, rank 0, N == 1.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from structured_light_calculation_b200 import synth  # noqa: E402
+from structured_light_calculation_b200.calibration import load_calibration  # noqa: E402
+from structured_light_calculation_b200.configs import CONFIGS  # noqa: E402
+from structured_light_calculation_b200 import distributed as D  # noqa: E402
+
+METRIC = "decoded_depth_frames_per_sec"
+UNIT = "frames/s"
+FALLBACK_HBM_GBS = 6650.0   # B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
+
+
+def hbm_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return FALLBACK_HBM_GBS, "fallback"
+
+
+def ncu_traffic_per_stack(cfg_name):
+    """DRAM bytes per frame set from the committed ncu --set full capture, if any."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)[cfg_name]["dram_bytes_per_stack"])
+    except Exception:
+        return None
+
+
+class ClockSampler:
+    """nvidia-smi clock / throttle-reason samples during the timed region."""
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                 "-lms", "50", "-f", self.path], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self) -> dict:
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        time.sleep(0.12)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        try:
+            with open(self.path) as f:
+                for line in f:
+                    parts = [p.strip() for p in line.split(",")]
+                    if len(parts) < 9:
+                        continue
+                    try:
+                        sm.append(float(parts[1]))
+                        mx.append(float(parts[2]))
+                    except ValueError:
+                        continue
+                    for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"),
+                                         parts[5:9]):
+                        if val.lower().startswith("active"):
+                            reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def build_inputs(cfg, pool: int):
+    base = load_calibration(os.path.join(ROOT, "tests", "golden", "Result.yml"))
+    cal = synth.synthetic_calibration(cfg, base)
+    scene = synth.make_scene(cfg, cal)
+    stacks = [synth.render_stack(cfg, scene, noise_sigma=1.0, seed=1234 + i) for i in range(pool)]
+    return cal, scene, stacks
+
+
+def run_reference(args, cfg):
+    """--impl reference: the reference's CPU path (oracle port, all host threads)."""
+    rank, _, world = D.env_rank_world()
+    if rank != 0:
+        return 0
+    from oracle import sl_oracle as O
+    threads = O.max_threads()
+    cal, _, stacks = build_inputs(cfg, 1)
+    ocfg = O.make_config(cfg.width, cfg.height, cfg.projector_width, cfg.gray_digits, cfg.phase_steps,
+                         cfg.fov_min, cfg.fov_max, cfg.modulation_min, threads)
+    ocal = O.make_calib(cal.cam, cal.pro, cal.R, cal.T)
+    per_step = args.ref_stacks_per_step
+    O.time_reconstruct(ocfg, ocal, stacks[0], max(1, args.warmup))          # warm-up
+    t0 = time.perf_counter()
+    secs = O.time_reconstruct(ocfg, ocal, stacks[0], args.steps * per_step)
+    wall = time.perf_counter() - t0
+    total = float(secs.sum())
+    value = args.steps * per_step / total
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(cfg), "frame_sets_per_step": per_step,
+                   "note": "CPU oracle port of the reference loops (reference needs OpenCV 2.4.9 + Windows, "
+                           "not buildable here); hot loops only, no I/O"},
+        "mpix_per_s": value * cfg.pixels / 1e6,
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"{args.steps * per_step} x one {cfg.width}x{cfg.height} stack, OpenMP {threads} threads"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "wall_s": wall,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def workload_name(cfg):
+    return (f"{cfg.width}x{cfg.height} stack, {cfg.gray_digits}-pair Gray (8 bits + complementary LSB) + "
+            f"{cfg.phase_steps}-step phase shift, projector width {cfg.projector_width} (BASELINE configs[1])")
+
+
+def cpu_baseline(cfg, cal, stack):
+    from oracle import sl_oracle as O
+    ocal = O.make_calib(cal.cam, cal.pro, cal.R, cal.T)
+    threads = O.max_threads()
+
+    def timed(nthreads, reps):
+        ocfg = O.make_config(cfg.width, cfg.height, cfg.projector_width, cfg.gray_digits, cfg.phase_steps,
+                             cfg.fov_min, cfg.fov_max, cfg.modulation_min, nthreads)
+        O.time_reconstruct(ocfg, ocal, stack, 1)
+        return float(np.median(O.time_reconstruct(ocfg, ocal, stack, reps)))
+
+    t1 = timed(1, 12)
+    tn = timed(threads, 40) if threads > 1 else t1
+    return {
+        "value": 1.0 / tn, "unit": UNIT, "cores": threads, "kind": "port",
+        "sample": f"one {cfg.width}x{cfg.height} stack: median of 40 reps on {threads} threads (OpenMP rows), "
+                  f"12 reps on 1 thread; hot loops only",
+        "single_thread_value": 1.0 / t1, "single_thread_ms_per_frame": 1e3 * t1,
+        "all_cores_ms_per_frame": 1e3 * tn,
+    }
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default="config2", choices=sorted(CONFIGS))
+    ap.add_argument("--batch", type=int, default=256, help="frame sets per step (device-resident batch)")
+    ap.add_argument("--pool", type=int, default=4, help="distinct rendered stacks tiled into the batch")
+    ap.add_argument("--e2e-stacks", type=int, default=24, help="frame sets per end-to-end step")
+    ap.add_argument("--e2e-chunk", type=int, default=4, help="frame sets per upload/launch/download chunk")
+    ap.add_argument("--e2e-slots", type=int, default=3)
+    ap.add_argument("--pxt", type=int, default=0, help="tuning: pixels per thread (4/8/16)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-stacks-per-step", type=int, default=2)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else max(args.warmup, 1)
+    cfg = CONFIGS[args.config]
+
+    if args.impl == "reference":
+        return run_reference(args, cfg)
+
+    import torch
+    from structured_light_calculation_b200 import capi
+
+    rank, local_rank, world = D.env_rank_world()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback "
+                         "(use --impl reference for the CPU path)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        D.init_process_group("nccl")
+    if args.pxt:
+        capi.load_library().slc_tune_pixels_per_thread(args.pxt)
+
+    F = args.batch
+    cal, scene, stacks = build_inputs(cfg, args.pool)
+    rec = capi.Reconstructor(cfg, device=local_rank, max_batch=args.e2e_chunk, num_slots=args.e2e_slots)
+    rec.set_calibration(cal)
+    info = rec.info()
+
+    # ---- device-resident batch (torch owns the memory; the kernel is ours) ----
+    d_in = torch.empty((F, cfg.planes, cfg.height, cfg.width), dtype=torch.uint8, device=dev)
+    d_xyzw = torch.empty((F, cfg.height, cfg.width, 4), dtype=torch.float32, device=dev)
+    d_mask = torch.empty((F, cfg.height, cfg.width), dtype=torch.uint8, device=dev)
+    pool_dev = [torch.from_numpy(s).to(dev) for s in stacks]
+    for i in range(F):
+        d_in[i].copy_(pool_dev[i % len(pool_dev)])
+    del pool_dev
+    torch.cuda.synchronize()
+    stream = torch.cuda.current_stream()
+
+    def step():
+        rec.reconstruct_device(d_in.data_ptr(), F, d_xyzw.data_ptr(), d_mask.data_ptr(), None, stream.cuda_stream)
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = rec.launch_count()
+    events = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    D.barrier()
+    torch.cuda.synchronize()
+    events[0].record(stream)
+    for i in range(args.steps):
+        step()
+        events[i + 1].record(stream)
+    torch.cuda.synchronize()
+    D.barrier()
+    total_ms = events[0].elapsed_time(events[-1])
+    per_launch_ms = [events[i].elapsed_time(events[i + 1]) for i in range(args.steps)]
+    launches = rec.launch_count() - launches0
+    total_ms_max = D.max_over_ranks(total_ms, dev)
+    launches_all = int(D.sum_over_ranks(launches, dev))
+    value = world * F * args.steps / (total_ms_max * 1e-3)
+
+    # ---- end to end through the public host call, pinned host buffers ----
+    E = args.e2e_stacks
+    h_in = capi.PinnedArray((E, cfg.planes, cfg.height, cfg.width), np.uint8)
+    h_xyzw = capi.PinnedArray((E, cfg.height, cfg.width, 4), np.float32)
+    h_mask = capi.PinnedArray((E, cfg.height, cfg.width), np.uint8)
+    for i in range(E):
+        h_in.array[i] = stacks[i % len(stacks)]
+    e2e_steps = args.steps
+    for _ in range(2):
+        rec.reconstruct_into(h_in, E, h_xyzw, h_mask)
+    D.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        rec.reconstruct_into(h_in, E, h_xyzw, h_mask)     # blocking: returns with results in host memory
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    D.barrier()
+    e2e_s_max = D.max_over_ranks(e2e_s, dev)
+    e2e_value = world * E * e2e_steps / e2e_s_max
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- spot check of what was just computed (not timed) ----
+    checked = None
+    cpu = None
+    if rank == 0:
+        from oracle import sl_oracle as O   # checker + CPU baseline only
+        ocfg = O.make_config(cfg.width, cfg.height, cfg.projector_width, cfg.gray_digits, cfg.phase_steps,
+                             cfg.fov_min, cfg.fov_max, cfg.modulation_min, O.max_threads())
+        want = O.reconstruct(ocfg, O.make_calib(cal.cam, cal.pro, cal.R, cal.T), stacks[0])
+        z_dev = d_xyzw[0, :, :, 2].cpu().numpy()
+        m_dev = d_mask[0].cpu().numpy()
+        tol = 1e-5 * (cfg.fov_max - cfg.fov_min)
+        checked = bool(np.array_equal(m_dev, want["mask"]) and np.abs(z_dev - want["z"]).max() <= tol
+                       and np.array_equal(h_mask.array[0], want["mask"])
+                       and np.abs(h_xyzw.array[0, :, :, 2] - want["z"]).max() <= tol)
+        if world == 1 and not args.no_cpu_baseline:
+            cpu = cpu_baseline(cfg, cal, stacks[0])
+
+    if rank == 0:
+        peak, peak_kind = hbm_peak()
+        mean_launch_ms = statistics.fmean(per_launch_ms)
+        alg_bytes = cfg.algorithmic_bytes_per_pixel * cfg.pixels * F
+        achieved = alg_bytes / (mean_launch_ms * 1e-3) / 1e9
+        traffic_ps = ncu_traffic_per_stack(args.config)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": total_ms_max / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(cfg), "frame_sets_per_step_per_gpu": F,
+                       "planes": cfg.planes, "bytes_per_pixel_algorithmic": cfg.algorithmic_bytes_per_pixel,
+                       "l2_policy": f"inputs larger than L2: {F * cfg.stack_bytes / 1e9:.1f} GB read + "
+                                    f"{F * cfg.pixels * 17 / 1e9:.1f} GB written per step",
+                       "parallelism": f"frame sets sharded over {world} GPU(s), no collective",
+                       "distinct_stacks_in_pool": len(stacks)},
+            "mpix_per_s": value * cfg.pixels / 1e6,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": E * cfg.stack_bytes,
+                    "d2h_bytes_per_step": E * cfg.pixels * 17, "frame_sets_per_step_per_gpu": E,
+                    "steps": e2e_steps, "ms_per_step": 1e3 * e2e_s_max / e2e_steps,
+                    "api": "capi.Reconstructor.reconstruct_into -> slc_reconstruct_host, pinned host buffers, "
+                           f"{args.e2e_slots} stream slots x {args.e2e_chunk} frame sets"},
+            "gpu_launches": launches_all,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": (traffic_ps * F if traffic_ps else None),
+                         "peak_kind": f"of {peak_kind}", "kernel": "slc::reconstruct_vec_kernel",
+                         "algorithmic_bytes_per_launch": alg_bytes, "mean_launch_ms": mean_launch_ms,
+                         "min_launch_ms": min(per_launch_ms), "max_launch_ms": max(per_launch_ms)},
+            "cpu_baseline": cpu,
+            "clocks": clocks,
+            "kernel": {"variant": info.kernel_variant, "regs": info.kernel_regs, "block": info.kernel_block,
+                       "smem": info.kernel_smem},
+            "checked_against_oracle": checked,
+        }
+        print(json.dumps(line), flush=True)
+    rec.close()
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,211 @@
+// dynaframe_b200.hpp -- the reference's own C++ entry points, re-hosted on the
+// C ABI of slcalc_b200.h.
+//
+// elevenface/Structured-Light-Calculation has no plugin layer; host code talks
+// to three classes (paths relative to DynaFrame/DynaFrame/):
+//     CDecodeGray   CDecodeGray.h:18-53
+//     CDecodePhase  CDecodePhase.h:12-39
+//     CCalculation  CCalculation.h:10-95
+// with a setter -> Decode()/Calculate*() -> getter protocol, bool returns and
+// ErrorHandling(string) for messages (GlobalFunction.h:9).  The classes below
+// keep those names, argument meanings and error behaviour, so reference-style
+// host code ports by changing an #include and a namespace.  What differs:
+//   * cv::Mat is replaced by dynaframe::Mat, a small ref-counted dense 2-D array
+//     with the members this path uses (rows, cols, type(), at<T>(), copyTo,
+//     clone, create, empty) -- OpenCV is not a dependency;
+//   * the compile-time globals of StaticParameters.{h,cpp} become the runtime
+//     struct StaticParameters handed to the constructors;
+//   * the file-backed CSensor (CSensorV.cpp) is replaced by an in-memory
+//     CSensor with the same LoadDatas / SetProPicture / GetCamPicture calls;
+//   * all arithmetic runs on the GPU through slcalc_b200.h.  No CPU fallback:
+//     without a CUDA device every Decode()/Calculate*() returns false.
+#ifndef DYNAFRAME_B200_HPP_
+#define DYNAFRAME_B200_HPP_
+
+#include <cstdint>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "slcalc_b200.h"
+
+namespace dynaframe {
+
+// OpenCV type codes used on the path
+enum { CV_8UC1 = 0, CV_16SC1 = 3, CV_32FC1 = 5, CV_64FC1 = 6, CV_32FC4 = 29 };
+
+class Mat {
+public:
+    int rows = 0, cols = 0;
+    Mat() = default;
+    Mat(int rows_, int cols_, int type_) { create(rows_, cols_, type_); }
+    // wrap caller-owned memory (no copy, like cv::Mat(rows, cols, type, data, step))
+    Mat(int rows_, int cols_, int type_, void* data, size_t step_bytes = 0);
+    void create(int rows_, int cols_, int type_);
+    bool empty() const { return data_ == nullptr || rows == 0 || cols == 0; }
+    int type() const { return type_; }
+    size_t elemSize() const;
+    size_t step() const { return step_; }
+    bool isContinuous() const { return step_ == (size_t)cols * elemSize(); }
+    uint8_t* ptr(int r = 0) { return data_ + (size_t)r * step_; }
+    const uint8_t* ptr(int r = 0) const { return data_ + (size_t)r * step_; }
+    template <typename T> T& at(int r, int c) { return reinterpret_cast<T*>(data_ + (size_t)r * step_)[c]; }
+    template <typename T> const T& at(int r, int c) const {
+        return reinterpret_cast<const T*>(data_ + (size_t)r * step_)[c];
+    }
+    void copyTo(Mat& dst) const;   // deep copy
+    Mat clone() const { Mat m; copyTo(m); return m; }
+
+private:
+    int type_ = CV_8UC1;
+    size_t step_ = 0;
+    uint8_t* data_ = nullptr;
+    std::shared_ptr<uint8_t> owner_;
+};
+
+// StaticParameters.cpp:4-38 as a runtime value; defaults are the reference's.
+struct StaticParameters {
+    int PROJECTOR_RESLINE = 1280;
+    int PROJECTOR_RESROW = 800;
+    int CAMERA_RESLINE = 1280;
+    int CAMERA_RESROW = 1024;
+    int GRAY_V_NUMDIGIT = 6;
+    int GRAY_H_NUMDIGIT = 5;
+    int PHASE_NUMDIGIT = 4;
+    bool VISUAL_DEBUG = false;
+    std::string DATA_PATH = "";
+    int DYNAFRAME_MAXNUM = 100;
+    int FOV_MIN_DISTANCE = 10;
+    int FOV_MAX_DISTANCE = 100;
+    int RECO_WINDOW_SIZE = 21;
+    // additions of this implementation
+    float MODULATION_MIN = 0.0f;   // [EXT] 0 = disabled (reference behaviour)
+    int CUDA_DEVICE = 0;
+};
+
+// GlobalFunction.cpp:3-8 without the system("PAUSE"): prints the message,
+// remembers it, returns 0.
+int ErrorHandling(std::string message);
+const std::string& LastErrorMessage();
+
+// In-memory replacement of the file-backed sensor (CSensorV.h:15-61).
+// group 0 = vGray images, 1 = vPhase images, 2 = dyna images.
+class CSensor {
+public:
+    bool InitSensor();
+    bool CloseSensor();
+    bool StoreDatas(int groupNum, int idx, const Mat& picture);   // feeds what LoadDatas would read from disk
+    bool LoadDatas(int groupNum);
+    bool UnloadDatas();
+    bool SetProPicture(int nowNum);
+    Mat GetCamPicture();        // deep copy, like the reference
+
+private:
+    std::vector<Mat> groups_[3];
+    int group_ = -1;
+    int now_ = 0;
+};
+
+// CDecodeGray.h:18-53
+class CDecodeGray {
+public:
+    explicit CDecodeGray(const StaticParameters& sp = StaticParameters());
+    ~CDecodeGray();
+    CDecodeGray(const CDecodeGray&) = delete;
+    CDecodeGray& operator=(const CDecodeGray&) = delete;
+
+    bool Decode();
+    Mat GetResult();                                         // CV_64FC1, deep copy
+    bool SetMat(int num, Mat pic);                           // deep-copies the input
+    bool SetNumDigit(int numDigit, bool ver);
+    bool SetMatFileName(std::string codeFilePath, std::string codeFileName);
+
+private:
+    bool AllocateSpace();
+    bool ReleaseSpace();
+    StaticParameters sp_;
+    int m_numDigit = 0;
+    int m_grayCodeSize = 0;
+    std::vector<int16_t> m_gray2bin;
+    std::string m_codeFilePath, m_codeFileName;
+    bool m_vertical = true;
+    bool allocated_ = false;
+    uint8_t* pinned_ = nullptr;          // [2G][H][W] staging, pinned
+    std::vector<uint8_t> have_;
+    Mat m_result;
+    slc_context* ctx_ = nullptr;
+};
+
+// CDecodePhase.h:12-39
+class CDecodePhase {
+public:
+    explicit CDecodePhase(const StaticParameters& sp = StaticParameters());
+    ~CDecodePhase();
+    CDecodePhase(const CDecodePhase&) = delete;
+    CDecodePhase& operator=(const CDecodePhase&) = delete;
+
+    bool Decode();
+    Mat GetResult();                                         // CV_64FC1, deep copy
+    bool SetMat(int num, Mat pic);
+    bool SetNumMat(int numMat, int pixperiod);
+
+private:
+    bool DeleteSpace();
+    StaticParameters sp_;
+    int m_numMat = 0;
+    int m_pixPeroid = 16;
+    bool allocated_ = false;
+    uint8_t* pinned_ = nullptr;
+    Mat m_result;
+    slc_context* ctx_ = nullptr;
+};
+
+// CCalculation.h:10-95 (first-frame path).
+class CCalculation {
+public:
+    explicit CCalculation(const StaticParameters& sp = StaticParameters());
+    ~CCalculation();
+    CCalculation(const CCalculation&) = delete;
+    CCalculation& operator=(const CCalculation&) = delete;
+
+    // Where Init() finds what the reference hard-codes (CCalculation.cpp:86-93,124-127):
+    void SetParameterFile(const std::string& ymlPath) { m_paraFile = ymlPath; }
+    void SetGrayCodeFile(const std::string& path, const std::string& name) { m_codePath = path; m_codeName = name; }
+    void SetPointCloudFile(const std::string& file) { m_pcFile = file; }
+    CSensor* Sensor() { return m_sensor; }                  // valid after Init()
+
+    bool Init();
+    bool CalculateFirst();
+    bool CalculateOther();      // dynamic-frame tracker: not part of this path, returns false
+    bool Result(std::string fileName, int i);
+
+    // results of frame 0 (valid after CalculateFirst): CV_32FC4 (x,y,z,U) and CV_8UC1 mask,
+    // plus the reference's separate planes on request
+    const Mat& PointMap() const { return m_xyzw; }
+    const Mat& ValidMask() const { return m_mask; }
+    Mat GetX() const;   // CV_64FC1 views of m_xMat[0] / m_yMat[0] / m_zMat[0] / m_ProjectorU[0]
+    Mat GetY() const;
+    Mat GetZ() const;
+    Mat GetProjectorU() const;
+
+private:
+    bool ReleaseSpace();
+    bool FillFirstProjectorUAndCoordinate();
+    StaticParameters sp_;
+    CSensor* m_sensor = nullptr;
+    slc_context* ctx_ = nullptr;
+    std::string m_paraFile = "parameters.yml";
+    std::string m_codePath = "Patterns/", m_codeName = "vGrayCode.txt";
+    std::string m_pcFile = "iFrame.txt";
+    uint8_t* pinned_stack_ = nullptr;
+    Mat m_xyzw, m_mask, m_projU;
+    bool calibrated_ = false;
+};
+
+// Helpers shared by the classes and usable on their own.
+bool ReadCalibrationYaml(const std::string& path, double cam[9], double pro[9], double R[9], double T[3]);
+bool ReadGrayCodeFile(const std::string& file, int grayCodeSize, std::vector<int16_t>& gray2bin);
+
+}  // namespace dynaframe
+
+#endif  // DYNAFRAME_B200_HPP_

@@ -1,0 +1,202 @@
+/*
+ * slcalc_b200.h -- C ABI of libslcalc_b200.so, the B200 (sm_100a) drop-in for
+ * DynaFrame's first-frame structured-light reconstruction path.
+ *
+ * The reference (elevenface/Structured-Light-Calculation) has no FFI layer:
+ * its seam is the C++ class API CDecodeGray / CDecodePhase / CCalculation.
+ * Each entry point below names the reference interface it replaces; paths are
+ * relative to DynaFrame/DynaFrame/ in the reference tree.  The C++ classes with
+ * the reference's own names live in include/dynaframe_b200.hpp and are built
+ * on nothing but this header.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no CUDA, torch or OpenCV types;
+ *   - every function returns an slc_status (0 = OK); the message for the last
+ *     failure on a context is slc_last_error(ctx) (slc_last_error(NULL) for a
+ *     failed slc_create).  The reference's bool + ErrorHandling(string)
+ *     convention (GlobalFunction.cpp:3-8) maps to status != SLC_OK + message;
+ *   - a context is bound to one CUDA device and is single-caller; distinct
+ *     contexts may be driven from distinct host threads (one per GPU);
+ *   - there is NO CPU fallback: without a CUDA device slc_create fails with
+ *     SLC_ERR_NO_DEVICE.
+ *
+ * Data layout
+ *   stack   : uint8 [n_stacks][P][H][W], P = 2*G + N, plane-major.  Planes
+ *             2b, 2b+1 are the Gray pattern / inverse pair of bit b, b = 0 the
+ *             LSB (CDecodeGray.cpp:159,193-198; the order CCalculation.cpp
+ *             :539-544 feeds SetMat), followed by the N phase images
+ *             (CDecodePhase.cpp:59-62; CCalculation.cpp:552-557).
+ *   xyzw    : float  [n_stacks][H][W][4] = (x, y, z, U) -- m_xMat/m_yMat/m_zMat
+ *             (CCalculation.cpp:118-120) packed, w = decoded projector column
+ *             (m_ProjectorU, :115) rounded to f32.  Invalid pixel => x=y=z=0.
+ *   mask    : uint8  [n_stacks][H][W], 1 = modulation_ok && U != 0 &&
+ *             fov_min <= z <= fov_max (CCalculation.cpp:678-682,701-704).
+ *   parity planes (optional): kbin int16, corr int8, phase_pix float,
+ *             proj_u double, each [n_stacks][H][W].
+ */
+#ifndef SLCALC_B200_H_
+#define SLCALC_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SLC_ABI_VERSION 1
+
+typedef enum {
+    SLC_OK = 0,
+    SLC_ERR_INVALID_ARG = 1,     /* bad geometry, NULL pointer, digit count outside 1..16 (CDecodeGray.cpp:39) */
+    SLC_ERR_NOT_INITIALISED = 2, /* calibration missing (CCalculation.cpp:176-181), SetMat before SetNum* */
+    SLC_ERR_CUDA = 3,            /* a CUDA runtime call or kernel launch failed */
+    SLC_ERR_NO_DEVICE = 4,       /* no usable CUDA device: there is no CPU path */
+    SLC_ERR_OUT_OF_MEMORY = 5,
+    SLC_ERR_STATE = 6            /* e.g. slot busy, Init twice (CCalculation.cpp:80-83) */
+} slc_status;
+
+/* slc_config.flags */
+#define SLC_FLAG_Z_FP64        (1u << 0) /* solve every z in f64 (validation mode); default is f32 with an
+                                            f64 re-solve of pixels near the FOV limits, which already makes
+                                            the mask bit-exact */
+#define SLC_FLAG_SCALAR_KERNEL (1u << 1) /* force the one-pixel-per-thread kernel (used for widths that are
+                                            not a multiple of 16, and as a cross-check) */
+
+typedef struct slc_context slc_context;
+
+/* The reference's compile-time constants (StaticParameters.cpp:4-9,16-18,
+ * 34-35) as a runtime struct. */
+typedef struct {
+    int32_t  width;            /* CAMERA_RESLINE */
+    int32_t  height;           /* CAMERA_RESROW */
+    int32_t  projector_width;  /* PROJECTOR_RESLINE */
+    int32_t  gray_digits;      /* GRAY_V_NUMDIGIT: pattern/inverse pairs, 1..16 */
+    int32_t  phase_steps;      /* PHASE_NUMDIGIT: N >= 3 (reference: 4) */
+    double   fov_min;          /* FOV_MIN_DISTANCE */
+    double   fov_max;          /* FOV_MAX_DISTANCE */
+    float    modulation_min;   /* [EXT] minimum fringe amplitude b in grey levels; 0 = off (reference) */
+    uint32_t flags;            /* SLC_FLAG_* */
+    int32_t  device;           /* CUDA device ordinal */
+    int32_t  max_batch;        /* stacks per slot the host path can stage on the device (>= 1) */
+    int32_t  num_slots;        /* stream slots for the pipelined host path, 1..8 */
+} slc_config;
+
+typedef struct {
+    int32_t  planes;           /* P = 2G + N */
+    int32_t  gray_period;      /* gp = PW / 2^G      (CDecodeGray.cpp:183) */
+    int32_t  phase_period;     /* T  = PW / 2^(G-1)  (CCalculation.cpp:550) */
+    int32_t  sm_count;
+    int64_t  pixels;           /* W*H */
+    int64_t  stack_bytes;      /* P*W*H */
+    int64_t  xyzw_bytes;       /* 16*W*H */
+    int64_t  mask_bytes;       /* W*H */
+    int32_t  kernel_variant;   /* 0 = specialised <G,N> vector kernel, 1 = generic vector, 2 = scalar */
+    int32_t  kernel_regs;      /* registers per thread of the kernel that will run */
+    int32_t  kernel_block;     /* threads per block */
+    int32_t  kernel_smem;      /* dynamic shared memory per block, bytes */
+} slc_info;
+
+/* Optional parity / debug planes.  NULL members are skipped. */
+typedef struct {
+    int16_t *kbin;       /* gray2bin[code]: half-period index (CDecodeGray.cpp:200 before the multiply) */
+    int8_t  *corr;       /* wrap correction taken at CCalculation.cpp:572-581: -1, 0, +1 */
+    float   *phase_pix;  /* CDecodePhase::CountResult value, (0, T] (CDecodePhase.cpp:69-75) */
+    double  *proj_u;     /* ProjectorU, exact f64 (CCalculation.cpp:587-589) */
+} slc_parity_planes;
+
+/* ---- life cycle ------------------------------------------------------- */
+/* replaces: CCalculation::Init allocation block (CCalculation.cpp:95-121) +
+ * CDecodeGray::SetNumDigit (CDecodeGray.cpp:36-53) + CDecodePhase::SetNumMat
+ * (CDecodePhase.cpp:119-137) */
+int slc_create(const slc_config *cfg, slc_context **out);
+/* replaces: CCalculation::ReleaseSpace (CCalculation.cpp:26-75) */
+void slc_destroy(slc_context *ctx);
+const char *slc_last_error(const slc_context *ctx);
+const char *slc_status_string(int status);
+int slc_abi_version(void);
+int slc_get_info(const slc_context *ctx, slc_info *out);
+
+/* replaces: the FileStorage read + C/P/A/B/cC/cD set-up of CCalculation::Init
+ * (CCalculation.cpp:124-166).  Row-major f64: CamMat 3x3, ProMat 3x3, R 3x3,
+ * T 3x1.  The per-pixel cC/cD LUT planes of the reference are not
+ * materialised: the kernel evaluates them from (u, v). */
+int slc_set_calibration(slc_context *ctx, const double cam[9], const double pro[9],
+                        const double R[9], const double T[3]);
+
+/* replaces: the gray2bin table CDecodeGray::Decode loads from
+ * Patterns/vGrayCode.txt (CDecodeGray.cpp:113-125): lut[grayCode] = binCode,
+ * n = 2^G entries.  Optional -- the default is the reflected binary code the
+ * shipped file holds, decoded arithmetically. */
+int slc_set_gray_lut(slc_context *ctx, const int16_t *gray2bin, int32_t n);
+
+/* ---- memory helpers --------------------------------------------------- */
+void *slc_host_alloc(size_t bytes);            /* pinned host memory */
+void slc_host_free(void *p);
+int slc_host_register(void *p, size_t bytes);  /* pin caller-owned memory */
+int slc_host_unregister(void *p);
+void *slc_device_alloc(slc_context *ctx, size_t bytes);
+void slc_device_free(slc_context *ctx, void *p);
+int slc_copy_to_device(slc_context *ctx, void *dst, const void *src, size_t bytes);
+int slc_copy_to_host(slc_context *ctx, void *dst, const void *src, size_t bytes);
+int slc_synchronize(slc_context *ctx);
+
+/* ---- the hot path ----------------------------------------------------- */
+/* replaces: CCalculation::CalculateFirst's compute, i.e. FillFirstProjectorU
+ * (CCalculation.cpp:525-592, with CDecodeGray::Decode CDecodeGray.cpp:108-204
+ * and CDecodePhase::Decode CDecodePhase.cpp:48-96 inside) + FillCoordinate(0)
+ * (CCalculation.cpp:666-771), for n_stacks independent frame sets, as ONE
+ * fused kernel launch.  All pointers are DEVICE pointers; cuda_stream is a
+ * cudaStream_t passed as void* (NULL = the context's own stream).
+ * Asynchronous with respect to the host. */
+int slc_reconstruct_device(slc_context *ctx, const uint8_t *d_stack, int32_t n_stacks,
+                           float *d_xyzw, uint8_t *d_mask,
+                           const slc_parity_planes *d_parity, void *cuda_stream);
+
+/* Same computation with HOST buffers: upload, kernel, download, synchronous.
+ * n_stacks may exceed max_batch; the call then pipelines chunks over the
+ * context's stream slots (copy-in / compute / copy-out overlapped).  Host
+ * buffers should be pinned (slc_host_alloc / slc_host_register) for the
+ * copies to overlap. */
+int slc_reconstruct_host(slc_context *ctx, const uint8_t *h_stack, int32_t n_stacks,
+                         float *h_xyzw, uint8_t *h_mask,
+                         const slc_parity_planes *h_parity);
+
+/* Explicit double-buffering: start upload+kernel+download of up to max_batch
+ * stacks on a slot, return immediately; slc_wait blocks until that slot's
+ * results are in the host buffers. */
+int slc_submit_host(slc_context *ctx, int32_t slot, const uint8_t *h_stack, int32_t n_stacks,
+                    float *h_xyzw, uint8_t *h_mask);
+int slc_wait(slc_context *ctx, int32_t slot);
+
+/* ---- the decoder objects on their own --------------------------------- */
+/* replaces: CDecodeGray::Decode + GetResult (CDecodeGray.cpp:108-147): 2G
+ * planes -> CV_64FC1 plane of left-edge projector columns; kbin optional. */
+int slc_decode_gray_host(slc_context *ctx, const uint8_t *h_gray_planes,
+                         double *h_gray_val, int16_t *h_kbin);
+/* replaces: CDecodePhase::Decode + GetResult (CDecodePhase.cpp:83-104): N
+ * planes -> CV_64FC1 plane of in-period offsets in (0, T]; mod_ok optional. */
+int slc_decode_phase_host(slc_context *ctx, const uint8_t *h_phase_planes,
+                          double *h_phase_pix, uint8_t *h_mod_ok);
+/* replaces: CCalculation::FillCoordinate(i) for an arbitrary ProjectorU plane
+ * (CCalculation.cpp:666-771), the step the dynamic-frame mode re-uses. */
+int slc_triangulate_host(slc_context *ctx, const double *h_proj_u,
+                         float *h_xyzw, uint8_t *h_mask);
+
+/* ---- measurement ------------------------------------------------------ */
+/* Launch the fused kernel `iters` times back to back on the context stream and
+ * report the average duration per launch in milliseconds, measured with CUDA
+ * events recorded on that same stream. */
+int slc_time_reconstruct_device(slc_context *ctx, const uint8_t *d_stack, int32_t n_stacks,
+                                float *d_xyzw, uint8_t *d_mask, int32_t iters,
+                                float *ms_per_launch);
+/* Number of kernels this library has launched on this context so far. */
+int64_t slc_launch_count(const slc_context *ctx);
+/* Tuning hook for bench/tests: pixels owned by one thread of the vector kernel
+ * (4, 8 or 16; process-wide).  Results do not depend on it. */
+void slc_tune_pixels_per_thread(int32_t pxt);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SLCALC_B200_H_ */

@@ -1,0 +1,309 @@
+"""ctypes binding of libslcalc_b200.so (include/slcalc_b200.h).
+
+Host plumbing only.  There is no CPU fallback: if the shared library is not
+built, or no CUDA device is present, the calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import re
+
+import numpy as np
+
+from .configs import StackConfig
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "lib", "libslcalc_b200.so")
+HEADER_PATH = os.path.join(os.path.dirname(_PKG), "include", "slcalc_b200.h")
+
+SLC_OK = 0
+SLC_ERR_INVALID_ARG = 1
+SLC_ERR_NOT_INITIALISED = 2
+SLC_ERR_CUDA = 3
+SLC_ERR_NO_DEVICE = 4
+SLC_ERR_OUT_OF_MEMORY = 5
+SLC_ERR_STATE = 6
+
+SLC_FLAG_Z_FP64 = 1 << 0
+SLC_FLAG_SCALAR_KERNEL = 1 << 1
+
+
+class SlcError(RuntimeError):
+    def __init__(self, status: int, message: str):
+        super().__init__(f"slcalc_b200 status {status}: {message}")
+        self.status = status
+        self.message = message
+
+
+class SlcConfig(C.Structure):
+    _fields_ = [
+        ("width", C.c_int32), ("height", C.c_int32), ("projector_width", C.c_int32),
+        ("gray_digits", C.c_int32), ("phase_steps", C.c_int32),
+        ("fov_min", C.c_double), ("fov_max", C.c_double),
+        ("modulation_min", C.c_float), ("flags", C.c_uint32),
+        ("device", C.c_int32), ("max_batch", C.c_int32), ("num_slots", C.c_int32),
+    ]
+
+
+class SlcInfo(C.Structure):
+    _fields_ = [
+        ("planes", C.c_int32), ("gray_period", C.c_int32), ("phase_period", C.c_int32), ("sm_count", C.c_int32),
+        ("pixels", C.c_int64), ("stack_bytes", C.c_int64), ("xyzw_bytes", C.c_int64), ("mask_bytes", C.c_int64),
+        ("kernel_variant", C.c_int32), ("kernel_regs", C.c_int32), ("kernel_block", C.c_int32),
+        ("kernel_smem", C.c_int32),
+    ]
+
+
+class SlcParityPlanes(C.Structure):
+    _fields_ = [("kbin", C.c_void_p), ("corr", C.c_void_p), ("phase_pix", C.c_void_p), ("proj_u", C.c_void_p)]
+
+
+def declared_symbols() -> list[str]:
+    """Every function name include/slcalc_b200.h declares."""
+    with open(HEADER_PATH, "r", encoding="utf-8") as f:
+        text = f.read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(slc_[a-z0-9_]+)\s*\(", text)))
+
+
+_lib = None
+
+
+def load_library():
+    """dlopen the CUDA library; raises if it has not been built (no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise FileNotFoundError(
+            f"{LIB_PATH} is missing: build it with __graft_entry__.build() or "
+            "`make -C structured_light_calculation_b200` (there is no CPU fallback)")
+    L = C.CDLL(LIB_PATH)
+    vp, i32 = C.c_void_p, C.c_int32
+    L.slc_create.argtypes = [C.POINTER(SlcConfig), C.POINTER(vp)]
+    L.slc_destroy.argtypes = [vp]
+    L.slc_destroy.restype = None
+    L.slc_last_error.argtypes = [vp]
+    L.slc_last_error.restype = C.c_char_p
+    L.slc_status_string.argtypes = [C.c_int]
+    L.slc_status_string.restype = C.c_char_p
+    L.slc_get_info.argtypes = [vp, C.POINTER(SlcInfo)]
+    L.slc_set_calibration.argtypes = [vp, vp, vp, vp, vp]
+    L.slc_set_gray_lut.argtypes = [vp, vp, i32]
+    L.slc_host_alloc.argtypes = [C.c_size_t]
+    L.slc_host_alloc.restype = vp
+    L.slc_host_free.argtypes = [vp]
+    L.slc_host_free.restype = None
+    L.slc_host_register.argtypes = [vp, C.c_size_t]
+    L.slc_host_unregister.argtypes = [vp]
+    L.slc_device_alloc.argtypes = [vp, C.c_size_t]
+    L.slc_device_alloc.restype = vp
+    L.slc_device_free.argtypes = [vp, vp]
+    L.slc_device_free.restype = None
+    L.slc_copy_to_device.argtypes = [vp, vp, vp, C.c_size_t]
+    L.slc_copy_to_host.argtypes = [vp, vp, vp, C.c_size_t]
+    L.slc_synchronize.argtypes = [vp]
+    L.slc_reconstruct_device.argtypes = [vp, vp, i32, vp, vp, C.POINTER(SlcParityPlanes), vp]
+    L.slc_reconstruct_host.argtypes = [vp, vp, i32, vp, vp, C.POINTER(SlcParityPlanes)]
+    L.slc_submit_host.argtypes = [vp, i32, vp, i32, vp, vp]
+    L.slc_wait.argtypes = [vp, i32]
+    L.slc_decode_gray_host.argtypes = [vp, vp, vp, vp]
+    L.slc_decode_phase_host.argtypes = [vp, vp, vp, vp]
+    L.slc_triangulate_host.argtypes = [vp, vp, vp, vp]
+    L.slc_time_reconstruct_device.argtypes = [vp, vp, i32, vp, vp, i32, C.POINTER(C.c_float)]
+    L.slc_launch_count.argtypes = [vp]
+    L.slc_launch_count.restype = C.c_int64
+    L.slc_tune_pixels_per_thread.argtypes = [i32]
+    L.slc_tune_pixels_per_thread.restype = None
+    _lib = L
+    return L
+
+
+class PinnedArray:
+    """numpy view over pinned host memory from slc_host_alloc."""
+
+    def __init__(self, shape, dtype):
+        self._lib = load_library()
+        self.shape = tuple(int(s) for s in shape)
+        self.dtype = np.dtype(dtype)
+        nbytes = int(np.prod(self.shape)) * self.dtype.itemsize
+        self.ptr = self._lib.slc_host_alloc(max(nbytes, 1))
+        if not self.ptr:
+            raise MemoryError(f"slc_host_alloc({nbytes}) failed")
+        buf = (C.c_uint8 * max(nbytes, 1)).from_address(self.ptr)
+        self.array = np.frombuffer(buf, dtype=self.dtype, count=int(np.prod(self.shape))).reshape(self.shape)
+
+    def free(self):
+        if self.ptr:
+            self.array = None
+            self._lib.slc_host_free(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if isinstance(a, PinnedArray):
+        return a.ptr
+    if isinstance(a, np.ndarray):
+        assert a.flags["C_CONTIGUOUS"]
+        return a.ctypes.data
+    return int(a)
+
+
+class Reconstructor:
+    """One slc_context: the fused decode -> unwrap -> triangulate path on one GPU."""
+
+    def __init__(self, cfg: StackConfig, device: int = 0, max_batch: int = 1, num_slots: int = 2, flags: int = 0):
+        self.lib = load_library()
+        self.cfg = cfg
+        self.max_batch = max_batch
+        c = SlcConfig(cfg.width, cfg.height, cfg.projector_width, cfg.gray_digits, cfg.phase_steps,
+                      float(cfg.fov_min), float(cfg.fov_max), float(cfg.modulation_min), flags, device,
+                      max_batch, num_slots)
+        h = C.c_void_p()
+        st = self.lib.slc_create(C.byref(c), C.byref(h))
+        if st != SLC_OK:
+            raise SlcError(st, (self.lib.slc_last_error(None) or b"").decode())
+        self.h = h
+
+    # -- helpers ---------------------------------------------------------
+    def _check(self, st: int):
+        if st != SLC_OK:
+            raise SlcError(st, (self.lib.slc_last_error(self.h) or b"").decode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.slc_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def info(self) -> SlcInfo:
+        out = SlcInfo()
+        self._check(self.lib.slc_get_info(self.h, C.byref(out)))
+        return out
+
+    def set_calibration(self, cal):
+        cam = np.ascontiguousarray(cal.cam, dtype=np.float64).reshape(9)
+        pro = np.ascontiguousarray(cal.pro, dtype=np.float64).reshape(9)
+        R = np.ascontiguousarray(cal.R, dtype=np.float64).reshape(9)
+        T = np.ascontiguousarray(cal.T, dtype=np.float64).reshape(3)
+        self._check(self.lib.slc_set_calibration(self.h, cam.ctypes.data, pro.ctypes.data, R.ctypes.data,
+                                                 T.ctypes.data))
+
+    def set_gray_lut(self, lut: np.ndarray):
+        lut = np.ascontiguousarray(lut, dtype=np.int16)
+        self._check(self.lib.slc_set_gray_lut(self.h, lut.ctypes.data, int(lut.size)))
+
+    # -- device memory ---------------------------------------------------
+    def device_alloc(self, nbytes: int) -> int:
+        p = self.lib.slc_device_alloc(self.h, nbytes)
+        if not p:
+            raise SlcError(SLC_ERR_OUT_OF_MEMORY, (self.lib.slc_last_error(self.h) or b"").decode())
+        return p
+
+    def device_free(self, p: int):
+        self.lib.slc_device_free(self.h, p)
+
+    def to_device(self, dptr: int, host, nbytes: int | None = None):
+        if nbytes is None:
+            nbytes = host.array.nbytes if isinstance(host, PinnedArray) else host.nbytes
+        self._check(self.lib.slc_copy_to_device(self.h, dptr, _ptr(host), nbytes))
+
+    def to_host(self, host, dptr: int, nbytes: int | None = None):
+        if nbytes is None:
+            nbytes = host.array.nbytes if isinstance(host, PinnedArray) else host.nbytes
+        self._check(self.lib.slc_copy_to_host(self.h, _ptr(host), dptr, nbytes))
+
+    def synchronize(self):
+        self._check(self.lib.slc_synchronize(self.h))
+
+    # -- hot path --------------------------------------------------------
+    def reconstruct_device(self, d_stack: int, n_stacks: int, d_xyzw: int, d_mask: int, d_parity=None,
+                           stream: int | None = None):
+        par = C.byref(d_parity) if d_parity is not None else None
+        self._check(self.lib.slc_reconstruct_device(self.h, d_stack, n_stacks, d_xyzw, d_mask, par, stream))
+
+    def reconstruct(self, stacks, parity: bool = False) -> dict:
+        """Host buffers in, host buffers out (numpy or PinnedArray): the public call."""
+        arr = stacks.array if isinstance(stacks, PinnedArray) else np.ascontiguousarray(stacks, dtype=np.uint8)
+        cfg = self.cfg
+        if arr.ndim == 3:
+            arr = arr[None]
+        n = arr.shape[0]
+        assert arr.shape[1:] == (cfg.planes, cfg.height, cfg.width), arr.shape
+        out = {
+            "xyzw": np.empty((n, cfg.height, cfg.width, 4), np.float32),
+            "mask": np.empty((n, cfg.height, cfg.width), np.uint8),
+        }
+        par = None
+        if parity:
+            out["kbin"] = np.empty((n, cfg.height, cfg.width), np.int16)
+            out["corr"] = np.empty((n, cfg.height, cfg.width), np.int8)
+            out["phase_pix"] = np.empty((n, cfg.height, cfg.width), np.float32)
+            out["proj_u"] = np.empty((n, cfg.height, cfg.width), np.float64)
+            par = SlcParityPlanes(out["kbin"].ctypes.data, out["corr"].ctypes.data,
+                                  out["phase_pix"].ctypes.data, out["proj_u"].ctypes.data)
+        self._check(self.lib.slc_reconstruct_host(self.h, arr.ctypes.data, n, out["xyzw"].ctypes.data,
+                                                  out["mask"].ctypes.data, C.byref(par) if par else None))
+        return out
+
+    def reconstruct_into(self, h_stack, n_stacks: int, h_xyzw, h_mask):
+        """Host path into caller-provided (ideally pinned) buffers."""
+        self._check(self.lib.slc_reconstruct_host(self.h, _ptr(h_stack), n_stacks, _ptr(h_xyzw), _ptr(h_mask), None))
+
+    def submit(self, slot: int, h_stack, n_stacks: int, h_xyzw, h_mask):
+        self._check(self.lib.slc_submit_host(self.h, slot, _ptr(h_stack), n_stacks, _ptr(h_xyzw), _ptr(h_mask)))
+
+    def wait(self, slot: int):
+        self._check(self.lib.slc_wait(self.h, slot))
+
+    # -- decoder objects ---------------------------------------------------
+    def decode_gray(self, gray_planes: np.ndarray):
+        cfg = self.cfg
+        gray_planes = np.ascontiguousarray(gray_planes, dtype=np.uint8)
+        assert gray_planes.shape == (2 * cfg.gray_digits, cfg.height, cfg.width)
+        val = np.empty((cfg.height, cfg.width), np.float64)
+        kbin = np.empty((cfg.height, cfg.width), np.int16)
+        self._check(self.lib.slc_decode_gray_host(self.h, gray_planes.ctypes.data, val.ctypes.data, kbin.ctypes.data))
+        return val, kbin
+
+    def decode_phase(self, phase_planes: np.ndarray):
+        cfg = self.cfg
+        phase_planes = np.ascontiguousarray(phase_planes, dtype=np.uint8)
+        assert phase_planes.shape == (cfg.phase_steps, cfg.height, cfg.width)
+        pix = np.empty((cfg.height, cfg.width), np.float64)
+        mod = np.empty((cfg.height, cfg.width), np.uint8)
+        self._check(self.lib.slc_decode_phase_host(self.h, phase_planes.ctypes.data, pix.ctypes.data, mod.ctypes.data))
+        return pix, mod
+
+    def triangulate(self, proj_u: np.ndarray):
+        cfg = self.cfg
+        proj_u = np.ascontiguousarray(proj_u, dtype=np.float64)
+        assert proj_u.shape == (cfg.height, cfg.width)
+        xyzw = np.empty((cfg.height, cfg.width, 4), np.float32)
+        mask = np.empty((cfg.height, cfg.width), np.uint8)
+        self._check(self.lib.slc_triangulate_host(self.h, proj_u.ctypes.data, xyzw.ctypes.data, mask.ctypes.data))
+        return xyzw, mask
+
+    # -- measurement -------------------------------------------------------
+    def time_device(self, d_stack: int, n_stacks: int, d_xyzw: int, d_mask: int, iters: int) -> float:
+        ms = C.c_float()
+        self._check(self.lib.slc_time_reconstruct_device(self.h, d_stack, n_stacks, d_xyzw, d_mask, iters,
+                                                         C.byref(ms)))
+        return float(ms.value)
+
+    def launch_count(self) -> int:
+        return int(self.lib.slc_launch_count(self.h))

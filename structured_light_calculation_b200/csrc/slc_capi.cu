@@ -1,0 +1,656 @@
+// slc_capi.cu -- the C ABI of include/slcalc_b200.h: context, calibration
+// set-up, device/pinned memory, stream slots, and the launches.
+//
+// Host-side f64 arithmetic that must reproduce CCalculation::Init
+// (CCalculation.cpp:135-166) is written one operation per statement and the
+// file is compiled with -ffp-contract=off, so it matches an SSE2 /fp:precise
+// build of the reference operation for operation.
+#include "../../include/slcalc_b200.h"
+#include "slc_kernels.h"
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+using slc::KParams;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct Slot {
+    cudaStream_t stream = nullptr;
+    uint8_t* d_stack = nullptr;
+    float* d_xyzw = nullptr;
+    uint8_t* d_mask = nullptr;
+    // parity planes, allocated on first use
+    int16_t* d_kbin = nullptr;
+    int8_t* d_corr = nullptr;
+    float* d_pix = nullptr;
+    double* d_proj_u = nullptr;
+    bool busy = false;
+};
+
+}  // namespace
+
+struct slc_context {
+    slc_config cfg{};
+    int gp = 0, T = 0;
+    int sm_count = 0;
+    bool calibrated = false;
+    KParams kp{};            // geometry + calibration constants, buffers unset
+    int16_t* d_lut = nullptr;
+    cudaStream_t stream = nullptr;
+    std::vector<Slot> slots;
+    // scratch for the stand-alone decoder entry points
+    void* d_scratch_in = nullptr;  size_t scratch_in_bytes = 0;
+    void* d_scratch_out = nullptr; size_t scratch_out_bytes = 0;
+    void* d_scratch_aux = nullptr; size_t scratch_aux_bytes = 0;
+    long long launches = 0;
+    std::string err;
+};
+
+namespace {
+
+int fail(slc_context* ctx, int status, const char* fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->err = buf; else g_create_error = buf;
+    return status;
+}
+
+#define SLC_CUDA(ctx, call)                                                                     \
+    do {                                                                                        \
+        cudaError_t e__ = (call);                                                               \
+        if (e__ != cudaSuccess)                                                                 \
+            return fail(ctx, e__ == cudaErrorMemoryAllocation ? SLC_ERR_OUT_OF_MEMORY : SLC_ERR_CUDA, \
+                        "%s failed: %s", #call, cudaGetErrorString(e__));                       \
+    } while (0)
+
+size_t stack_bytes(const slc_context* c) { return (size_t)c->kp.P * (size_t)c->kp.npx; }
+size_t xyzw_bytes(const slc_context* c) { return 16 * (size_t)c->kp.npx; }
+size_t mask_bytes(const slc_context* c) { return (size_t)c->kp.npx; }
+
+int ensure_scratch(slc_context* ctx, void** p, size_t* have, size_t want)
+{
+    if (*have >= want) return SLC_OK;
+    if (*p) cudaFree(*p);
+    *p = nullptr; *have = 0;
+    SLC_CUDA(ctx, cudaMalloc(p, want));
+    *have = want;
+    return SLC_OK;
+}
+
+int ensure_parity(slc_context* ctx, Slot& s, const slc_parity_planes* want)
+{
+    const size_t n = (size_t)ctx->cfg.max_batch * (size_t)ctx->kp.npx;
+    if (want->kbin && !s.d_kbin) SLC_CUDA(ctx, cudaMalloc(&s.d_kbin, n * sizeof(int16_t)));
+    if (want->corr && !s.d_corr) SLC_CUDA(ctx, cudaMalloc(&s.d_corr, n * sizeof(int8_t)));
+    if (want->phase_pix && !s.d_pix) SLC_CUDA(ctx, cudaMalloc(&s.d_pix, n * sizeof(float)));
+    if (want->proj_u && !s.d_proj_u) SLC_CUDA(ctx, cudaMalloc(&s.d_proj_u, n * sizeof(double)));
+    return SLC_OK;
+}
+
+int launch(slc_context* ctx, const uint8_t* d_stack, int n_stacks, float* d_xyzw, uint8_t* d_mask,
+           const slc_parity_planes* par, cudaStream_t stream)
+{
+    KParams p = ctx->kp;
+    p.n_stacks = n_stacks;
+    p.stack = d_stack;
+    p.xyzw = reinterpret_cast<float4*>(d_xyzw);
+    p.mask = d_mask;
+    p.kbin = par ? par->kbin : nullptr;
+    p.corr = par ? par->corr : nullptr;
+    p.phase_pix = par ? par->phase_pix : nullptr;
+    p.proj_u = par ? par->proj_u : nullptr;
+    p.lut = ctx->d_lut;
+    const bool scalar = (ctx->cfg.flags & SLC_FLAG_SCALAR_KERNEL) != 0;
+    SLC_CUDA(ctx, slc::launch_reconstruct(p, scalar, stream, nullptr));
+    ctx->launches++;
+    return SLC_OK;
+}
+
+int check_ready(slc_context* ctx, const void* a, const void* b, const void* c, int n_stacks)
+{
+    if (!ctx) return SLC_ERR_INVALID_ARG;
+    if (!ctx->calibrated)
+        return fail(ctx, SLC_ERR_NOT_INITIALISED, "calibration not set: call slc_set_calibration first");
+    if (!a || !b || !c) return fail(ctx, SLC_ERR_INVALID_ARG, "NULL buffer");
+    if (n_stacks < 0) return fail(ctx, SLC_ERR_INVALID_ARG, "n_stacks < 0");
+    return SLC_OK;
+}
+
+// Enqueue upload + kernel + download of one chunk on a slot.
+int enqueue_chunk(slc_context* ctx, Slot& s, const uint8_t* h_stack, int n, float* h_xyzw, uint8_t* h_mask,
+                  const slc_parity_planes* h_par, size_t par_offset_px)
+{
+    const size_t npx = (size_t)ctx->kp.npx;
+    SLC_CUDA(ctx, cudaMemcpyAsync(s.d_stack, h_stack, stack_bytes(ctx) * n, cudaMemcpyHostToDevice, s.stream));
+    slc_parity_planes dpar{};
+    const slc_parity_planes* dparp = nullptr;
+    if (h_par && (h_par->kbin || h_par->corr || h_par->phase_pix || h_par->proj_u)) {
+        int rc = ensure_parity(ctx, s, h_par);
+        if (rc != SLC_OK) return rc;
+        dpar.kbin = h_par->kbin ? s.d_kbin : nullptr;
+        dpar.corr = h_par->corr ? s.d_corr : nullptr;
+        dpar.phase_pix = h_par->phase_pix ? s.d_pix : nullptr;
+        dpar.proj_u = h_par->proj_u ? s.d_proj_u : nullptr;
+        dparp = &dpar;
+    }
+    int rc = launch(ctx, s.d_stack, n, s.d_xyzw, s.d_mask, dparp, s.stream);
+    if (rc != SLC_OK) return rc;
+    SLC_CUDA(ctx, cudaMemcpyAsync(h_xyzw, s.d_xyzw, xyzw_bytes(ctx) * n, cudaMemcpyDeviceToHost, s.stream));
+    SLC_CUDA(ctx, cudaMemcpyAsync(h_mask, s.d_mask, mask_bytes(ctx) * n, cudaMemcpyDeviceToHost, s.stream));
+    if (dparp) {
+        const size_t cnt = npx * n;
+        if (dpar.kbin)
+            SLC_CUDA(ctx, cudaMemcpyAsync(h_par->kbin + par_offset_px, dpar.kbin, cnt * sizeof(int16_t),
+                                          cudaMemcpyDeviceToHost, s.stream));
+        if (dpar.corr)
+            SLC_CUDA(ctx, cudaMemcpyAsync(h_par->corr + par_offset_px, dpar.corr, cnt * sizeof(int8_t),
+                                          cudaMemcpyDeviceToHost, s.stream));
+        if (dpar.phase_pix)
+            SLC_CUDA(ctx, cudaMemcpyAsync(h_par->phase_pix + par_offset_px, dpar.phase_pix, cnt * sizeof(float),
+                                          cudaMemcpyDeviceToHost, s.stream));
+        if (dpar.proj_u)
+            SLC_CUDA(ctx, cudaMemcpyAsync(h_par->proj_u + par_offset_px, dpar.proj_u, cnt * sizeof(double),
+                                          cudaMemcpyDeviceToHost, s.stream));
+    }
+    s.busy = true;
+    return SLC_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int slc_abi_version(void) { return SLC_ABI_VERSION; }
+
+const char* slc_status_string(int status)
+{
+    switch (status) {
+    case SLC_OK: return "ok";
+    case SLC_ERR_INVALID_ARG: return "invalid argument";
+    case SLC_ERR_NOT_INITIALISED: return "not initialised";
+    case SLC_ERR_CUDA: return "CUDA error";
+    case SLC_ERR_NO_DEVICE: return "no CUDA device (there is no CPU path)";
+    case SLC_ERR_OUT_OF_MEMORY: return "out of memory";
+    case SLC_ERR_STATE: return "invalid state";
+    default: return "unknown status";
+    }
+}
+
+const char* slc_last_error(const slc_context* ctx)
+{
+    return ctx ? ctx->err.c_str() : g_create_error.c_str();
+}
+
+int slc_create(const slc_config* cfg, slc_context** out)
+{
+    if (!cfg || !out) return fail(nullptr, SLC_ERR_INVALID_ARG, "slc_create: NULL argument");
+    *out = nullptr;
+    if (cfg->width <= 0 || cfg->height <= 0)
+        return fail(nullptr, SLC_ERR_INVALID_ARG, "camera size %dx%d is not positive", cfg->width, cfg->height);
+    if ((long long)cfg->width * cfg->height > 0x7fffffffLL)
+        return fail(nullptr, SLC_ERR_INVALID_ARG, "camera size %dx%d exceeds 2^31 pixels", cfg->width, cfg->height);
+    // CDecodeGray::SetNumDigit accepts 1..16 (CDecodeGray.cpp:39)
+    if (cfg->gray_digits <= 0 || cfg->gray_digits > 16)
+        return fail(nullptr, SLC_ERR_INVALID_ARG, "gray_digits %d outside 1..16", cfg->gray_digits);
+    // CDecodePhase::SetNumMat rejects numMat <= 0 (CDecodePhase.cpp:122); phase shifting needs >= 3
+    if (cfg->phase_steps < 3)
+        return fail(nullptr, SLC_ERR_INVALID_ARG, "phase_steps %d < 3", cfg->phase_steps);
+    const bool even = (cfg->phase_steps & 1) == 0;
+    if ((even && cfg->phase_steps > 2 * slc::kMaxPhaseTable) || (!even && cfg->phase_steps > slc::kMaxPhaseTable))
+        return fail(nullptr, SLC_ERR_INVALID_ARG, "phase_steps %d too large (max %d even / %d odd)",
+                    cfg->phase_steps, 2 * slc::kMaxPhaseTable, slc::kMaxPhaseTable);
+    const int gp = cfg->projector_width / (1 << cfg->gray_digits);          // CDecodeGray.cpp:183
+    const int T = cfg->projector_width / (1 << (cfg->gray_digits - 1));     // CCalculation.cpp:550
+    if (cfg->projector_width <= 0 || gp < 1)
+        return fail(nullptr, SLC_ERR_INVALID_ARG,
+                    "projector_width %d gives a Gray stripe of %d px for %d digits (needs >= 1; the reference "
+                    "would divide by zero at CCalculation.cpp:570)", cfg->projector_width, gp, cfg->gray_digits);
+    if (!(cfg->fov_min <= cfg->fov_max))
+        return fail(nullptr, SLC_ERR_INVALID_ARG, "fov_min > fov_max");
+    if (cfg->max_batch < 1 || cfg->num_slots < 1 || cfg->num_slots > 8)
+        return fail(nullptr, SLC_ERR_INVALID_ARG, "max_batch must be >= 1 and num_slots in 1..8");
+    if (cfg->modulation_min < 0.f || !(cfg->modulation_min == cfg->modulation_min))
+        return fail(nullptr, SLC_ERR_INVALID_ARG, "modulation_min must be >= 0");
+
+    int n_dev = 0;
+    cudaError_t e = cudaGetDeviceCount(&n_dev);
+    if (e != cudaSuccess || n_dev <= 0)
+        return fail(nullptr, SLC_ERR_NO_DEVICE, "no CUDA device available (%s); this library has no CPU path",
+                    e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    if (cfg->device < 0 || cfg->device >= n_dev)
+        return fail(nullptr, SLC_ERR_INVALID_ARG, "device %d out of range (0..%d)", cfg->device, n_dev - 1);
+
+    slc_context* ctx = new (std::nothrow) slc_context();
+    if (!ctx) return fail(nullptr, SLC_ERR_OUT_OF_MEMORY, "host allocation failed");
+    ctx->cfg = *cfg;
+    ctx->gp = gp;
+    ctx->T = T;
+    KParams& p = ctx->kp;
+    p.W = cfg->width; p.H = cfg->height;
+    p.G = cfg->gray_digits; p.N = cfg->phase_steps; p.P = 2 * p.G + p.N;
+    p.npx = (long long)p.W * p.H;
+    p.gp = gp; p.T = T;
+    p.Tf = (float)T; p.T075 = (float)(0.75 * T); p.T025 = (float)(0.25 * T); p.halfT = (float)(0.5 * T);
+    p.gpf = (float)gp;
+    // [EXT] phase tables and modulation threshold; same expressions as the oracle
+    const int nk = (p.N == 4) ? 0 : (even ? p.N / 2 : p.N);
+    for (int k = 0; k < slc::kMaxPhaseTable; k++) { p.ck[k] = 0.f; p.sk[k] = 0.f; }
+    for (int k = 0; k < nk; k++) {
+        double c = std::cos(2.0 * M_PI * (double)k / (double)p.N);
+        double s = std::sin(2.0 * M_PI * (double)k / (double)p.N);
+        if (std::fabs(c) < 1e-9) c = 0.0;
+        if (std::fabs(s) < 1e-9) s = 0.0;
+        p.ck[k] = (float)c;
+        p.sk[k] = (float)s;
+    }
+    {
+        const double scale = p.N == 4 ? 1.0 : 0.5 * (double)p.N;
+        const double t = (double)cfg->modulation_min * scale;
+        p.thr2 = (float)(t * t);
+        p.use_mod = cfg->modulation_min > 0.f ? 1 : 0;
+    }
+    p.z_fp64 = (cfg->flags & SLC_FLAG_Z_FP64) ? 1 : 0;
+    p.fov_min = cfg->fov_min; p.fov_max = cfg->fov_max;
+    p.fov_min32 = (float)cfg->fov_min; p.fov_max32 = (float)cfg->fov_max;
+    {
+        const double band = 1e-3 * std::fmax(std::fmax(std::fabs(cfg->fov_min), std::fabs(cfg->fov_max)), 1e-30);
+        p.guard_lo_min = (float)(cfg->fov_min - band); p.guard_hi_min = (float)(cfg->fov_min + band);
+        p.guard_lo_max = (float)(cfg->fov_max - band); p.guard_hi_max = (float)(cfg->fov_max + band);
+    }
+
+#define SLC_CREATE_CUDA(call)                                                                      \
+    do {                                                                                           \
+        cudaError_t e__ = (call);                                                                  \
+        if (e__ != cudaSuccess) {                                                                  \
+            int st__ = fail(nullptr, e__ == cudaErrorMemoryAllocation ? SLC_ERR_OUT_OF_MEMORY : SLC_ERR_CUDA, \
+                            "%s failed: %s", #call, cudaGetErrorString(e__));                      \
+            slc_destroy(ctx);                                                                      \
+            return st__;                                                                           \
+        }                                                                                          \
+    } while (0)
+
+    SLC_CREATE_CUDA(cudaSetDevice(cfg->device));
+    cudaDeviceProp prop;
+    SLC_CREATE_CUDA(cudaGetDeviceProperties(&prop, cfg->device));
+    ctx->sm_count = prop.multiProcessorCount;
+    SLC_CREATE_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    ctx->slots.resize(cfg->num_slots);
+    for (Slot& s : ctx->slots) {
+        SLC_CREATE_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+        SLC_CREATE_CUDA(cudaMalloc(&s.d_stack, stack_bytes(ctx) * cfg->max_batch));
+        SLC_CREATE_CUDA(cudaMalloc(&s.d_xyzw, xyzw_bytes(ctx) * cfg->max_batch));
+        SLC_CREATE_CUDA(cudaMalloc(&s.d_mask, mask_bytes(ctx) * cfg->max_batch));
+    }
+#undef SLC_CREATE_CUDA
+    *out = ctx;
+    return SLC_OK;
+}
+
+void slc_destroy(slc_context* ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->cfg.device);
+    for (Slot& s : ctx->slots) {
+        if (s.stream) { cudaStreamSynchronize(s.stream); cudaStreamDestroy(s.stream); }
+        cudaFree(s.d_stack); cudaFree(s.d_xyzw); cudaFree(s.d_mask);
+        cudaFree(s.d_kbin); cudaFree(s.d_corr); cudaFree(s.d_pix); cudaFree(s.d_proj_u);
+    }
+    if (ctx->stream) { cudaStreamSynchronize(ctx->stream); cudaStreamDestroy(ctx->stream); }
+    cudaFree(ctx->d_lut);
+    cudaFree(ctx->d_scratch_in); cudaFree(ctx->d_scratch_out); cudaFree(ctx->d_scratch_aux);
+    delete ctx;
+}
+
+int slc_get_info(const slc_context* cctx, slc_info* out)
+{
+    slc_context* ctx = const_cast<slc_context*>(cctx);
+    if (!ctx || !out) return SLC_ERR_INVALID_ARG;
+    std::memset(out, 0, sizeof(*out));
+    out->planes = ctx->kp.P;
+    out->gray_period = ctx->gp;
+    out->phase_period = ctx->T;
+    out->sm_count = ctx->sm_count;
+    out->pixels = ctx->kp.npx;
+    out->stack_bytes = (int64_t)stack_bytes(ctx);
+    out->xyzw_bytes = (int64_t)xyzw_bytes(ctx);
+    out->mask_bytes = (int64_t)mask_bytes(ctx);
+    SLC_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+    slc::LaunchInfo li;
+    li.query_only = true;
+    KParams p = ctx->kp;
+    p.n_stacks = 1;
+    p.stack = ctx->slots[0].d_stack;
+    p.xyzw = reinterpret_cast<float4*>(ctx->slots[0].d_xyzw);
+    p.mask = ctx->slots[0].d_mask;
+    p.lut = ctx->d_lut;
+    SLC_CUDA(ctx, slc::launch_reconstruct(p, (ctx->cfg.flags & SLC_FLAG_SCALAR_KERNEL) != 0, nullptr, &li));
+    out->kernel_variant = li.variant;
+    out->kernel_regs = li.regs;
+    out->kernel_block = li.block;
+    out->kernel_smem = li.smem;
+    return SLC_OK;
+}
+
+int slc_set_calibration(slc_context* ctx, const double cam[9], const double pro[9], const double R[9],
+                        const double T[3])
+{
+    if (!ctx) return SLC_ERR_INVALID_ARG;
+    if (!cam || !pro || !R || !T) return fail(ctx, SLC_ERR_INVALID_ARG, "NULL calibration matrix");
+    for (int i = 0; i < 9; i++)
+        if (!std::isfinite(cam[i]) || !std::isfinite(pro[i]) || !std::isfinite(R[i]))
+            return fail(ctx, SLC_ERR_INVALID_ARG, "calibration contains a non-finite value");
+    for (int i = 0; i < 3; i++)
+        if (!std::isfinite(T[i])) return fail(ctx, SLC_ERR_INVALID_ARG, "calibration contains a non-finite value");
+    if (cam[0] == 0.0 || cam[4] == 0.0) return fail(ctx, SLC_ERR_INVALID_ARG, "camera focal length is zero");
+
+    // P = ProMat * [R | T]  (CCalculation.cpp:141-145), accumulated k = 0,1,2
+    double RT[12], P[12];
+    for (int r = 0; r < 3; r++) {
+        for (int c = 0; c < 3; c++) RT[r * 4 + c] = R[r * 3 + c];
+        RT[r * 4 + 3] = T[r];
+    }
+    for (int r = 0; r < 3; r++)
+        for (int c = 0; c < 4; c++) {
+            double s = 0.0;
+            for (int k = 0; k < 3; k++) {
+                const double prod = pro[r * 3 + k] * RT[k * 4 + c];
+                s = s + prod;
+            }
+            P[r * 4 + c] = s;
+        }
+    KParams& p = ctx->kp;
+    const double fu = cam[0], fv = cam[4], cu = cam[2], cv = cam[5];
+    const double fufv = fu * fv;
+    p.fu = fu; p.fv = fv; p.cu = cu; p.cv = cv;
+    p.A = fufv * P[3];        // :151
+    p.B = fufv * P[11];       // :152
+    p.P00 = P[0]; p.P01 = P[1]; p.fufvP02 = fufv * P[2];     // :159-161
+    p.P20 = P[8]; p.P21 = P[9]; p.fufvP22 = fufv * P[10];    // :162-164
+
+    // f32 coefficients of the same rational map, divided through by fu*fv:
+    // C(u,v) = fv*P00*(u-cu) + fu*P01*(v-cv) + fu*fv*P02, D likewise with row 2.
+    const double s = 1.0 / fufv;
+    const double au = fv * P[0], av = fu * P[1], a0 = fufv * P[2];
+    const double bu = fv * P[8], bv = fu * P[9], b0 = fufv * P[10];
+    p.A32 = (float)(p.A * s); p.B32 = (float)(p.B * s);
+    p.c0 = (float)((a0 - au * cu - av * cv) * s); p.cu1 = (float)(au * s); p.cv1 = (float)(av * s);
+    p.d0 = (float)((b0 - bu * cu - bv * cv) * s); p.du1 = (float)(bu * s); p.dv1 = (float)(bv * s);
+    p.c0a = (float)((std::fabs(a0) + std::fabs(au * cu) + std::fabs(av * cv)) * std::fabs(s));
+    p.cu1a = std::fabs(p.cu1); p.cv1a = std::fabs(p.cv1);
+    p.d0a = (float)((std::fabs(b0) + std::fabs(bu * cu) + std::fabs(bv * cv)) * std::fabs(s));
+    p.du1a = std::fabs(p.du1); p.dv1a = std::fabs(p.dv1);
+    p.rx1 = (float)(1.0 / fu); p.rx0 = (float)(-cu / fu);    // x = z*(u-cu)/fu  (:766)
+    p.ry1 = (float)(1.0 / fv); p.ry0 = (float)(-cv / fv);    // y = z*(v-cv)/fv  (:767)
+    ctx->calibrated = true;
+    return SLC_OK;
+}
+
+int slc_set_gray_lut(slc_context* ctx, const int16_t* lut, int32_t n)
+{
+    if (!ctx) return SLC_ERR_INVALID_ARG;
+    const int want = 1 << ctx->cfg.gray_digits;
+    if (!lut || n != want) return fail(ctx, SLC_ERR_INVALID_ARG, "gray LUT must have 2^G = %d entries", want);
+    SLC_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+    bool standard = true;
+    for (int g = 0; g < want && standard; g++) {
+        int b = g;
+        for (int sft = 1; sft < 16; sft <<= 1) b ^= b >> sft;   // inverse of bin ^ (bin >> 1)
+        standard = (lut[g] == (int16_t)b);
+    }
+    for (Slot& s : ctx->slots) SLC_CUDA(ctx, cudaStreamSynchronize(s.stream));
+    SLC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (standard) {   // the shipped Patterns/vGrayCode.txt: decode arithmetically
+        cudaFree(ctx->d_lut);
+        ctx->d_lut = nullptr;
+        return SLC_OK;
+    }
+    if (!ctx->d_lut) SLC_CUDA(ctx, cudaMalloc(&ctx->d_lut, sizeof(int16_t) * 65536));
+    SLC_CUDA(ctx, cudaMemset(ctx->d_lut, 0, sizeof(int16_t) * 65536));
+    SLC_CUDA(ctx, cudaMemcpy(ctx->d_lut, lut, sizeof(int16_t) * want, cudaMemcpyHostToDevice));
+    return SLC_OK;
+}
+
+/* ---- memory ---------------------------------------------------------- */
+void* slc_host_alloc(size_t bytes)
+{
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) return nullptr;
+    return p;
+}
+void slc_host_free(void* p) { if (p) cudaFreeHost(p); }
+int slc_host_register(void* p, size_t bytes)
+{
+    return cudaHostRegister(p, bytes, cudaHostRegisterPortable) == cudaSuccess ? SLC_OK : SLC_ERR_CUDA;
+}
+int slc_host_unregister(void* p) { return cudaHostUnregister(p) == cudaSuccess ? SLC_OK : SLC_ERR_CUDA; }
+
+void* slc_device_alloc(slc_context* ctx, size_t bytes)
+{
+    if (!ctx) return nullptr;
+    void* p = nullptr;
+    if (cudaSetDevice(ctx->cfg.device) != cudaSuccess) return nullptr;
+    cudaError_t e = cudaMalloc(&p, bytes ? bytes : 1);
+    if (e != cudaSuccess) { fail(ctx, SLC_ERR_OUT_OF_MEMORY, "cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e)); return nullptr; }
+    return p;
+}
+void slc_device_free(slc_context* ctx, void* p)
+{
+    if (!ctx || !p) return;
+    cudaSetDevice(ctx->cfg.device);
+    cudaFree(p);
+}
+int slc_copy_to_device(slc_context* ctx, void* dst, const void* src, size_t bytes)
+{
+    if (!ctx) return SLC_ERR_INVALID_ARG;
+    SLC_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+    SLC_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    SLC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SLC_OK;
+}
+int slc_copy_to_host(slc_context* ctx, void* dst, const void* src, size_t bytes)
+{
+    if (!ctx) return SLC_ERR_INVALID_ARG;
+    SLC_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+    SLC_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    SLC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SLC_OK;
+}
+int slc_synchronize(slc_context* ctx)
+{
+    if (!ctx) return SLC_ERR_INVALID_ARG;
+    SLC_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+    for (Slot& s : ctx->slots) { SLC_CUDA(ctx, cudaStreamSynchronize(s.stream)); s.busy = false; }
+    SLC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SLC_OK;
+}
+
+/* ---- hot path --------------------------------------------------------- */
+int slc_reconstruct_device(slc_context* ctx, const uint8_t* d_stack, int32_t n_stacks, float* d_xyzw,
+                           uint8_t* d_mask, const slc_parity_planes* d_parity, void* cuda_stream)
+{
+    int rc = check_ready(ctx, d_stack, d_xyzw, d_mask, n_stacks);
+    if (rc != SLC_OK) return rc;
+    if (n_stacks == 0) return SLC_OK;
+    SLC_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+    cudaStream_t st = cuda_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : ctx->stream;
+    // one launch covers up to 65535 stacks (grid.y); split beyond that
+    const size_t npx = (size_t)ctx->kp.npx;
+    for (int done = 0; done < n_stacks;) {
+        const int n = (n_stacks - done) > 65535 ? 65535 : (n_stacks - done);
+        slc_parity_planes par{};
+        if (d_parity) {
+            par.kbin = d_parity->kbin ? d_parity->kbin + (size_t)done * npx : nullptr;
+            par.corr = d_parity->corr ? d_parity->corr + (size_t)done * npx : nullptr;
+            par.phase_pix = d_parity->phase_pix ? d_parity->phase_pix + (size_t)done * npx : nullptr;
+            par.proj_u = d_parity->proj_u ? d_parity->proj_u + (size_t)done * npx : nullptr;
+        }
+        rc = launch(ctx, d_stack + (size_t)done * stack_bytes(ctx), n, d_xyzw + (size_t)done * npx * 4,
+                    d_mask + (size_t)done * npx, d_parity ? &par : nullptr, st);
+        if (rc != SLC_OK) return rc;
+        done += n;
+    }
+    return SLC_OK;
+}
+
+int slc_reconstruct_host(slc_context* ctx, const uint8_t* h_stack, int32_t n_stacks, float* h_xyzw,
+                         uint8_t* h_mask, const slc_parity_planes* h_parity)
+{
+    int rc = check_ready(ctx, h_stack, h_xyzw, h_mask, n_stacks);
+    if (rc != SLC_OK) return rc;
+    SLC_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+    const size_t npx = (size_t)ctx->kp.npx;
+    const int chunk = ctx->cfg.max_batch;
+    int slot = 0;
+    // Stream order on a slot serialises "download chunk i" before "upload chunk
+    // i + num_slots" into the same device buffers; different slots overlap.
+    for (int done = 0; done < n_stacks; done += chunk) {
+        const int n = (n_stacks - done) < chunk ? (n_stacks - done) : chunk;
+        Slot& s = ctx->slots[slot];
+        rc = enqueue_chunk(ctx, s, h_stack + (size_t)done * stack_bytes(ctx), n, h_xyzw + (size_t)done * npx * 4,
+                           h_mask + (size_t)done * npx, h_parity, (size_t)done * npx);
+        if (rc != SLC_OK) return rc;
+        slot = (slot + 1) % (int)ctx->slots.size();
+    }
+    for (Slot& s : ctx->slots) { SLC_CUDA(ctx, cudaStreamSynchronize(s.stream)); s.busy = false; }
+    return SLC_OK;
+}
+
+int slc_submit_host(slc_context* ctx, int32_t slot, const uint8_t* h_stack, int32_t n_stacks, float* h_xyzw,
+                    uint8_t* h_mask)
+{
+    int rc = check_ready(ctx, h_stack, h_xyzw, h_mask, n_stacks);
+    if (rc != SLC_OK) return rc;
+    if (slot < 0 || slot >= (int)ctx->slots.size()) return fail(ctx, SLC_ERR_INVALID_ARG, "slot %d out of range", slot);
+    if (n_stacks < 1 || n_stacks > ctx->cfg.max_batch)
+        return fail(ctx, SLC_ERR_INVALID_ARG, "n_stacks %d outside 1..max_batch (%d)", n_stacks, ctx->cfg.max_batch);
+    Slot& s = ctx->slots[slot];
+    if (s.busy) return fail(ctx, SLC_ERR_STATE, "slot %d still in flight: call slc_wait first", slot);
+    SLC_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+    return enqueue_chunk(ctx, s, h_stack, n_stacks, h_xyzw, h_mask, nullptr, 0);
+}
+
+int slc_wait(slc_context* ctx, int32_t slot)
+{
+    if (!ctx) return SLC_ERR_INVALID_ARG;
+    if (slot < 0 || slot >= (int)ctx->slots.size()) return fail(ctx, SLC_ERR_INVALID_ARG, "slot %d out of range", slot);
+    SLC_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+    SLC_CUDA(ctx, cudaStreamSynchronize(ctx->slots[slot].stream));
+    ctx->slots[slot].busy = false;
+    return SLC_OK;
+}
+
+/* ---- decoder objects -------------------------------------------------- */
+int slc_decode_gray_host(slc_context* ctx, const uint8_t* h_planes, double* h_gray_val, int16_t* h_kbin)
+{
+    if (!ctx) return SLC_ERR_INVALID_ARG;
+    if (!h_planes || !h_gray_val) return fail(ctx, SLC_ERR_INVALID_ARG, "NULL buffer");
+    SLC_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+    const size_t npx = (size_t)ctx->kp.npx;
+    const size_t in_bytes = npx * 2 * ctx->kp.G;
+    int rc = ensure_scratch(ctx, &ctx->d_scratch_in, &ctx->scratch_in_bytes, in_bytes);
+    if (rc == SLC_OK) rc = ensure_scratch(ctx, &ctx->d_scratch_out, &ctx->scratch_out_bytes, npx * sizeof(double));
+    if (rc == SLC_OK) rc = ensure_scratch(ctx, &ctx->d_scratch_aux, &ctx->scratch_aux_bytes, npx * sizeof(int16_t));
+    if (rc != SLC_OK) return rc;
+    SLC_CUDA(ctx, cudaMemcpyAsync(ctx->d_scratch_in, h_planes, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    KParams p = ctx->kp;
+    p.lut = ctx->d_lut;
+    SLC_CUDA(ctx, slc::launch_decode_gray(p, (const uint8_t*)ctx->d_scratch_in, (double*)ctx->d_scratch_out,
+                                          h_kbin ? (int16_t*)ctx->d_scratch_aux : nullptr, ctx->stream));
+    ctx->launches++;
+    SLC_CUDA(ctx, cudaMemcpyAsync(h_gray_val, ctx->d_scratch_out, npx * sizeof(double), cudaMemcpyDeviceToHost,
+                                  ctx->stream));
+    if (h_kbin)
+        SLC_CUDA(ctx, cudaMemcpyAsync(h_kbin, ctx->d_scratch_aux, npx * sizeof(int16_t), cudaMemcpyDeviceToHost,
+                                      ctx->stream));
+    SLC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SLC_OK;
+}
+
+int slc_decode_phase_host(slc_context* ctx, const uint8_t* h_planes, double* h_phase_pix, uint8_t* h_mod_ok)
+{
+    if (!ctx) return SLC_ERR_INVALID_ARG;
+    if (!h_planes || !h_phase_pix) return fail(ctx, SLC_ERR_INVALID_ARG, "NULL buffer");
+    SLC_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+    const size_t npx = (size_t)ctx->kp.npx;
+    const size_t in_bytes = npx * ctx->kp.N;
+    int rc = ensure_scratch(ctx, &ctx->d_scratch_in, &ctx->scratch_in_bytes, in_bytes);
+    if (rc == SLC_OK) rc = ensure_scratch(ctx, &ctx->d_scratch_out, &ctx->scratch_out_bytes, npx * sizeof(double));
+    if (rc == SLC_OK) rc = ensure_scratch(ctx, &ctx->d_scratch_aux, &ctx->scratch_aux_bytes, npx * sizeof(int16_t));
+    if (rc != SLC_OK) return rc;
+    SLC_CUDA(ctx, cudaMemcpyAsync(ctx->d_scratch_in, h_planes, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    SLC_CUDA(ctx, slc::launch_decode_phase(ctx->kp, (const uint8_t*)ctx->d_scratch_in, (double*)ctx->d_scratch_out,
+                                           h_mod_ok ? (uint8_t*)ctx->d_scratch_aux : nullptr, ctx->stream));
+    ctx->launches++;
+    SLC_CUDA(ctx, cudaMemcpyAsync(h_phase_pix, ctx->d_scratch_out, npx * sizeof(double), cudaMemcpyDeviceToHost,
+                                  ctx->stream));
+    if (h_mod_ok)
+        SLC_CUDA(ctx, cudaMemcpyAsync(h_mod_ok, ctx->d_scratch_aux, npx, cudaMemcpyDeviceToHost, ctx->stream));
+    SLC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SLC_OK;
+}
+
+int slc_triangulate_host(slc_context* ctx, const double* h_proj_u, float* h_xyzw, uint8_t* h_mask)
+{
+    int rc = check_ready(ctx, h_proj_u, h_xyzw, h_mask, 1);
+    if (rc != SLC_OK) return rc;
+    SLC_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+    const size_t npx = (size_t)ctx->kp.npx;
+    rc = ensure_scratch(ctx, &ctx->d_scratch_in, &ctx->scratch_in_bytes, npx * sizeof(double));
+    if (rc == SLC_OK) rc = ensure_scratch(ctx, &ctx->d_scratch_out, &ctx->scratch_out_bytes, npx * 16);
+    if (rc == SLC_OK) rc = ensure_scratch(ctx, &ctx->d_scratch_aux, &ctx->scratch_aux_bytes, npx * sizeof(int16_t));
+    if (rc != SLC_OK) return rc;
+    SLC_CUDA(ctx, cudaMemcpyAsync(ctx->d_scratch_in, h_proj_u, npx * sizeof(double), cudaMemcpyHostToDevice,
+                                  ctx->stream));
+    SLC_CUDA(ctx, slc::launch_triangulate(ctx->kp, (const double*)ctx->d_scratch_in, (float*)ctx->d_scratch_out,
+                                          (uint8_t*)ctx->d_scratch_aux, ctx->stream));
+    ctx->launches++;
+    SLC_CUDA(ctx, cudaMemcpyAsync(h_xyzw, ctx->d_scratch_out, npx * 16, cudaMemcpyDeviceToHost, ctx->stream));
+    SLC_CUDA(ctx, cudaMemcpyAsync(h_mask, ctx->d_scratch_aux, npx, cudaMemcpyDeviceToHost, ctx->stream));
+    SLC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SLC_OK;
+}
+
+/* ---- measurement ------------------------------------------------------ */
+int slc_time_reconstruct_device(slc_context* ctx, const uint8_t* d_stack, int32_t n_stacks, float* d_xyzw,
+                                uint8_t* d_mask, int32_t iters, float* ms_per_launch)
+{
+    int rc = check_ready(ctx, d_stack, d_xyzw, d_mask, n_stacks);
+    if (rc != SLC_OK) return rc;
+    if (iters < 1 || !ms_per_launch || n_stacks < 1 || n_stacks > 65535)
+        return fail(ctx, SLC_ERR_INVALID_ARG, "bad iters / n_stacks / output pointer");
+    SLC_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+    cudaEvent_t e0, e1;
+    SLC_CUDA(ctx, cudaEventCreate(&e0));
+    SLC_CUDA(ctx, cudaEventCreate(&e1));
+    SLC_CUDA(ctx, cudaEventRecord(e0, ctx->stream));
+    for (int i = 0; i < iters; i++) {
+        rc = launch(ctx, d_stack, n_stacks, d_xyzw, d_mask, nullptr, ctx->stream);
+        if (rc != SLC_OK) { cudaEventDestroy(e0); cudaEventDestroy(e1); return rc; }
+    }
+    SLC_CUDA(ctx, cudaEventRecord(e1, ctx->stream));
+    SLC_CUDA(ctx, cudaEventSynchronize(e1));
+    float ms = 0.f;
+    SLC_CUDA(ctx, cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *ms_per_launch = ms / (float)iters;
+    return SLC_OK;
+}
+
+int64_t slc_launch_count(const slc_context* ctx) { return ctx ? ctx->launches : 0; }
+
+void slc_tune_pixels_per_thread(int32_t pxt) { slc::set_default_pixels_per_thread(pxt); }
+
+}  // extern "C"

@@ -1,0 +1,499 @@
+// slc_kernels.cu -- sm_100a kernels of the DynaFrame first-frame path.
+//
+// reconstruct_vec_kernel is the product: ONE fused pass per pixel that replaces
+// the reference's six full-image loops (CDecodeGray.cpp:150-204,
+// CDecodePhase.cpp:48-80, CCalculation.cpp:562-589, 672-708, 756-771) and
+// writes no intermediates to HBM.
+//
+// Mapping.  A thread owns PXT consecutive pixels of one image row (PXT = 16, 8
+// or 4): one PXT-byte load per u8 plane, so a warp reads 32*PXT contiguous
+// bytes of every plane (whole 128 B lines).  Results are float4 per pixel; to
+// keep the stores whole-line too, each warp transposes its 32*PXT float4
+// through a private, XOR-swizzled (bank-conflict-free) shared-memory tile and
+// writes 512 contiguous bytes per store instruction.  Loads are
+// ld.global.nc.L1::no_allocate, stores st.global.cs: every
+// byte is touched exactly once.  Nothing here is a contraction, so tensor
+// cores / TMEM are not used; the bound is HBM bandwidth.
+#include "slc_kernels.h"
+
+#include <cstdio>
+
+namespace slc {
+
+namespace {
+
+constexpr int kBlock = 256;
+
+template <int PXT> struct VecLoad;
+template <> struct VecLoad<16> {
+    static __device__ __forceinline__ void load(const uint8_t* p, uint32_t (&w)[4]) {
+        const uint4 v = ld_stream_u4(p); w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
+    }
+};
+template <> struct VecLoad<8> {
+    static __device__ __forceinline__ void load(const uint8_t* p, uint32_t (&w)[2]) {
+        const uint2 v = ld_stream_u2(p); w[0] = v.x; w[1] = v.y;
+    }
+};
+template <> struct VecLoad<4> {
+    static __device__ __forceinline__ void load(const uint8_t* p, uint32_t (&w)[1]) {
+        uint32_t v;
+        asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
+        w[0] = v;
+    }
+};
+
+// XOR swizzle of the transpose tile (in float4 slots): conflict-free both for the
+// owner-major write (8 lanes, same i) and for the pixel-major read.
+template <int PXT> __device__ __forceinline__ int swizzle(int t) { return PXT == 4 ? ((t >> 1) & 3) : (t & 7); }
+
+// The fused kernel.  G_T / N_T > 0 bake the digit and step counts in (all plane
+// loops unroll and every load is issued up front); 0 means "read it from p".
+template <int PXT, int G_T, int N_T, bool PARITY>
+__global__ void __launch_bounds__(kBlock)
+reconstruct_vec_kernel(const __grid_constant__ KParams p)
+{
+    constexpr int NW = PXT / 4;  // 32-bit words (4 pixels each) per thread
+    extern __shared__ float4 s_tile[];
+
+    const int G = G_T > 0 ? G_T : p.G;
+    const int N = N_T > 0 ? N_T : p.N;
+    const int lane = threadIdx.x & 31;
+    const int warp_in_block = threadIdx.x >> 5;
+    float4* tile = s_tile + warp_in_block * (32 * PXT);
+
+    // grid.y = stack, grid.x covers the stack's pixel groups: a warp tile never straddles stacks
+    const int stack = blockIdx.y;
+    const unsigned n_groups = (unsigned)p.n_groups;
+    const unsigned g = blockIdx.x * kBlock + threadIdx.x;       // group inside the stack
+    const bool active = g < n_groups;
+    const long long out0 = (long long)stack * p.npx;            // first output pixel of the stack
+
+    uint32_t maskw[NW];
+#pragma unroll
+    for (int w = 0; w < NW; w++) maskw[w] = 0;
+
+    if (active) {
+        const unsigned off = g * PXT;             // first pixel of the group inside the stack
+        const int v = (int)(off / (unsigned)p.W);
+        const int u0 = (int)(off - (unsigned)v * (unsigned)p.W);
+        const uint8_t* base = p.stack + (long long)stack * p.P * p.npx + off;
+
+        // ---- a3 + a4: Gray pairs -> per-pixel code bits (CDecodeGray.cpp:155-199) ----
+        uint32_t lo[NW], hi[NW];
+#pragma unroll
+        for (int w = 0; w < NW; w++) { lo[w] = 0; hi[w] = 0; }
+        auto gray_bit = [&](int b) {
+            uint32_t pa[NW], pb[NW];
+            VecLoad<PXT>::load(base + (long long)(2 * b) * p.npx, pa);
+            VecLoad<PXT>::load(base + (long long)(2 * b + 1) * p.npx, pb);
+#pragma unroll
+            for (int w = 0; w < NW; w++) {
+                const uint32_t t = gt_u8x4_msb(pa[w], pb[w]);
+                if (b < 8) lo[w] |= (t >> (7 - b)) & (0x01010101u << b);
+                else       hi[w] |= (t >> (15 - b)) & (0x01010101u << (b - 8));
+            }
+        };
+        if constexpr (G_T > 0) {
+#pragma unroll
+            for (int b = 0; b < G_T; b++) gray_bit(b);
+        } else {
+#pragma unroll 1
+            for (int b = 0; b < G; b++) gray_bit(b);
+        }
+        // gray2bin (CDecodeGray.cpp:120-125,200): arithmetic for the reflected code
+        uint32_t bl[NW], bh[NW];
+        if (p.lut == nullptr) {
+#pragma unroll
+            for (int w = 0; w < NW; w++) {
+                bh[w] = (G > 8) ? prefix_xor_u8x4(hi[w]) : 0u;
+                bl[w] = prefix_xor_u8x4(lo[w]) ^ ((bh[w] & 0x01010101u) * 0xFFu);
+            }
+        } else {
+#pragma unroll
+            for (int w = 0; w < NW; w++) { bl[w] = lo[w]; bh[w] = hi[w]; }
+        }
+
+        // ---- a6: phase images -> (sin, cos) sums (CDecodePhase.cpp:59-65) ----
+        float sv[PXT], cv[PXT];
+        if (N == 4) {
+            uint32_t q0[NW], q1[NW], q2[NW], q3[NW];
+            const uint8_t* ph = base + (long long)(2 * G) * p.npx;
+            VecLoad<PXT>::load(ph, q0);
+            VecLoad<PXT>::load(ph + p.npx, q1);
+            VecLoad<PXT>::load(ph + 2 * p.npx, q2);
+            VecLoad<PXT>::load(ph + 3 * p.npx, q3);
+#pragma unroll
+            for (int w = 0; w < NW; w++)
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    sv[4 * w + j] = __fmul_rn(__fsub_rn(u8_magic(q0[w], j), u8_magic(q2[w], j)), 0.5f);
+                    cv[4 * w + j] = __fmul_rn(__fsub_rn(u8_magic(q1[w], j), u8_magic(q3[w], j)), 0.5f);
+                }
+        } else if ((N & 1) == 0) {
+            // [EXT] even N: d_k = I_k - I_{k+N/2}; S = sum d_k cos(2 pi k/N), Cc = sum d_k sin(2 pi k/N)
+#pragma unroll
+            for (int i = 0; i < PXT; i++) { sv[i] = 0.f; cv[i] = 0.f; }
+            const int half = N >> 1;
+            auto phase_pair = [&](int k) {
+                uint32_t qa[NW], qb[NW];
+                const uint8_t* ph = base + (long long)(2 * G + k) * p.npx;
+                VecLoad<PXT>::load(ph, qa);
+                VecLoad<PXT>::load(ph + (long long)half * p.npx, qb);
+                const float ck = p.ck[k], sk = p.sk[k];
+#pragma unroll
+                for (int w = 0; w < NW; w++)
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        const float d = __fsub_rn(u8_magic(qa[w], j), u8_magic(qb[w], j));
+                        sv[4 * w + j] = __fmaf_rn(d, ck, sv[4 * w + j]);
+                        cv[4 * w + j] = __fmaf_rn(d, sk, cv[4 * w + j]);
+                    }
+            };
+            if constexpr (N_T > 0) {
+#pragma unroll
+                for (int k = 0; k < N_T / 2; k++) phase_pair(k);
+            } else {
+#pragma unroll 1
+                for (int k = 0; k < half; k++) phase_pair(k);
+            }
+        } else {
+            // [EXT] odd N: plain sums
+#pragma unroll
+            for (int i = 0; i < PXT; i++) { sv[i] = 0.f; cv[i] = 0.f; }
+#pragma unroll 1
+            for (int k = 0; k < N; k++) {
+                uint32_t qa[NW];
+                VecLoad<PXT>::load(base + (long long)(2 * G + k) * p.npx, qa);
+                const float ck = p.ck[k], sk = p.sk[k];
+#pragma unroll
+                for (int w = 0; w < NW; w++)
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        const float gk = __fsub_rn(u8_magic(qa[w], j), 8388608.f);
+                        sv[4 * w + j] = __fmaf_rn(gk, ck, sv[4 * w + j]);
+                        cv[4 * w + j] = __fmaf_rn(gk, sk, cv[4 * w + j]);
+                    }
+            }
+        }
+
+        // ---- per pixel: arctan, offset, unwrap, triangulate ----
+#pragma unroll
+        for (int w = 0; w < NW; w++) {
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int i = 4 * w + j;
+                int kbin = (int)((bl[w] >> (8 * j)) & 0xFFu) | (int)(((bh[w] >> (8 * j)) & 0xFFu) << 8);
+                if (p.lut != nullptr) kbin = (int)__ldg(p.lut + kbin);
+                else if (G == 16) kbin = (int)(short)kbin;   // m_gray2bin is `short` (CDecodeGray.h:23)
+                const float s = sv[i], c = cv[i];
+                const float pix = phase_to_pix(fast_atan2_deg(s, c), p.Tf);
+                bool mod_ok = true;
+                if (p.use_mod) mod_ok = __fadd_rn(__fmul_rn(s, s), __fmul_rn(c, c)) >= p.thr2;
+                PixelResult r;
+                unwrap_and_triangulate(p, kbin, pix, mod_ok, u0 + i, v, r);
+                // swizzled slot: conflict-free for this write (8 lanes, same i) and for the
+                // transposed read below (same owner lane, 8 consecutive i)
+                tile[lane * PXT + (i ^ swizzle<PXT>(lane))] = make_float4(r.x, r.y, r.z, r.w);
+                maskw[w] |= (uint32_t)r.valid << (8 * j);
+                if (PARITY) {
+                    const long long o = out0 + off + i;
+                    if (p.kbin) p.kbin[o] = (int16_t)kbin;
+                    if (p.corr) p.corr[o] = (int8_t)r.corr;
+                    if (p.phase_pix) p.phase_pix[o] = r.pix;
+                    if (p.proj_u) p.proj_u[o] = __dadd_rn((double)r.gint, (double)r.pix);
+                }
+            }
+        }
+        // validity mask: PXT contiguous bytes per thread, 32*PXT per warp
+        uint8_t* mptr = p.mask + out0 + off;
+        if constexpr (PXT == 16) st_stream_u4(mptr, make_uint4(maskw[0], maskw[1], maskw[2], maskw[3]));
+        else if constexpr (PXT == 8) st_stream_u2(mptr, make_uint2(maskw[0], maskw[1]));
+        else *reinterpret_cast<uint32_t*>(mptr) = maskw[0];
+    }
+
+    // ---- transposed, fully coalesced float4 stores ----
+    __syncwarp();
+    const unsigned px0 = (blockIdx.x * kBlock + (threadIdx.x & ~31u)) * PXT;  // warp's first pixel in the stack
+    const unsigned stack_px = n_groups * PXT;
+    float4* out = p.xyzw + out0;
+#pragma unroll
+    for (int it = 0; it < PXT; it++) {
+        const int pidx = it * 32 + lane;                       // pixel inside the warp tile
+        const int owner = pidx / PXT, i = pidx % PXT;
+        const float4 val = tile[owner * PXT + (i ^ swizzle<PXT>(owner))];
+        if (px0 + pidx < stack_px) st_stream_f4(out + px0 + pidx, val);
+    }
+}
+
+// One pixel per thread: any width, any alignment.  Same per-pixel math.
+template <bool PARITY>
+__global__ void __launch_bounds__(kBlock)
+reconstruct_scalar_kernel(const __grid_constant__ KParams p)
+{
+    const long long total = p.npx * (long long)p.n_stacks;
+    const long long idx = (long long)blockIdx.x * kBlock + threadIdx.x;
+    if (idx >= total) return;
+    const int stack = (int)(idx / p.npx);
+    const long long off = idx - (long long)stack * p.npx;
+    const int v = (int)(off / p.W);
+    const int u = (int)(off - (long long)v * p.W);
+    const uint8_t* base = p.stack + (long long)stack * p.P * p.npx + off;
+    unsigned code = 0;
+    for (int b = 0; b < p.G; b++) {
+        const unsigned a = base[(long long)(2 * b) * p.npx];
+        const unsigned bb = base[(long long)(2 * b + 1) * p.npx];
+        code |= (a > bb ? 1u : 0u) << b;   // sat_u8(a-b) > 0  (CDecodeGray.cpp:159,168)
+    }
+    int kbin;
+    if (p.lut) {
+        kbin = (int)__ldg(p.lut + code);
+    } else {
+        unsigned g = code;
+        g ^= g >> 1; g ^= g >> 2; g ^= g >> 4; g ^= g >> 8;
+        kbin = (int)(short)(g & 0xFFFFu);   // m_gray2bin is `short` (CDecodeGray.h:23)
+    }
+    const uint8_t* ph = base + (long long)(2 * p.G) * p.npx;
+    float s, c;
+    if (p.N == 4) {
+        s = __fmul_rn(__fsub_rn((float)ph[0], (float)ph[2 * p.npx]), 0.5f);
+        c = __fmul_rn(__fsub_rn((float)ph[p.npx], (float)ph[3 * p.npx]), 0.5f);
+    } else if ((p.N & 1) == 0) {
+        s = 0.f; c = 0.f;
+        const int half = p.N >> 1;
+        for (int k = 0; k < half; k++) {
+            const float d = __fsub_rn((float)ph[(long long)k * p.npx], (float)ph[(long long)(k + half) * p.npx]);
+            s = __fmaf_rn(d, p.ck[k], s);
+            c = __fmaf_rn(d, p.sk[k], c);
+        }
+    } else {
+        s = 0.f; c = 0.f;
+        for (int k = 0; k < p.N; k++) {
+            const float gk = (float)ph[(long long)k * p.npx];
+            s = __fmaf_rn(gk, p.ck[k], s);
+            c = __fmaf_rn(gk, p.sk[k], c);
+        }
+    }
+    const float pix = phase_to_pix(fast_atan2_deg(s, c), p.Tf);
+    bool mod_ok = true;
+    if (p.use_mod) mod_ok = __fadd_rn(__fmul_rn(s, s), __fmul_rn(c, c)) >= p.thr2;
+    PixelResult r;
+    unwrap_and_triangulate(p, kbin, pix, mod_ok, u, v, r);
+    p.xyzw[idx] = make_float4(r.x, r.y, r.z, r.w);
+    p.mask[idx] = (uint8_t)r.valid;
+    if (PARITY) {
+        if (p.kbin) p.kbin[idx] = (int16_t)kbin;
+        if (p.corr) p.corr[idx] = (int8_t)r.corr;
+        if (p.phase_pix) p.phase_pix[idx] = r.pix;
+        if (p.proj_u) p.proj_u[idx] = __dadd_rn((double)r.gint, (double)r.pix);
+    }
+}
+
+// CDecodeGray::Decode on its own: 2G planes -> f64 plane (+ optional kbin).
+__global__ void __launch_bounds__(kBlock)
+decode_gray_kernel(const __grid_constant__ KParams p, const uint8_t* __restrict__ planes,
+                   double* __restrict__ gray_val, int16_t* __restrict__ kbin_out)
+{
+    const long long idx = (long long)blockIdx.x * kBlock + threadIdx.x;
+    if (idx >= p.npx) return;
+    unsigned code = 0;
+    for (int b = 0; b < p.G; b++) {
+        const unsigned a = planes[(long long)(2 * b) * p.npx + idx];
+        const unsigned bb = planes[(long long)(2 * b + 1) * p.npx + idx];
+        code |= (a > bb ? 1u : 0u) << b;
+    }
+    int kbin;
+    if (p.lut) {
+        kbin = (int)__ldg(p.lut + code);
+    } else {
+        unsigned g = code;
+        g ^= g >> 1; g ^= g >> 2; g ^= g >> 4; g ^= g >> 8;
+        kbin = (int)(short)(g & 0xFFFFu);   // m_gray2bin is `short` (CDecodeGray.h:23)
+    }
+    // (double)m_gray2bin[grayCode] * pixPeriod   (CDecodeGray.cpp:200)
+    gray_val[idx] = __dmul_rn((double)kbin, (double)p.gp);
+    if (kbin_out) kbin_out[idx] = (int16_t)kbin;
+}
+
+// CDecodePhase::Decode on its own: N planes -> f64 plane of offsets in (0, T].
+__global__ void __launch_bounds__(kBlock)
+decode_phase_kernel(const __grid_constant__ KParams p, const uint8_t* __restrict__ ph,
+                    double* __restrict__ phase_pix, uint8_t* __restrict__ mod_out)
+{
+    const long long idx = (long long)blockIdx.x * kBlock + threadIdx.x;
+    if (idx >= p.npx) return;
+    float s, c;
+    if (p.N == 4) {
+        s = __fmul_rn(__fsub_rn((float)ph[idx], (float)ph[2 * p.npx + idx]), 0.5f);
+        c = __fmul_rn(__fsub_rn((float)ph[p.npx + idx], (float)ph[3 * p.npx + idx]), 0.5f);
+    } else if ((p.N & 1) == 0) {
+        s = 0.f; c = 0.f;
+        const int half = p.N >> 1;
+        for (int k = 0; k < half; k++) {
+            const float d = __fsub_rn((float)ph[(long long)k * p.npx + idx],
+                                      (float)ph[(long long)(k + half) * p.npx + idx]);
+            s = __fmaf_rn(d, p.ck[k], s);
+            c = __fmaf_rn(d, p.sk[k], c);
+        }
+    } else {
+        s = 0.f; c = 0.f;
+        for (int k = 0; k < p.N; k++) {
+            const float gk = (float)ph[(long long)k * p.npx + idx];
+            s = __fmaf_rn(gk, p.ck[k], s);
+            c = __fmaf_rn(gk, p.sk[k], c);
+        }
+    }
+    phase_pix[idx] = (double)phase_to_pix(fast_atan2_deg(s, c), p.Tf);
+    if (mod_out) {
+        const bool ok = !p.use_mod || (__fadd_rn(__fmul_rn(s, s), __fmul_rn(c, c)) >= p.thr2);
+        mod_out[idx] = ok ? 1 : 0;
+    }
+}
+
+// CCalculation::FillCoordinate(i) for an arbitrary f64 ProjectorU plane
+// (CCalculation.cpp:666-771).  U is arbitrary here (the dynamic mode adds f32
+// deltas to it), so z is always solved in f64.
+__global__ void __launch_bounds__(kBlock)
+triangulate_kernel(const __grid_constant__ KParams p, const double* __restrict__ proj_u,
+                   float4* __restrict__ xyzw, uint8_t* __restrict__ mask)
+{
+    const long long idx = (long long)blockIdx.x * kBlock + threadIdx.x;
+    if (idx >= p.npx) return;
+    const int v = (int)(idx / p.W);
+    const int u = (int)(idx - (long long)v * p.W);
+    const double U = proj_u[idx];
+    float z = 0.f;
+    int valid = 0;
+    if (U != 0.0) {
+        const double zd = z_exact(p, U, u, v);
+        valid = !((zd < p.fov_min) || (zd > p.fov_max));
+        z = valid ? (float)zd : 0.f;
+    }
+    const float x = z * fmaf(p.rx1, (float)u, p.rx0);
+    const float y = z * fmaf(p.ry1, (float)v, p.ry0);
+    xyzw[idx] = make_float4(x, y, z, (float)U);
+    mask[idx] = (uint8_t)valid;
+}
+
+// ---------------------------------------------------------------------------
+using VecKernel = void (*)(const KParams);
+
+struct VecEntry { int G, N, pxt; bool parity; VecKernel fn; };
+
+#define SLC_VEC(PXT, G, N) \
+    { G, N, PXT, false, reconstruct_vec_kernel<PXT, G, N, false> }, \
+    { G, N, PXT, true,  reconstruct_vec_kernel<PXT, G, N, true> }
+
+// Specialised <G, N> instances: the reference default and BASELINE.json's
+// configurations; anything else runs the generic (0, 0) instance.
+const VecEntry kVecTable[] = {
+    SLC_VEC(16, 6, 4),  SLC_VEC(16, 7, 4),  SLC_VEC(16, 8, 4), SLC_VEC(16, 9, 4),
+    SLC_VEC(16, 8, 8),  SLC_VEC(16, 10, 12), SLC_VEC(16, 0, 0),
+    SLC_VEC(8, 9, 4),   SLC_VEC(8, 8, 8),   SLC_VEC(8, 10, 12), SLC_VEC(8, 0, 0),
+    SLC_VEC(4, 9, 4),   SLC_VEC(4, 0, 0),
+};
+
+const VecEntry* find_vec(int G, int N, int pxt, bool parity, bool* specialised)
+{
+    const VecEntry* generic = nullptr;
+    for (const VecEntry& e : kVecTable) {
+        if (e.pxt != pxt || e.parity != parity) continue;
+        if (e.G == G && e.N == N) { *specialised = true; return &e; }
+        if (e.G == 0 && e.N == 0) generic = &e;
+    }
+    *specialised = false;
+    return generic;
+}
+
+int g_default_pxt = 16;
+
+}  // namespace
+
+void set_default_pixels_per_thread(int pxt)
+{
+    if (pxt == 4 || pxt == 8 || pxt == 16) g_default_pxt = pxt;
+}
+
+bool vector_kernel_applicable(const KParams& p, int pxt)
+{
+    // groups must not straddle rows and every plane base must stay PXT-aligned
+    return (p.W % pxt == 0) && (p.npx % 16 == 0) && (reinterpret_cast<uintptr_t>(p.stack) % 16 == 0) &&
+           (reinterpret_cast<uintptr_t>(p.mask) % 16 == 0) && (reinterpret_cast<uintptr_t>(p.xyzw) % 16 == 0);
+}
+
+cudaError_t launch_reconstruct(KParams p, bool force_scalar, cudaStream_t stream, LaunchInfo* info)
+{
+    const bool parity = p.kbin || p.corr || p.phase_pix || p.proj_u;
+    int pxt = g_default_pxt;
+    if (!force_scalar && p.W % 16 != 0) pxt = (p.W % 8 == 0) ? 8 : (p.W % 4 == 0 ? 4 : 0);
+    if (!force_scalar && pxt != 0 && vector_kernel_applicable(p, pxt)) {
+        bool spec = false;
+        const VecEntry* e = find_vec(p.G, p.N, pxt, parity, &spec);
+        if (e != nullptr) {
+            p.n_groups = p.npx / pxt;
+            const long long blocks = (p.n_groups + kBlock - 1) / kBlock;
+            const int smem = kBlock * pxt * (int)sizeof(float4);
+            if (blocks > 0x7fffffffLL || p.n_stacks > 65535 || p.npx > 0x7fffffffLL)
+                return cudaErrorInvalidConfiguration;
+            cudaError_t err = cudaFuncSetAttribute(e->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            if (err != cudaSuccess) return err;
+            if (info) {
+                cudaFuncAttributes fa;
+                err = cudaFuncGetAttributes(&fa, e->fn);
+                if (err != cudaSuccess) return err;
+                info->variant = spec ? 0 : 1;
+                info->regs = fa.numRegs;
+                info->block = kBlock;
+                info->smem = smem;
+                info->pxt = pxt;
+                if (info->query_only) return cudaSuccess;
+            }
+            e->fn<<<dim3((unsigned)blocks, (unsigned)p.n_stacks), kBlock, smem, stream>>>(p);
+            return cudaGetLastError();
+        }
+    }
+    const long long total = p.npx * (long long)p.n_stacks;
+    const long long blocks = (total + kBlock - 1) / kBlock;
+    if (blocks > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
+    auto fn = parity ? reconstruct_scalar_kernel<true> : reconstruct_scalar_kernel<false>;
+    if (info) {
+        cudaFuncAttributes fa;
+        cudaError_t err = cudaFuncGetAttributes(&fa, fn);
+        if (err != cudaSuccess) return err;
+        info->variant = 2;
+        info->regs = fa.numRegs;
+        info->block = kBlock;
+        info->smem = 0;
+        info->pxt = 1;
+        if (info->query_only) return cudaSuccess;
+    }
+    fn<<<(unsigned)blocks, kBlock, 0, stream>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_decode_gray(const KParams& p, const uint8_t* d_planes, double* d_gray_val,
+                               int16_t* d_kbin, cudaStream_t stream)
+{
+    const long long blocks = (p.npx + kBlock - 1) / kBlock;
+    decode_gray_kernel<<<(unsigned)blocks, kBlock, 0, stream>>>(p, d_planes, d_gray_val, d_kbin);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_decode_phase(const KParams& p, const uint8_t* d_planes, double* d_phase_pix,
+                                uint8_t* d_mod_ok, cudaStream_t stream)
+{
+    const long long blocks = (p.npx + kBlock - 1) / kBlock;
+    decode_phase_kernel<<<(unsigned)blocks, kBlock, 0, stream>>>(p, d_planes, d_phase_pix, d_mod_ok);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_triangulate(const KParams& p, const double* d_proj_u, float* d_xyzw, uint8_t* d_mask,
+                               cudaStream_t stream)
+{
+    const long long blocks = (p.npx + kBlock - 1) / kBlock;
+    triangulate_kernel<<<(unsigned)blocks, kBlock, 0, stream>>>(p, d_proj_u, reinterpret_cast<float4*>(d_xyzw),
+                                                                d_mask);
+    return cudaGetLastError();
+}
+
+}  // namespace slc

@@ -1,0 +1,32 @@
+// slc_kernels.h -- internal launch interface between the C ABI (slc_capi.cu)
+// and the kernels (slc_kernels.cu).  Not installed; the public surface is
+// include/slcalc_b200.h.
+#pragma once
+
+#include "slc_device.cuh"
+
+namespace slc {
+
+struct LaunchInfo {
+    int variant = -1;   // 0 specialised vector, 1 generic vector, 2 scalar
+    int regs = 0;
+    int block = 0;
+    int smem = 0;
+    int pxt = 0;        // pixels per thread
+    bool query_only = false;
+};
+
+// The fused decode -> unwrap -> triangulate kernel over p.n_stacks stacks.
+cudaError_t launch_reconstruct(KParams p, bool force_scalar, cudaStream_t stream, LaunchInfo* info);
+
+cudaError_t launch_decode_gray(const KParams& p, const uint8_t* d_planes, double* d_gray_val,
+                               int16_t* d_kbin, cudaStream_t stream);
+cudaError_t launch_decode_phase(const KParams& p, const uint8_t* d_planes, double* d_phase_pix,
+                                uint8_t* d_mod_ok, cudaStream_t stream);
+cudaError_t launch_triangulate(const KParams& p, const double* d_proj_u, float* d_xyzw, uint8_t* d_mask,
+                               cudaStream_t stream);
+
+// tuning hook (bench / tests): pixels per thread of the vector kernel, 4 / 8 / 16
+void set_default_pixels_per_thread(int pxt);
+
+}  // namespace slc

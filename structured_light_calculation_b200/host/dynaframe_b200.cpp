@@ -1,0 +1,505 @@
+// dynaframe_b200.cpp -- host-side mirror of the reference's class API
+// (CDecodeGray.h:18-53, CDecodePhase.h:12-39, CCalculation.h:10-95) on top of
+// the C ABI.  Plain C++17, no CUDA headers, no OpenCV.
+#include "dynaframe_b200.hpp"
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+#include <sstream>
+
+namespace dynaframe {
+
+// ---------------------------------------------------------------- Mat -----
+static size_t elem_size_of(int type)
+{
+    switch (type) {
+    case CV_8UC1: return 1;
+    case CV_16SC1: return 2;
+    case CV_32FC1: return 4;
+    case CV_64FC1: return 8;
+    case CV_32FC4: return 16;
+    default: return 1;
+    }
+}
+
+size_t Mat::elemSize() const { return elem_size_of(type_); }
+
+Mat::Mat(int rows_, int cols_, int type__, void* data, size_t step_bytes)
+{
+    rows = rows_; cols = cols_; type_ = type__;
+    step_ = step_bytes ? step_bytes : (size_t)cols_ * elem_size_of(type__);
+    data_ = static_cast<uint8_t*>(data);
+}
+
+void Mat::create(int rows_, int cols_, int type__)
+{
+    if (rows == rows_ && cols == cols_ && type_ == type__ && owner_ && isContinuous()) return;
+    rows = rows_; cols = cols_; type_ = type__;
+    step_ = (size_t)cols_ * elem_size_of(type__);
+    const size_t bytes = step_ * (size_t)rows_;
+    void* p = nullptr;
+    if (bytes && posix_memalign(&p, 64, bytes) != 0) p = nullptr;
+    owner_.reset(static_cast<uint8_t*>(p), [](uint8_t* q) { free(q); });
+    data_ = owner_.get();
+}
+
+void Mat::copyTo(Mat& dst) const
+{
+    if (empty()) { dst = Mat(); return; }
+    dst.create(rows, cols, type_);
+    const size_t row_bytes = (size_t)cols * elemSize();
+    for (int r = 0; r < rows; r++) std::memcpy(dst.ptr(r), ptr(r), row_bytes);
+}
+
+// ------------------------------------------------------- ErrorHandling ----
+static thread_local std::string g_last_message;
+
+int ErrorHandling(std::string message)
+{
+    // GlobalFunction.cpp:5 prints the same line; the system("PAUSE") at :6 is dropped
+    std::cout << "An Error Occurs:" << message << std::endl;
+    g_last_message = message;
+    return 0;
+}
+
+const std::string& LastErrorMessage() { return g_last_message; }
+
+// ------------------------------------------------------------ helpers -----
+bool ReadGrayCodeFile(const std::string& file, int grayCodeSize, std::vector<int16_t>& gray2bin)
+{
+    // CDecodeGray.cpp:113-125
+    std::ifstream codeFile(file.c_str(), std::ios::in);
+    if (!codeFile) return false;
+    gray2bin.assign((size_t)grayCodeSize, 0);
+    for (int i = 0; i < grayCodeSize; i++) {
+        int binCode = 0, grayCode = 0;
+        if (!(codeFile >> binCode >> grayCode)) return false;
+        if (grayCode < 0 || grayCode >= grayCodeSize) return false;
+        gray2bin[(size_t)grayCode] = (int16_t)binCode;
+    }
+    return true;
+}
+
+static bool parse_matrix(const std::string& text, const std::string& key, int want, double* out)
+{
+    // the subset of YAML 1.0 that cv::FileStorage writes for !!opencv-matrix
+    const size_t k = text.find(key + ":");
+    if (k == std::string::npos) return false;
+    const size_t d = text.find("data:", k);
+    if (d == std::string::npos) return false;
+    const size_t lb = text.find('[', d), rb = text.find(']', d);
+    if (lb == std::string::npos || rb == std::string::npos || rb < lb) return false;
+    std::string body = text.substr(lb + 1, rb - lb - 1);
+    for (char& c : body) if (c == ',' || c == '\n' || c == '\r') c = ' ';
+    std::istringstream ss(body);
+    int n = 0;
+    std::string tok;
+    while (ss >> tok) {
+        if (n >= want) return false;
+        out[n++] = std::strtod(tok.c_str(), nullptr);   // accepts "0." and "1.2e+003"
+    }
+    return n == want;
+}
+
+bool ReadCalibrationYaml(const std::string& path, double cam[9], double pro[9], double R[9], double T[3])
+{
+    // CCalculation.cpp:124-132: keys CamMat, ProMat, R, T
+    std::ifstream f(path.c_str(), std::ios::in | std::ios::binary);
+    if (!f) return false;
+    std::stringstream buf;
+    buf << f.rdbuf();
+    const std::string text = buf.str();
+    // "R:" and "T:" must match at line start so they are not found inside other keys
+    auto find_line_key = [&](const std::string& key, int want, double* out) {
+        size_t pos = 0;
+        while ((pos = text.find(key + ":", pos)) != std::string::npos) {
+            if (pos == 0 || text[pos - 1] == '\n') return parse_matrix(text.substr(pos), key, want, out);
+            pos += key.size();
+        }
+        return false;
+    };
+    return find_line_key("CamMat", 9, cam) && find_line_key("ProMat", 9, pro) && find_line_key("R", 9, R) &&
+           find_line_key("T", 3, T);
+}
+
+static slc_config make_cfg(const StaticParameters& sp, int projector_width, int gray_digits, int phase_steps)
+{
+    slc_config c;
+    std::memset(&c, 0, sizeof(c));
+    c.width = sp.CAMERA_RESLINE;
+    c.height = sp.CAMERA_RESROW;
+    c.projector_width = projector_width;
+    c.gray_digits = gray_digits;
+    c.phase_steps = phase_steps;
+    c.fov_min = sp.FOV_MIN_DISTANCE;
+    c.fov_max = sp.FOV_MAX_DISTANCE;
+    c.modulation_min = sp.MODULATION_MIN;
+    c.flags = 0;
+    c.device = sp.CUDA_DEVICE;
+    c.max_batch = 1;
+    c.num_slots = 1;
+    return c;
+}
+
+static bool copy_plane(const Mat& pic, const StaticParameters& sp, uint8_t* dst, const char* who)
+{
+    if (pic.empty() || pic.type() != CV_8UC1 || pic.rows != sp.CAMERA_RESROW || pic.cols != sp.CAMERA_RESLINE) {
+        ErrorHandling(std::string(who) + "->picture must be CV_8UC1 of the camera resolution.");
+        return false;
+    }
+    for (int r = 0; r < pic.rows; r++)
+        std::memcpy(dst + (size_t)r * pic.cols, pic.ptr(r), (size_t)pic.cols);
+    return true;
+}
+
+// ------------------------------------------------------------ CSensor -----
+bool CSensor::InitSensor() { group_ = -1; now_ = 0; return true; }
+bool CSensor::CloseSensor() { for (auto& g : groups_) g.clear(); group_ = -1; return true; }
+
+bool CSensor::StoreDatas(int groupNum, int idx, const Mat& picture)
+{
+    if (groupNum < 0 || groupNum > 2 || idx < 0) return false;
+    if ((size_t)idx >= groups_[groupNum].size()) groups_[groupNum].resize((size_t)idx + 1);
+    picture.copyTo(groups_[groupNum][(size_t)idx]);
+    return true;
+}
+
+bool CSensor::LoadDatas(int groupNum)
+{
+    // CSensorV.cpp:60-133 chooses the file group; here the group is already in memory
+    if (groupNum < 0 || groupNum > 2) { ErrorHandling("CSensor::LoadDatas->invalid groupNum."); return false; }
+    group_ = groupNum;
+    now_ = 0;
+    return true;
+}
+
+bool CSensor::UnloadDatas() { group_ = -1; return true; }
+
+bool CSensor::SetProPicture(int nowNum)
+{
+    if (group_ < 0 || nowNum < 0 || (size_t)nowNum >= groups_[group_].size()) return false;
+    now_ = nowNum;
+    return true;
+}
+
+Mat CSensor::GetCamPicture()
+{
+    Mat out;
+    if (group_ >= 0 && (size_t)now_ < groups_[group_].size()) groups_[group_][(size_t)now_].copyTo(out);
+    return out;
+}
+
+// -------------------------------------------------------- CDecodeGray -----
+CDecodeGray::CDecodeGray(const StaticParameters& sp) : sp_(sp) {}
+CDecodeGray::~CDecodeGray() { ReleaseSpace(); }
+
+bool CDecodeGray::SetNumDigit(int numDigit, bool ver)
+{
+    if ((numDigit <= 0) || (numDigit > 16)) return false;          // CDecodeGray.cpp:39-40
+    m_numDigit = numDigit;
+    m_grayCodeSize = 1 << m_numDigit;
+    m_vertical = ver;
+    if (allocated_) ReleaseSpace();                                 // :48-49
+    return AllocateSpace();
+}
+
+bool CDecodeGray::SetMatFileName(std::string codeFilePath, std::string codeFileName)
+{
+    m_codeFilePath = codeFilePath;
+    m_codeFileName = codeFileName;
+    return true;
+}
+
+bool CDecodeGray::AllocateSpace()
+{
+    if ((m_numDigit <= 0) || (m_numDigit > 16)) return false;
+    const int pw = m_vertical ? sp_.PROJECTOR_RESLINE : sp_.PROJECTOR_RESROW;   // CDecodeGray.cpp:182-185
+    slc_config cfg = make_cfg(sp_, pw, m_numDigit, 4);
+    if (slc_create(&cfg, &ctx_) != SLC_OK) {
+        ErrorHandling(std::string("CDecodeGray.AllocateSpace->") + slc_last_error(nullptr));
+        ctx_ = nullptr;
+        return false;
+    }
+    const size_t bytes = (size_t)2 * m_numDigit * sp_.CAMERA_RESROW * sp_.CAMERA_RESLINE;
+    pinned_ = static_cast<uint8_t*>(slc_host_alloc(bytes));
+    if (!pinned_) { ErrorHandling("CDecodeGray.AllocateSpace->pinned allocation failed."); ReleaseSpace(); return false; }
+    std::memset(pinned_, 0, bytes);
+    m_gray2bin.assign((size_t)m_grayCodeSize, 0);
+    allocated_ = true;
+    return true;
+}
+
+bool CDecodeGray::ReleaseSpace()
+{
+    if (pinned_) { slc_host_free(pinned_); pinned_ = nullptr; }
+    if (ctx_) { slc_destroy(ctx_); ctx_ = nullptr; }
+    m_gray2bin.clear();
+    allocated_ = false;
+    return true;
+}
+
+bool CDecodeGray::SetMat(int num, Mat pic)
+{
+    if (!allocated_) {                                              // CDecodeGray.cpp:26-30
+        ErrorHandling("CDecodeGray.SetMat->grePicture Space is not allocated.");
+        return false;
+    }
+    if (num < 0 || num >= 2 * m_numDigit) {
+        ErrorHandling("CDecodeGray.SetMat->num out of range.");
+        return false;
+    }
+    const size_t plane = (size_t)sp_.CAMERA_RESROW * sp_.CAMERA_RESLINE;
+    return copy_plane(pic, sp_, pinned_ + (size_t)num * plane, "CDecodeGray.SetMat");   // :31 deep copy
+}
+
+bool CDecodeGray::Decode()
+{
+    if (!allocated_) { ErrorHandling("Gray Decode->Space is not allocated."); return false; }
+    if (!ReadGrayCodeFile(m_codeFilePath + m_codeFileName, m_grayCodeSize, m_gray2bin)) {
+        ErrorHandling("Gray Decode->Open file error.");             // CDecodeGray.cpp:115-119
+        return false;
+    }
+    if (slc_set_gray_lut(ctx_, m_gray2bin.data(), m_grayCodeSize) != SLC_OK) {
+        ErrorHandling(std::string("Gray Decode->") + slc_last_error(ctx_));
+        return false;
+    }
+    m_result.create(sp_.CAMERA_RESROW, sp_.CAMERA_RESLINE, CV_64FC1);   // :187
+    if (slc_decode_gray_host(ctx_, pinned_, reinterpret_cast<double*>(m_result.ptr()), nullptr) != SLC_OK) {
+        ErrorHandling(std::string("Gray Decode->") + slc_last_error(ctx_));
+        return false;
+    }
+    return true;
+}
+
+Mat CDecodeGray::GetResult()
+{
+    Mat result;                                                     // CDecodeGray.cpp:142-147
+    m_result.copyTo(result);
+    return result;
+}
+
+// ------------------------------------------------------- CDecodePhase -----
+CDecodePhase::CDecodePhase(const StaticParameters& sp) : sp_(sp) {}
+CDecodePhase::~CDecodePhase() { DeleteSpace(); }
+
+bool CDecodePhase::DeleteSpace()
+{
+    if (pinned_) { slc_host_free(pinned_); pinned_ = nullptr; }
+    if (ctx_) { slc_destroy(ctx_); ctx_ = nullptr; }
+    allocated_ = false;
+    return true;
+}
+
+bool CDecodePhase::SetNumMat(int numMat, int pixperiod)
+{
+    if ((numMat <= 0)) return false;                                // CDecodePhase.cpp:122-123
+    m_numMat = numMat;
+    m_pixPeroid = pixperiod;
+    if (allocated_) DeleteSpace();                                  // :130-133
+    // a 1-digit Gray geometry whose phase period PW / 2^0 is exactly pixperiod
+    slc_config cfg = make_cfg(sp_, pixperiod, 1, numMat);
+    if (slc_create(&cfg, &ctx_) != SLC_OK) {
+        ErrorHandling(std::string("CDecodePhase.SetNumMat->") + slc_last_error(nullptr));
+        ctx_ = nullptr;
+        return false;
+    }
+    const size_t bytes = (size_t)numMat * sp_.CAMERA_RESROW * sp_.CAMERA_RESLINE;
+    pinned_ = static_cast<uint8_t*>(slc_host_alloc(bytes));
+    if (!pinned_) { ErrorHandling("CDecodePhase.SetNumMat->pinned allocation failed."); DeleteSpace(); return false; }
+    std::memset(pinned_, 0, bytes);
+    allocated_ = true;
+    return true;
+}
+
+bool CDecodePhase::SetMat(int num, Mat pic)
+{
+    if (!allocated_) {                                              // CDecodePhase.cpp:109-113
+        ErrorHandling("CDecodePhase.SetMat->grePicture Space is not allocated.");
+        return false;
+    }
+    if (num < 0 || num >= m_numMat) {
+        ErrorHandling("CDecodePhase.SetMat->num out of range.");
+        return false;
+    }
+    const size_t plane = (size_t)sp_.CAMERA_RESROW * sp_.CAMERA_RESLINE;
+    return copy_plane(pic, sp_, pinned_ + (size_t)num * plane, "CDecodePhase.SetMat");
+}
+
+bool CDecodePhase::Decode()
+{
+    if (!allocated_) { ErrorHandling("CDecodePhase.Decode()->CountResult fault"); return false; }
+    m_result.create(sp_.CAMERA_RESROW, sp_.CAMERA_RESLINE, CV_64FC1);   // CDecodePhase.cpp:50
+    if (slc_decode_phase_host(ctx_, pinned_, reinterpret_cast<double*>(m_result.ptr()), nullptr) != SLC_OK) {
+        ErrorHandling("CDecodePhase.Decode()->CountResult fault");      // :88
+        return false;
+    }
+    return true;
+}
+
+Mat CDecodePhase::GetResult()
+{
+    Mat result;                                                     // CDecodePhase.cpp:99-104
+    m_result.copyTo(result);
+    return result;
+}
+
+// ------------------------------------------------------- CCalculation -----
+CCalculation::CCalculation(const StaticParameters& sp) : sp_(sp) {}
+CCalculation::~CCalculation() { ReleaseSpace(); }
+
+bool CCalculation::ReleaseSpace()
+{
+    if (m_sensor) { delete m_sensor; m_sensor = nullptr; }
+    if (pinned_stack_) { slc_host_free(pinned_stack_); pinned_stack_ = nullptr; }
+    if (ctx_) { slc_destroy(ctx_); ctx_ = nullptr; }
+    calibrated_ = false;
+    return true;
+}
+
+bool CCalculation::Init()
+{
+    if (m_sensor != nullptr) return false;                          // CCalculation.cpp:80-81
+    if (ctx_ != nullptr) return false;                              // :82-83
+    m_sensor = new CSensor;                                         // :96-97
+    m_sensor->InitSensor();
+    slc_config cfg = make_cfg(sp_, sp_.PROJECTOR_RESLINE, sp_.GRAY_V_NUMDIGIT, sp_.PHASE_NUMDIGIT);
+    if (slc_create(&cfg, &ctx_) != SLC_OK) {
+        ErrorHandling(std::string("CCalculation::Init()->") + slc_last_error(nullptr));
+        ctx_ = nullptr;
+        ReleaseSpace();
+        return false;
+    }
+    const size_t npx = (size_t)sp_.CAMERA_RESROW * sp_.CAMERA_RESLINE;
+    const size_t planes = (size_t)2 * sp_.GRAY_V_NUMDIGIT + sp_.PHASE_NUMDIGIT;
+    pinned_stack_ = static_cast<uint8_t*>(slc_host_alloc(planes * npx));
+    if (!pinned_stack_) { ErrorHandling("CCalculation::Init()->pinned allocation failed."); ReleaseSpace(); return false; }
+    // :124-132 calibration
+    double cam[9], pro[9], R[9], T[3];
+    if (!ReadCalibrationYaml(sp_.DATA_PATH + m_paraFile, cam, pro, R, T)) {
+        ErrorHandling("CCalculation::Init() OpenFile Error:" + sp_.DATA_PATH + m_paraFile);
+        ReleaseSpace();
+        return false;
+    }
+    if (slc_set_calibration(ctx_, cam, pro, R, T) != SLC_OK) {      // :135-166
+        ErrorHandling(std::string("CCalculation::Init()->") + slc_last_error(ctx_));
+        ReleaseSpace();
+        return false;
+    }
+    calibrated_ = true;
+    return true;
+}
+
+bool CCalculation::FillFirstProjectorUAndCoordinate()
+{
+    const size_t npx = (size_t)sp_.CAMERA_RESROW * sp_.CAMERA_RESLINE;
+    const int G = sp_.GRAY_V_NUMDIGIT, N = sp_.PHASE_NUMDIGIT;
+    // CCalculation.cpp:536-544: Gray images through the sensor, in SetMat order
+    m_sensor->LoadDatas(0);
+    for (int i = 0; i < G * 2; i++) {
+        m_sensor->SetProPicture(i);
+        Mat sensorMat = m_sensor->GetCamPicture();
+        if (!copy_plane(sensorMat, sp_, pinned_stack_ + (size_t)i * npx, "CCalculation::FillFirstProjectorU")) return false;
+    }
+    // :549-557 phase images
+    m_sensor->LoadDatas(1);
+    for (int i = 0; i < N; i++) {
+        m_sensor->SetProPicture(i);
+        Mat sensorMat = m_sensor->GetCamPicture();
+        if (!copy_plane(sensorMat, sp_, pinned_stack_ + (size_t)(2 * G + i) * npx, "CCalculation::FillFirstProjectorU")) return false;
+    }
+    // :538 + CDecodeGray.cpp:113-125 Gray code table
+    if (!m_codeName.empty()) {
+        std::vector<int16_t> lut;
+        if (!ReadGrayCodeFile(m_codePath + m_codeName, 1 << G, lut)) {
+            ErrorHandling("Gray Decode->Open file error.");
+            return false;
+        }
+        if (slc_set_gray_lut(ctx_, lut.data(), 1 << G) != SLC_OK) {
+            ErrorHandling(std::string("Gray Decode->") + slc_last_error(ctx_));
+            return false;
+        }
+    }
+    m_xyzw.create(sp_.CAMERA_RESROW, sp_.CAMERA_RESLINE, CV_32FC4);
+    m_mask.create(sp_.CAMERA_RESROW, sp_.CAMERA_RESLINE, CV_8UC1);
+    m_projU.create(sp_.CAMERA_RESROW, sp_.CAMERA_RESLINE, CV_64FC1);
+    slc_parity_planes par;
+    std::memset(&par, 0, sizeof(par));
+    par.proj_u = reinterpret_cast<double*>(m_projU.ptr());
+    // :545-589 decode + combine and :666-771 FillCoordinate(0): one fused launch
+    if (slc_reconstruct_host(ctx_, pinned_stack_, 1, reinterpret_cast<float*>(m_xyzw.ptr()), m_mask.ptr(), &par) != SLC_OK) {
+        ErrorHandling(std::string("CCalculation::CalculateFirst()->") + slc_last_error(ctx_));
+        return false;
+    }
+    return true;
+}
+
+bool CCalculation::CalculateFirst()
+{
+    if (m_sensor == nullptr) return false;                          // CCalculation.cpp:176-177
+    if (ctx_ == nullptr) return false;                              // :178-179
+    if (!calibrated_) return false;                                 // :180-181
+    std::cout << "Begin calculate first frame." << std::endl;       // :183
+    if (!FillFirstProjectorUAndCoordinate()) return false;
+    if (!m_pcFile.empty()) {                                        // :192-198
+        printf("Begin writing...");
+        Result(sp_.DATA_PATH + m_pcFile, 0);
+        printf("Finished FirstFrame PointCloud.\n");
+    }
+    std::cout << "First frame finished." << std::endl;              // :203
+    return true;
+}
+
+bool CCalculation::CalculateOther()
+{
+    // The dynamic-frame tracker (CCalculation.cpp:208-320) is a different algorithm
+    // with a frame-to-frame recurrence; it is outside this drop-in's path.
+    ErrorHandling("CCalculation::CalculateOther()->dynamic frames are not part of the B200 first-frame path.");
+    return false;
+}
+
+bool CCalculation::Result(std::string fileName, int i)
+{
+    // CCalculation.cpp:323-357: "x y z\n" per in-FOV pixel, u outer / v inner
+    if (i != 0 || m_xyzw.empty()) return false;
+    std::fstream file;
+    file.open(fileName.c_str(), std::ios::out);
+    if (!file) {
+        ErrorHandling("CCalculation::Result() OpenFile Error:" + fileName);
+        return false;
+    }
+    for (int u = 0; u < sp_.CAMERA_RESLINE; u++) {
+        for (int v = 0; v < sp_.CAMERA_RESROW; v++) {
+            const float* p = &m_xyzw.at<float>(v, 4 * u);
+            const double valZ = p[2];
+            if ((valZ < sp_.FOV_MIN_DISTANCE) || (valZ > sp_.FOV_MAX_DISTANCE)) continue;
+            file << (double)p[0] << ' ';
+            file << (double)p[1] << ' ';
+            file << (double)p[2] << std::endl;
+        }
+    }
+    file.close();
+    return true;
+}
+
+static Mat channel_as_f64(const Mat& xyzw, int ch)
+{
+    Mat out;
+    if (xyzw.empty()) return out;
+    out.create(xyzw.rows, xyzw.cols, CV_64FC1);
+    for (int r = 0; r < xyzw.rows; r++) {
+        const float* src = reinterpret_cast<const float*>(xyzw.ptr(r));
+        double* dst = reinterpret_cast<double*>(out.ptr(r));
+        for (int c = 0; c < xyzw.cols; c++) dst[c] = (double)src[4 * c + ch];
+    }
+    return out;
+}
+
+Mat CCalculation::GetX() const { return channel_as_f64(m_xyzw, 0); }
+Mat CCalculation::GetY() const { return channel_as_f64(m_xyzw, 1); }
+Mat CCalculation::GetZ() const { return channel_as_f64(m_xyzw, 2); }
+Mat CCalculation::GetProjectorU() const { return m_projU.clone(); }
+
+}  // namespace dynaframe

@@ -1,0 +1,377 @@
+"""GPU parity tests (-m gpu): the CUDA path, called through the C ABI, against
+the CPU oracle on identical seeded inputs.
+
+Bars (BASELINE.json north_star):
+  * Gray period index, wrap correction, phase offset, ProjectorU (f64) and the
+    validity mask: BIT-EXACT;
+  * unwrapped phase 2*pi*U/T taken from the f32 `w` output: <= 1e-4 rad;
+  * XYZ: <= 1e-5 of the depth range (range 10..100 => 9e-4 units).  The residual
+    is FP32-vs-f64: the kernel solves z in f32 (f64 only inside guard bands at the
+    FOV limits, which is what keeps the mask bit-exact) and stores f32.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, bits_equal, make_case, oracle_run
+
+pytestmark = pytest.mark.gpu
+
+XYZ_REL_TOL = 1e-5      # of the depth range
+PHASE_TOL_RAD = 1e-4
+
+
+def _reconstructor(cfg, cal, **kw):
+    from structured_light_calculation_b200 import capi
+    rec = capi.Reconstructor(cfg, device=0, **kw)
+    rec.set_calibration(cal)
+    return rec
+
+
+def check_parity(got, want, cfg, stack=0):
+    assert bits_equal(got["kbin"][stack], want["kbin"]), "period index"
+    assert bits_equal(got["corr"][stack], want["corr"]), "wrap correction"
+    assert bits_equal(got["phase_pix"][stack].astype(np.float64), want["phase_pix"]), "phase offset"
+    assert bits_equal(got["proj_u"][stack], want["proj_u"]), "ProjectorU"
+    assert bits_equal(got["mask"][stack], want["mask"]), "validity mask"
+    T = cfg.phase_period
+    # w is ProjectorU rounded once to f32; as a phase that is within 1e-4 rad for every
+    # BASELINE geometry (projector width <= 4096)
+    assert bits_equal(got["xyzw"][stack, :, :, 3], want["proj_u"].astype(np.float32)), "w != f32(U)"
+    w = got["xyzw"][stack, :, :, 3].astype(np.float64)
+    phase_err = np.abs(w - want["proj_u"]).max() * 2 * np.pi / T
+    if cfg.projector_width <= 4096:
+        assert phase_err <= PHASE_TOL_RAD, f"unwrapped phase error {phase_err} rad"
+    tol = XYZ_REL_TOL * (cfg.fov_max - cfg.fov_min)
+    errs = {}
+    for ch, key in enumerate("xyz"):
+        a = got["xyzw"][stack, :, :, ch].astype(np.float64)
+        b = want[key]
+        assert np.array_equal(np.isnan(a), np.isnan(b))
+        err = np.nanmax(np.abs(a - b)) if a.size else 0.0
+        errs[key] = err
+        assert err <= tol, f"{key}: {err} > {tol}"
+    invalid = want["mask"] == 0
+    assert not got["xyzw"][stack, :, :, :3][invalid].any(), "invalid pixels must be (0,0,0)"
+    return errs, phase_err
+
+
+CASES = [
+    # (name, G, N, PW, W, H, noise, modulation)
+    ("ref_default", 6, 4, 1280, 256, 96, 1.0, 0.0),
+    ("config1", 7, 4, 1280, 320, 128, 1.0, 0.0),
+    ("config2", 9, 4, 2560, 384, 160, 2.0, 0.0),
+    ("config3", 8, 8, 2048, 272, 128, 1.0, 8.0),
+    ("config5", 10, 12, 4096, 512, 96, 1.0, 0.0),
+    ("generic_g5n6", 5, 6, 640, 128, 64, 1.0, 4.0),
+    ("generic_g11n4", 11, 4, 4096, 128, 64, 0.0, 0.0),
+    ("odd_n5", 8, 5, 2048, 128, 64, 1.0, 0.0),
+    ("odd_n3", 7, 3, 1280, 128, 64, 1.0, 2.0),
+    ("g1", 1, 4, 64, 64, 32, 1.0, 0.0),
+    ("g16", 16, 4, 65536, 64, 32, 0.0, 0.0),
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+@pytest.mark.parametrize("pxt", [16, 8, 4])
+def test_fused_kernel_matches_oracle(built_library, oracle, base_calibration, case, pxt):
+    from structured_light_calculation_b200 import capi
+    from structured_light_calculation_b200.configs import StackConfig
+    name, G, N, PW, W, H, noise, mod = case
+    cfg = StackConfig(W, H, PW, G, N, modulation_min=mod, name=name)
+    cal, scene, planes = make_case(cfg, base_calibration, noise=noise, seed=G * 100 + N)
+    built_library.slc_tune_pixels_per_thread(pxt)
+    try:
+        rec = _reconstructor(cfg, cal)
+        got = rec.reconstruct(planes, parity=True)
+        assert rec.launch_count() == 1
+        assert rec.info().kernel_variant in (0, 1)
+        rec.close()
+    finally:
+        built_library.slc_tune_pixels_per_thread(16)
+    want = oracle_run(oracle, cfg, cal, planes)
+    check_parity(got, want, cfg)
+    del capi
+
+
+@pytest.mark.parametrize("flags_name", ["z_fp64", "scalar"])
+def test_kernel_modes_match_oracle(built_library, oracle, base_calibration, flags_name):
+    from structured_light_calculation_b200 import capi
+    from structured_light_calculation_b200.configs import CONFIGS
+    flags = capi.SLC_FLAG_Z_FP64 if flags_name == "z_fp64" else capi.SLC_FLAG_SCALAR_KERNEL
+    cfg = CONFIGS["config2"].with_(width=320, height=200)
+    cal, scene, planes = make_case(cfg, base_calibration, noise=1.0, seed=21)
+    rec = _reconstructor(cfg, cal, flags=flags)
+    got = rec.reconstruct(planes, parity=True)
+    if flags_name == "scalar":
+        assert rec.info().kernel_variant == 2
+    rec.close()
+    want = oracle_run(oracle, cfg, cal, planes)
+    errs, _ = check_parity(got, want, cfg)
+    if flags_name == "z_fp64":
+        # z is then the f32 rounding of the reference's own f64 value
+        z = got["xyzw"][0, :, :, 2]
+        assert np.array_equal(z, want["z"].astype(np.float32))
+
+
+@pytest.mark.parametrize("W,H", [(100, 37), (17, 5), (24, 9), (1, 1), (1000, 3), (36, 7)])
+def test_ragged_sizes(built_library, oracle, base_calibration, W, H):
+    """Widths that are not a multiple of 16 / 8 / 4 fall back to narrower vectors or the scalar kernel."""
+    from structured_light_calculation_b200.configs import StackConfig
+    cfg = StackConfig(W, H, 1280, 6, 4)
+    cal, scene, planes = make_case(cfg, base_calibration, noise=1.0, seed=W)
+    rec = _reconstructor(cfg, cal)
+    got = rec.reconstruct(planes, parity=True)
+    rec.close()
+    check_parity(got, oracle_run(oracle, cfg, cal, planes), cfg)
+
+
+@pytest.mark.parametrize("name", ["pipeline_g6n4", "pipeline_g9n4"])
+def test_golden_fixture_through_cuda(built_library, name):
+    """CUDA path against the committed numpy+cv2 fixtures directly (no oracle in between)."""
+    from structured_light_calculation_b200.calibration import Calibration
+    from structured_light_calculation_b200.configs import StackConfig
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    W, H, PW, G, N = [int(v) for v in g["cfg"]]
+    cfg = StackConfig(W, H, PW, G, N)
+    rec = _reconstructor(cfg, Calibration(g["cam"], g["pro"], g["R"], g["T"]))
+    got = rec.reconstruct(g["planes"], parity=True)
+    rec.close()
+    want = {k: g[k] for k in ("kbin", "corr", "phase_pix", "proj_u", "mask", "x", "y", "z")}
+    check_parity(got, want, cfg)
+
+
+def test_extreme_inputs(built_library, oracle, base_calibration):
+    """All-black, all-white, saturated and random-noise stacks (no structure at all)."""
+    from structured_light_calculation_b200.configs import CONFIGS
+    cfg = CONFIGS["config1"].with_(width=128, height=48)
+    cal, _, _ = make_case(cfg, base_calibration)
+    rng = np.random.Generator(np.random.PCG64(99))
+    stacks = [
+        np.zeros((cfg.planes, cfg.height, cfg.width), np.uint8),
+        np.full((cfg.planes, cfg.height, cfg.width), 255, np.uint8),
+        rng.integers(0, 256, (cfg.planes, cfg.height, cfg.width), dtype=np.uint8),
+        rng.integers(0, 2, (cfg.planes, cfg.height, cfg.width), dtype=np.uint8) * 255,
+        rng.integers(126, 130, (cfg.planes, cfg.height, cfg.width), dtype=np.uint8),
+    ]
+    rec = _reconstructor(cfg, cal, max_batch=len(stacks))
+    got = rec.reconstruct(np.stack(stacks), parity=True)
+    rec.close()
+    for i, st in enumerate(stacks):
+        check_parity(got, oracle_run(oracle, cfg, cal, st), cfg, stack=i)
+
+
+def test_all_4step_phase_inputs_bit_exact(built_library, oracle):
+    """Every (I0-I2, I1-I3) pair a 4-step u8 stack can produce, in both kbin parities:
+    the arctan polynomial, the offset arithmetic and both wrap branches, exhaustively."""
+    from structured_light_calculation_b200.calibration import Calibration
+    from structured_light_calculation_b200.configs import StackConfig
+    W, H = 512, 511
+    cfg = StackConfig(W, H, 1280, 6, 4)
+    cal = Calibration(np.array([[2400.0, 0, 255.5], [0, 2400.0, 255.5], [0, 0, 1]]),
+                      np.array([[2000.0, 0, 640], [0, 2000.0, 400], [0, 0, 1]]), np.eye(3),
+                      np.array([-8.0, 0.0, 0.5]))
+    planes = np.zeros((cfg.planes, H, W), np.uint8)
+    d = np.arange(-255, 256)
+    ds, dc = np.meshgrid(d, d, indexing="ij")          # 511 x 511 differences
+    i0 = np.where(ds >= 0, ds, 0); i2 = np.where(ds >= 0, 0, -ds)
+    i1 = np.where(dc >= 0, dc, 0); i3 = np.where(dc >= 0, 0, -dc)
+    for k, img in enumerate((i0, i1, i2, i3)):
+        planes[12 + k, :, :511] = img.astype(np.uint8)
+    # kbin parity alternates by row; higher bits vary by column block
+    rows = np.arange(H)[:, None]
+    cols = np.arange(W)[None, :]
+    code = ((rows & 1) | ((cols >> 4) << 1)) & 63
+    for b in range(6):
+        bit = ((code >> b) & 1).astype(bool)
+        planes[2 * b] = np.where(bit, 180, 40)
+        planes[2 * b + 1] = np.where(bit, 40, 180)
+    rec = _reconstructor(cfg, cal)
+    got = rec.reconstruct(planes, parity=True)
+    rec.close()
+    want = oracle_run(oracle, cfg, cal, planes)
+    check_parity(got, want, cfg)
+    assert set(np.unique(want["corr"])) == {-1, 0, 1}
+
+
+def test_fov_boundary_mask_is_bit_exact(built_library, oracle, base_calibration):
+    """A plane swept through z = fov_min and z = fov_max: pixels arbitrarily close to the
+    limits must take the same side as the reference's f64 comparison (SURVEY hard part 3)."""
+    from structured_light_calculation_b200.configs import StackConfig
+    cfg = StackConfig(640, 512, 1280, 6, 4)
+    cal = base_calibration
+    from structured_light_calculation_b200 import capi
+    rec = capi.Reconstructor(cfg, device=0)
+    rec.set_calibration(cal)
+    ocfg = oracle.make_config(cfg.width, cfg.height, cfg.projector_width, cfg.gray_digits, cfg.phase_steps)
+    A, B, cC, cD, _ = oracle.calibration(ocfg, oracle.make_calib(cal.cam, cal.pro, cal.R, cal.T))
+    rng = np.random.Generator(np.random.PCG64(5))
+    n_flips_seen = 0
+    for limit in (cfg.fov_min, cfg.fov_max):
+        # U that puts z exactly on the limit, then jitter by a few f32 ulps of U
+        U0 = (A + limit * cC) / (B + limit * cD)
+        U = U0 + rng.integers(-3, 4, U0.shape) * np.spacing(U0.astype(np.float32)).astype(np.float64)
+        xyzw, mask = rec.triangulate(U)
+        z = -(A - B * U) / (cC - cD * U)
+        want = ((U != 0) & ~((z < cfg.fov_min) | (z > cfg.fov_max))).astype(np.uint8)
+        assert bits_equal(mask, want)
+        n_flips_seen += int((want == 0).sum() > 1000 and (want == 1).sum() > 1000)
+    rec.close()
+    assert n_flips_seen == 2   # the sweep really straddled both limits
+
+
+def test_fused_kernel_fov_guard_band(built_library, oracle, base_calibration):
+    """Same question for the fused kernel's f32 solve + f64 guard band: render scenes whose
+    surface sits within ~1e-6 of the FOV limits so thousands of pixels are borderline."""
+    from structured_light_calculation_b200 import synth
+    from structured_light_calculation_b200.configs import StackConfig
+    cfg = StackConfig(640, 256, 1280, 6, 4)
+    cal = synth.synthetic_calibration(cfg, base_calibration)
+    scene = synth.make_scene(cfg, cal)
+    ocfg = oracle.make_config(cfg.width, cfg.height, cfg.projector_width, cfg.gray_digits, cfg.phase_steps)
+    ocal = oracle.make_calib(cal.cam, cal.pro, cal.R, cal.T)
+    planes = synth.render_stack(cfg, scene, noise_sigma=0.5, seed=3)
+    base = oracle.reconstruct(ocfg, ocal, planes)
+    zs = base["z"][base["mask"] == 1]
+    rec = _reconstructor(cfg, cal)
+    for lim_lo, lim_hi in ((float(np.median(zs)), 100.0), (10.0, float(np.median(zs))),
+                           (float(np.percentile(zs, 30)), float(np.percentile(zs, 70)))):
+        c2 = cfg.with_(fov_min=lim_lo, fov_max=lim_hi)
+        rec2 = _reconstructor(c2, cal)
+        got = rec2.reconstruct(planes, parity=True)
+        rec2.close()
+        want = oracle_run(oracle, c2, cal, planes)
+        assert 0.05 < want["mask"].mean() < 0.95
+        check_parity(got, want, c2)
+    rec.close()
+
+
+def test_custom_gray_lut(built_library, oracle, base_calibration):
+    """A non-reflected code table (CDecodeGray.cpp:120-125 loads whatever the file holds)."""
+    from structured_light_calculation_b200.configs import CONFIGS
+    cfg = CONFIGS["config1"].with_(width=160, height=64)
+    cal, _, planes = make_case(cfg, base_calibration, seed=8)
+    rng = np.random.Generator(np.random.PCG64(1))
+    lut = rng.permutation(1 << cfg.gray_digits).astype(np.int16)
+    rec = _reconstructor(cfg, cal)
+    rec.set_gray_lut(lut)
+    got = rec.reconstruct(planes, parity=True)
+    check_parity(got, oracle_run(oracle, cfg, cal, planes, lut=lut), cfg)
+    # handing back the standard table returns to the arithmetic decode
+    rec.set_gray_lut(oracle.default_gray_lut(cfg.gray_digits))
+    got = rec.reconstruct(planes, parity=True)
+    check_parity(got, oracle_run(oracle, cfg, cal, planes), cfg)
+    rec.close()
+
+
+def test_decoder_objects(built_library, oracle, base_calibration):
+    """CDecodeGray / CDecodePhase stand-alone entry points (f64 planes like GetResult())."""
+    from structured_light_calculation_b200.configs import CONFIGS
+    for cfg in (CONFIGS["reference_default"].with_(width=200, height=50),
+                CONFIGS["config3"].with_(width=96, height=40)):
+        cal, _, planes = make_case(cfg, base_calibration, seed=4)
+        want = oracle_run(oracle, cfg, cal, planes)
+        rec = _reconstructor(cfg, cal)
+        val, kbin = rec.decode_gray(planes[: 2 * cfg.gray_digits])
+        pix, mod = rec.decode_phase(planes[2 * cfg.gray_digits:])
+        xyzw, mask = rec.triangulate(want["proj_u"])
+        rec.close()
+        assert bits_equal(val, want["gray_val"]) and bits_equal(kbin, want["kbin"])
+        assert bits_equal(pix, want["phase_pix"]) and bits_equal(mod, want["mod_ok"])
+        # triangulate() knows nothing about modulation: compare where modulation passed
+        ok = want["mod_ok"].astype(bool)
+        assert np.array_equal(mask[ok], want["mask"][ok])
+        assert np.array_equal(xyzw[..., 2][ok], want["z"].astype(np.float32)[ok])
+
+
+def test_batched_and_pipelined_host_paths(built_library, oracle, base_calibration):
+    from structured_light_calculation_b200 import capi
+    from structured_light_calculation_b200.configs import CONFIGS
+    cfg = CONFIGS["config2"].with_(width=192, height=80)
+    cal, scene, _ = make_case(cfg, base_calibration)
+    from structured_light_calculation_b200 import synth
+    n = 7
+    stacks = np.stack([synth.render_stack(cfg, scene, noise_sigma=1.5, seed=100 + i) for i in range(n)])
+    wants = [oracle_run(oracle, cfg, cal, stacks[i]) for i in range(n)]
+    # (a) one launch for the whole batch
+    rec = _reconstructor(cfg, cal, max_batch=n, num_slots=1)
+    got = rec.reconstruct(stacks, parity=True)
+    assert rec.launch_count() == 1
+    rec.close()
+    for i in range(n):
+        check_parity(got, wants[i], cfg, stack=i)
+    # (b) chunked over 3 stream slots, max_batch 2 -> 4 launches, same answers
+    rec = _reconstructor(cfg, cal, max_batch=2, num_slots=3)
+    got2 = rec.reconstruct(stacks, parity=True)
+    assert rec.launch_count() == 4
+    for k in got:
+        assert bits_equal(got[k], got2[k]), k
+    # (c) explicit double buffering with pinned memory
+    pin_in = capi.PinnedArray(stacks.shape, np.uint8)
+    pin_in.array[...] = stacks
+    pin_xyzw = capi.PinnedArray((n, cfg.height, cfg.width, 4), np.float32)
+    pin_mask = capi.PinnedArray((n, cfg.height, cfg.width), np.uint8)
+    sb = cfg.stack_bytes
+    for i in range(n):
+        slot = i % 3
+        if i >= 3:
+            rec.wait(slot)
+        rec.submit(slot, pin_in.ptr + i * sb, 1, pin_xyzw.ptr + i * cfg.pixels * 16, pin_mask.ptr + i * cfg.pixels)
+    with pytest.raises(capi.SlcError):      # slot still in flight
+        rec.submit((n - 1) % 3, pin_in.ptr, 1, pin_xyzw.ptr, pin_mask.ptr)
+    for s in range(3):
+        rec.wait(s)
+    assert bits_equal(pin_xyzw.array, got["xyzw"]) and bits_equal(pin_mask.array, got["mask"])
+    rec.close()
+
+
+def test_error_paths(built_library, base_calibration):
+    from structured_light_calculation_b200 import capi
+    from structured_light_calculation_b200.configs import CONFIGS, StackConfig
+    cfg = CONFIGS["config1"].with_(width=64, height=32)
+    rec = capi.Reconstructor(cfg, device=0)
+    with pytest.raises(capi.SlcError) as e:     # Calculate* before Init (CCalculation.cpp:176-181)
+        rec.reconstruct(np.zeros((cfg.planes, cfg.height, cfg.width), np.uint8))
+    assert e.value.status == capi.SLC_ERR_NOT_INITIALISED
+    with pytest.raises(capi.SlcError):
+        rec.set_gray_lut(np.zeros(5, np.int16))
+    rec.close()
+    for bad in (StackConfig(64, 32, 1280, 0, 4), StackConfig(64, 32, 1280, 17, 4), StackConfig(64, 32, 1280, 6, 2),
+                StackConfig(64, 32, 32, 6, 4), StackConfig(0, 32, 1280, 6, 4), StackConfig(64, 32, 1280, 6, 66)):
+        with pytest.raises(capi.SlcError) as e:
+            capi.Reconstructor(bad, device=0)
+        assert e.value.status == capi.SLC_ERR_INVALID_ARG
+    with pytest.raises(capi.SlcError):
+        capi.Reconstructor(cfg, device=1000)
+
+
+@pytest.mark.parametrize("name", ["config2", "config3"])
+def test_full_size_properties(built_library, oracle, base_calibration, name):
+    """BASELINE sizes: full parity against the (multi-threaded) oracle on one stack, plus
+    size-independent properties on a batch: batch == single, determinism, ground truth."""
+    from structured_light_calculation_b200 import synth
+    from structured_light_calculation_b200.configs import CONFIGS
+    cfg = CONFIGS[name]
+    cal, scene, planes = make_case(cfg, base_calibration, noise=1.0, seed=77)
+    rec = _reconstructor(cfg, cal, max_batch=3)
+    got = rec.reconstruct(planes, parity=True)
+    want = oracle_run(oracle, cfg, cal, planes, threads=min(8, oracle.max_threads()))
+    errs, perr = check_parity(got, want, cfg)
+    print(f"{name}: max |dx|,|dy|,|dz| = {errs}, phase err {perr:.3e} rad")
+    # decode recovers the rendered ground truth
+    m = want["mask"].astype(bool) & scene.lit & (scene.albedo > 0.2) & (scene.z < cfg.fov_max)
+    assert np.percentile(np.abs(got["xyzw"][0, :, :, 2] - scene.z)[m], 99) < 0.25
+    # batch of 3 (two copies + a different stack) == singles; rerun is deterministic
+    p2 = synth.render_stack(cfg, scene, noise_sigma=2.0, seed=78)
+    batch = rec.reconstruct(np.stack([planes, p2, planes]))
+    assert bits_equal(batch["xyzw"][0], got["xyzw"][0]) and bits_equal(batch["xyzw"][2], got["xyzw"][0])
+    assert bits_equal(batch["mask"][0], got["mask"][0])
+    again = rec.reconstruct(np.stack([planes, p2, planes]))
+    assert bits_equal(again["xyzw"], batch["xyzw"]) and bits_equal(again["mask"], batch["mask"])
+    rec.close()
+
+
+def test_smoke_entry_point(built_library):
+    import __graft_entry__
+    __graft_entry__.smoke()
