@@ -247,7 +247,10 @@ def main():
         d_in[i].copy_(pool_dev[i % len(pool_dev)])
     del pool_dev
     torch.cuda.synchronize()
-    stream = torch.cuda.current_stream()
+    # a dedicated (non-default) torch stream: the kernel is launched on it and the
+    # torch.cuda.Events that time it are recorded on it
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
 
     def step():
         rec.reconstruct_device(d_in.data_ptr(), F, d_xyzw.data_ptr(), d_mask.data_ptr(), None, stream.cuda_stream)

@@ -147,7 +147,7 @@ int slc_synchronize(slc_context *ctx);
  * and CDecodePhase::Decode CDecodePhase.cpp:48-96 inside) + FillCoordinate(0)
  * (CCalculation.cpp:666-771), for n_stacks independent frame sets, as ONE
  * fused kernel launch.  All pointers are DEVICE pointers; cuda_stream is a
- * cudaStream_t passed as void* (NULL = the context's own stream).
+ * cudaStream_t passed as void* (NULL = the context's own stream; the legacy default stream, whose handle is 0, cannot be named).
  * Asynchronous with respect to the host. */
 int slc_reconstruct_device(slc_context *ctx, const uint8_t *d_stack, int32_t n_stacks,
                            float *d_xyzw, uint8_t *d_mask,

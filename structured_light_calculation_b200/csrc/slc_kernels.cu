@@ -387,9 +387,9 @@ struct VecEntry { int G, N, pxt; bool parity; VecKernel fn; };
 // Specialised <G, N> instances: the reference default and BASELINE.json's
 // configurations; anything else runs the generic (0, 0) instance.
 const VecEntry kVecTable[] = {
-    SLC_VEC(16, 6, 4),  SLC_VEC(16, 7, 4),  SLC_VEC(16, 8, 4), SLC_VEC(16, 9, 4),
-    SLC_VEC(16, 8, 8),  SLC_VEC(16, 10, 12), SLC_VEC(16, 0, 0),
-    SLC_VEC(8, 9, 4),   SLC_VEC(8, 8, 8),   SLC_VEC(8, 10, 12), SLC_VEC(8, 0, 0),
+    SLC_VEC(8, 6, 4),   SLC_VEC(8, 7, 4),   SLC_VEC(8, 8, 4),  SLC_VEC(8, 9, 4),
+    SLC_VEC(8, 8, 8),   SLC_VEC(8, 10, 12), SLC_VEC(8, 0, 0),
+    SLC_VEC(16, 9, 4),  SLC_VEC(16, 8, 8),  SLC_VEC(16, 10, 12), SLC_VEC(16, 0, 0),
     SLC_VEC(4, 9, 4),   SLC_VEC(4, 0, 0),
 };
 
@@ -405,7 +405,7 @@ const VecEntry* find_vec(int G, int N, int pxt, bool parity, bool* specialised)
     return generic;
 }
 
-int g_default_pxt = 16;
+int g_default_pxt = 8;
 
 }  // namespace
 
@@ -425,7 +425,8 @@ cudaError_t launch_reconstruct(KParams p, bool force_scalar, cudaStream_t stream
 {
     const bool parity = p.kbin || p.corr || p.phase_pix || p.proj_u;
     int pxt = g_default_pxt;
-    if (!force_scalar && p.W % 16 != 0) pxt = (p.W % 8 == 0) ? 8 : (p.W % 4 == 0 ? 4 : 0);
+    while (pxt >= 4 && p.W % pxt != 0) pxt >>= 1;   // groups must not straddle rows
+    if (pxt < 4) pxt = 0;
     if (!force_scalar && pxt != 0 && vector_kernel_applicable(p, pxt)) {
         bool spec = false;
         const VecEntry* e = find_vec(p.G, p.N, pxt, parity, &spec);

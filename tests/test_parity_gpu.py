@@ -37,11 +37,12 @@ def check_parity(got, want, cfg, stack=0):
     assert bits_equal(got["mask"][stack], want["mask"]), "validity mask"
     T = cfg.phase_period
     # w is ProjectorU rounded once to f32; as a phase that is within 1e-4 rad for every
-    # BASELINE geometry (projector width <= 4096)
+    # BASELINE geometry (projector width <= 4096 with T >= 8: half an f32 ulp of U is
+    # 1.2e-4 px there, x 2 pi / 8 = 9.6e-5 rad).  The exact U is the proj_u plane.
     assert bits_equal(got["xyzw"][stack, :, :, 3], want["proj_u"].astype(np.float32)), "w != f32(U)"
     w = got["xyzw"][stack, :, :, 3].astype(np.float64)
     phase_err = np.abs(w - want["proj_u"]).max() * 2 * np.pi / T
-    if cfg.projector_width <= 4096:
+    if cfg.projector_width <= 4096 and T >= 8:
         assert phase_err <= PHASE_TOL_RAD, f"unwrapped phase error {phase_err} rad"
     tol = XYZ_REL_TOL * (cfg.fov_max - cfg.fov_min)
     errs = {}
@@ -89,7 +90,7 @@ def test_fused_kernel_matches_oracle(built_library, oracle, base_calibration, ca
         assert rec.info().kernel_variant in (0, 1)
         rec.close()
     finally:
-        built_library.slc_tune_pixels_per_thread(16)
+        built_library.slc_tune_pixels_per_thread(8)
     want = oracle_run(oracle, cfg, cal, planes)
     check_parity(got, want, cfg)
     del capi
