@@ -262,12 +262,13 @@ int slc_create(const slc_config* cfg, slc_context** out)
         p.use_mod = cfg->modulation_min > 0.f ? 1 : 0;
     }
     p.z_fp64 = (cfg->flags & SLC_FLAG_Z_FP64) ? 1 : 0;
+    p.magic_one = 0x4B000000u; p.magic_half = 0x4A800000u;
     p.fov_min = cfg->fov_min; p.fov_max = cfg->fov_max;
-    p.fov_min32 = (float)cfg->fov_min; p.fov_max32 = (float)cfg->fov_max;
     {
+        // valid <=> |z - mid| <= half; pixels within `band` of either limit are re-solved in f64
+        const double mid = 0.5 * (cfg->fov_min + cfg->fov_max), half = 0.5 * (cfg->fov_max - cfg->fov_min);
         const double band = 1e-3 * std::fmax(std::fmax(std::fabs(cfg->fov_min), std::fabs(cfg->fov_max)), 1e-30);
-        p.guard_lo_min = (float)(cfg->fov_min - band); p.guard_hi_min = (float)(cfg->fov_min + band);
-        p.guard_lo_max = (float)(cfg->fov_max - band); p.guard_hi_max = (float)(cfg->fov_max + band);
+        p.fov_mid32 = (float)mid; p.fov_half32 = (float)half; p.guard_band = (float)band;
     }
 
 #define SLC_CREATE_CUDA(call)                                                                      \
@@ -387,10 +388,19 @@ int slc_set_calibration(slc_context* ctx, const double cam[9], const double pro[
     p.A32 = (float)(p.A * s); p.B32 = (float)(p.B * s);
     p.c0 = (float)((a0 - au * cu - av * cv) * s); p.cu1 = (float)(au * s); p.cv1 = (float)(av * s);
     p.d0 = (float)((b0 - bu * cu - bv * cv) * s); p.du1 = (float)(bu * s); p.dv1 = (float)(bv * s);
-    p.c0a = (float)((std::fabs(a0) + std::fabs(au * cu) + std::fabs(av * cv)) * std::fabs(s));
-    p.cu1a = std::fabs(p.cu1); p.cv1a = std::fabs(p.cv1);
-    p.d0a = (float)((std::fabs(b0) + std::fabs(bu * cu) + std::fabs(bv * cv)) * std::fabs(s));
-    p.du1a = std::fabs(p.du1); p.dv1a = std::fabs(p.dv1);
+    // Cancellation guards: 2^-8 of the largest magnitude that can be summed into num / den
+    // anywhere in the image for any decodable U (|U| <= PW + 2T).
+    {
+        const double as = std::fabs(s);
+        const double umax = (double)(p.W - 1), vmax = (double)(p.H - 1);
+        const double Umax = (double)ctx->cfg.projector_width + 2.0 * (double)ctx->T;
+        const double Cm = (std::fabs(a0) + std::fabs(au * cu) + std::fabs(av * cv) + std::fabs(au) * umax +
+                           std::fabs(av) * vmax) * as;
+        const double Dm = (std::fabs(b0) + std::fabs(bu * cu) + std::fabs(bv * cv) + std::fabs(bu) * umax +
+                           std::fabs(bv) * vmax) * as;
+        p.num_guard = (float)((std::fabs(p.B * s) * Umax + std::fabs(p.A * s)) / 256.0);
+        p.den_guard = (float)((Cm + Dm * Umax) / 256.0);
+    }
     p.rx1 = (float)(1.0 / fu); p.rx0 = (float)(-cu / fu);    // x = z*(u-cu)/fu  (:766)
     p.ry1 = (float)(1.0 / fv); p.ry0 = (float)(-cv / fv);    // y = z*(v-cv)/fv  (:767)
     ctx->calibrated = true;

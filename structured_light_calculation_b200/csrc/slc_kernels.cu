@@ -43,24 +43,44 @@ template <> struct VecLoad<4> {
     }
 };
 
-// XOR swizzle of the transpose tile (in float4 slots): conflict-free both for the
-// owner-major write (8 lanes, same i) and for the pixel-major read.
-template <int PXT> __device__ __forceinline__ int swizzle(int t) { return PXT == 4 ? ((t >> 1) & 3) : (t & 7); }
+// Transpose tile: each warp owns 32 rows of PXT float4 padded to PXT+1 slots.  With
+// the odd stride both the owner-major write (8 lanes, same i) and the pixel-major
+// read (8 consecutive pixels of one owner) touch 8 distinct 16-byte bank groups,
+// and every address is "per-thread base + compile-time immediate".
+template <int PXT> struct Tile { static constexpr int kStride = PXT + 1; static constexpr int kSlots = 32 * (PXT + 1); };
+
+// MODE 0: no parity planes, reflected Gray code, f32 z with f64 guard band, no modulation test
+// MODE 1: as 0 with the [EXT] modulation test
+// MODE 2: everything decided at run time (parity planes, custom LUT, SLC_FLAG_Z_FP64, modulation)
+template <int MODE, bool Z64>
+__device__ __forceinline__ float solve_pixel(const KParams& p, const RowConst& rc, int kbin, float s, float c,
+                                             float uf, PixelResult& r)
+{
+    const float pix = phase_to_pix(fast_atan2_deg(s, c), p.Tf);
+    bool mod_ok = true;
+    if (MODE == 1 || (MODE == 2 && p.use_mod)) mod_ok = __fadd_rn(__fmul_rn(s, s), __fmul_rn(c, c)) >= p.thr2;
+    unwrap_and_triangulate<MODE == 2, Z64>(p, rc, kbin, pix, mod_ok, uf, r);
+    return pix;
+}
+
+// valid bits b0..b3 -> bytes 0/1
+__device__ __forceinline__ uint32_t spread_bits4(uint32_t b) { return ((b & 0xFu) * 0x00204081u) & 0x01010101u; }
 
 // The fused kernel.  G_T / N_T > 0 bake the digit and step counts in (all plane
 // loops unroll and every load is issued up front); 0 means "read it from p".
-template <int PXT, int G_T, int N_T, bool PARITY>
+template <int PXT, int G_T, int N_T, int MODE>
 __global__ void __launch_bounds__(kBlock)
 reconstruct_vec_kernel(const __grid_constant__ KParams p)
 {
     constexpr int NW = PXT / 4;  // 32-bit words (4 pixels each) per thread
+    constexpr int kStride = Tile<PXT>::kStride;
     extern __shared__ float4 s_tile[];
 
     const int G = G_T > 0 ? G_T : p.G;
     const int N = N_T > 0 ? N_T : p.N;
     const int lane = threadIdx.x & 31;
     const int warp_in_block = threadIdx.x >> 5;
-    float4* tile = s_tile + warp_in_block * (32 * PXT);
+    float4* tile = s_tile + warp_in_block * Tile<PXT>::kSlots;
 
     // grid.y = stack, grid.x covers the stack's pixel groups: a warp tile never straddles stacks
     const int stack = blockIdx.y;
@@ -69,15 +89,13 @@ reconstruct_vec_kernel(const __grid_constant__ KParams p)
     const bool active = g < n_groups;
     const long long out0 = (long long)stack * p.npx;            // first output pixel of the stack
 
-    uint32_t maskw[NW];
-#pragma unroll
-    for (int w = 0; w < NW; w++) maskw[w] = 0;
-
     if (active) {
         const unsigned off = g * PXT;             // first pixel of the group inside the stack
-        const int v = (int)(off / (unsigned)p.W);
-        const int u0 = (int)(off - (unsigned)v * (unsigned)p.W);
-        const uint8_t* base = p.stack + (long long)stack * p.P * p.npx + off;
+        int v, u0;
+        split_row_col(p, off, v, u0);
+        // block-uniform plane base + 32-bit per-thread offset
+        const uint8_t* sbase = p.stack + (long long)stack * p.P * p.npx;
+        auto plane = [&](int q) { return sbase + (long long)q * p.npx + off; };
 
         // ---- a3 + a4: Gray pairs -> per-pixel code bits (CDecodeGray.cpp:155-199) ----
         uint32_t lo[NW], hi[NW];
@@ -85,8 +103,8 @@ reconstruct_vec_kernel(const __grid_constant__ KParams p)
         for (int w = 0; w < NW; w++) { lo[w] = 0; hi[w] = 0; }
         auto gray_bit = [&](int b) {
             uint32_t pa[NW], pb[NW];
-            VecLoad<PXT>::load(base + (long long)(2 * b) * p.npx, pa);
-            VecLoad<PXT>::load(base + (long long)(2 * b + 1) * p.npx, pb);
+            VecLoad<PXT>::load(plane(2 * b), pa);
+            VecLoad<PXT>::load(plane(2 * b + 1), pb);
 #pragma unroll
             for (int w = 0; w < NW; w++) {
                 const uint32_t t = gt_u8x4_msb(pa[w], pb[w]);
@@ -102,33 +120,32 @@ reconstruct_vec_kernel(const __grid_constant__ KParams p)
             for (int b = 0; b < G; b++) gray_bit(b);
         }
         // gray2bin (CDecodeGray.cpp:120-125,200): arithmetic for the reflected code
+        const bool use_lut = (MODE == 2) && (p.lut != nullptr);
         uint32_t bl[NW], bh[NW];
-        if (p.lut == nullptr) {
 #pragma unroll
-            for (int w = 0; w < NW; w++) {
+        for (int w = 0; w < NW; w++) {
+            if (use_lut) { bl[w] = lo[w]; bh[w] = hi[w]; }
+            else {
                 bh[w] = (G > 8) ? prefix_xor_u8x4(hi[w]) : 0u;
                 bl[w] = prefix_xor_u8x4(lo[w]) ^ ((bh[w] & 0x01010101u) * 0xFFu);
             }
-        } else {
-#pragma unroll
-            for (int w = 0; w < NW; w++) { bl[w] = lo[w]; bh[w] = hi[w]; }
         }
 
         // ---- a6: phase images -> (sin, cos) sums (CDecodePhase.cpp:59-65) ----
         float sv[PXT], cv[PXT];
         if (N == 4) {
             uint32_t q0[NW], q1[NW], q2[NW], q3[NW];
-            const uint8_t* ph = base + (long long)(2 * G) * p.npx;
-            VecLoad<PXT>::load(ph, q0);
-            VecLoad<PXT>::load(ph + p.npx, q1);
-            VecLoad<PXT>::load(ph + 2 * p.npx, q2);
-            VecLoad<PXT>::load(ph + 3 * p.npx, q3);
+            VecLoad<PXT>::load(plane(2 * G), q0);
+            VecLoad<PXT>::load(plane(2 * G + 1), q1);
+            VecLoad<PXT>::load(plane(2 * G + 2), q2);
+            VecLoad<PXT>::load(plane(2 * G + 3), q3);
 #pragma unroll
             for (int w = 0; w < NW; w++)
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
-                    sv[4 * w + j] = __fmul_rn(__fsub_rn(u8_magic(q0[w], j), u8_magic(q2[w], j)), 0.5f);
-                    cv[4 * w + j] = __fmul_rn(__fsub_rn(u8_magic(q1[w], j), u8_magic(q3[w], j)), 0.5f);
+                    // (float(I0) - float(I2)) / 2, exact: both operands are 2^22 + I/2
+                    sv[4 * w + j] = __fsub_rn(u8_magic_half(q0[w], j, p.magic_half), u8_magic_half(q2[w], j, p.magic_half));
+                    cv[4 * w + j] = __fsub_rn(u8_magic_half(q1[w], j, p.magic_half), u8_magic_half(q3[w], j, p.magic_half));
                 }
         } else if ((N & 1) == 0) {
             // [EXT] even N: d_k = I_k - I_{k+N/2}; S = sum d_k cos(2 pi k/N), Cc = sum d_k sin(2 pi k/N)
@@ -137,15 +154,14 @@ reconstruct_vec_kernel(const __grid_constant__ KParams p)
             const int half = N >> 1;
             auto phase_pair = [&](int k) {
                 uint32_t qa[NW], qb[NW];
-                const uint8_t* ph = base + (long long)(2 * G + k) * p.npx;
-                VecLoad<PXT>::load(ph, qa);
-                VecLoad<PXT>::load(ph + (long long)half * p.npx, qb);
+                VecLoad<PXT>::load(plane(2 * G + k), qa);
+                VecLoad<PXT>::load(plane(2 * G + k + half), qb);
                 const float ck = p.ck[k], sk = p.sk[k];
 #pragma unroll
                 for (int w = 0; w < NW; w++)
 #pragma unroll
                     for (int j = 0; j < 4; j++) {
-                        const float d = __fsub_rn(u8_magic(qa[w], j), u8_magic(qb[w], j));
+                        const float d = __fsub_rn(u8_magic(qa[w], j, p.magic_one), u8_magic(qb[w], j, p.magic_one));
                         sv[4 * w + j] = __fmaf_rn(d, ck, sv[4 * w + j]);
                         cv[4 * w + j] = __fmaf_rn(d, sk, cv[4 * w + j]);
                     }
@@ -164,65 +180,90 @@ reconstruct_vec_kernel(const __grid_constant__ KParams p)
 #pragma unroll 1
             for (int k = 0; k < N; k++) {
                 uint32_t qa[NW];
-                VecLoad<PXT>::load(base + (long long)(2 * G + k) * p.npx, qa);
+                VecLoad<PXT>::load(plane(2 * G + k), qa);
                 const float ck = p.ck[k], sk = p.sk[k];
 #pragma unroll
                 for (int w = 0; w < NW; w++)
 #pragma unroll
                     for (int j = 0; j < 4; j++) {
-                        const float gk = __fsub_rn(u8_magic(qa[w], j), 8388608.f);
+                        const float gk = __fsub_rn(u8_magic(qa[w], j, p.magic_one), 8388608.f);
                         sv[4 * w + j] = __fmaf_rn(gk, ck, sv[4 * w + j]);
                         cv[4 * w + j] = __fmaf_rn(gk, sk, cv[4 * w + j]);
                     }
             }
         }
 
-        // ---- per pixel: arctan, offset, unwrap, triangulate ----
+        // ---- per pixel: arctan, offset, unwrap, f32 triangulation (branch free) ----
+        const RowConst rc = make_row_const(p, v);
+        const float u0f = (float)u0;
+        float4* trow = tile + lane * kStride;
+        uint32_t validbits = 0, slowbits = 0;
+        const bool z64 = (MODE == 2) && (p.z_fp64 != 0);
 #pragma unroll
         for (int w = 0; w < NW; w++) {
 #pragma unroll
             for (int j = 0; j < 4; j++) {
                 const int i = 4 * w + j;
-                int kbin = (int)((bl[w] >> (8 * j)) & 0xFFu) | (int)(((bh[w] >> (8 * j)) & 0xFFu) << 8);
-                if (p.lut != nullptr) kbin = (int)__ldg(p.lut + kbin);
+                int kbin;
+                if (G > 8 || use_lut)
+                    kbin = (int)__byte_perm(bl[w], bh[w], 0x4400u + (uint32_t)j + ((uint32_t)(4 + j) << 4)) & 0xFFFF;
+                else
+                    kbin = (int)((bl[w] >> (8 * j)) & 0xFFu);
+                if (use_lut) kbin = (int)__ldg(p.lut + kbin);
                 else if (G == 16) kbin = (int)(short)kbin;   // m_gray2bin is `short` (CDecodeGray.h:23)
-                const float s = sv[i], c = cv[i];
-                const float pix = phase_to_pix(fast_atan2_deg(s, c), p.Tf);
-                bool mod_ok = true;
-                if (p.use_mod) mod_ok = __fadd_rn(__fmul_rn(s, s), __fmul_rn(c, c)) >= p.thr2;
+                const float uf = u0f + (float)i;
                 PixelResult r;
-                unwrap_and_triangulate(p, kbin, pix, mod_ok, u0 + i, v, r);
-                // swizzled slot: conflict-free for this write (8 lanes, same i) and for the
-                // transposed read below (same owner lane, 8 consecutive i)
-                tile[lane * PXT + (i ^ swizzle<PXT>(lane))] = make_float4(r.x, r.y, r.z, r.w);
-                maskw[w] |= (uint32_t)r.valid << (8 * j);
-                if (PARITY) {
+                float pix;
+                if (z64) pix = solve_pixel<MODE, true>(p, rc, kbin, sv[i], cv[i], uf, r);
+                else pix = solve_pixel<MODE, false>(p, rc, kbin, sv[i], cv[i], uf, r);
+                // pixels awaiting the f64 re-solve park (gint, pix) in their tile slot
+                trow[i] = make_float4(r.need64 ? r.gint : r.x, r.need64 ? pix : r.y, r.z, r.w);
+                validbits |= (r.valid ? 1u : 0u) << i;
+                slowbits |= (r.need64 ? 1u : 0u) << i;
+                if (MODE == 2) {
                     const long long o = out0 + off + i;
                     if (p.kbin) p.kbin[o] = (int16_t)kbin;
                     if (p.corr) p.corr[o] = (int8_t)r.corr;
-                    if (p.phase_pix) p.phase_pix[o] = r.pix;
-                    if (p.proj_u) p.proj_u[o] = __dadd_rn((double)r.gint, (double)r.pix);
+                    if (p.phase_pix) p.phase_pix[o] = pix;
+                    if (p.proj_u) p.proj_u[o] = __dadd_rn((double)r.gint, (double)pix);
                 }
             }
         }
+        // ---- rare: pixels whose validity f32 cannot decide are re-solved in f64 ----
+        while (slowbits != 0u) {
+            const int i = __ffs((int)slowbits) - 1;
+            slowbits &= slowbits - 1u;
+            const float4 t = trow[i];
+            int ok;
+            trow[i] = resolve_f64(p, t.x, t.y, u0 + i, v, &ok);
+            validbits = (validbits & ~(1u << i)) | ((uint32_t)ok << i);
+        }
         // validity mask: PXT contiguous bytes per thread, 32*PXT per warp
         uint8_t* mptr = p.mask + out0 + off;
-        if constexpr (PXT == 16) st_stream_u4(mptr, make_uint4(maskw[0], maskw[1], maskw[2], maskw[3]));
-        else if constexpr (PXT == 8) st_stream_u2(mptr, make_uint2(maskw[0], maskw[1]));
-        else *reinterpret_cast<uint32_t*>(mptr) = maskw[0];
+        if constexpr (PXT == 16)
+            st_stream_u4(mptr, make_uint4(spread_bits4(validbits), spread_bits4(validbits >> 4),
+                                          spread_bits4(validbits >> 8), spread_bits4(validbits >> 12)));
+        else if constexpr (PXT == 8)
+            st_stream_u2(mptr, make_uint2(spread_bits4(validbits), spread_bits4(validbits >> 4)));
+        else
+            st_stream_u1(mptr, spread_bits4(validbits));
     }
 
-    // ---- transposed, fully coalesced float4 stores ----
+    // ---- transposed, fully coalesced float4 stores: 512 contiguous bytes per instruction ----
     __syncwarp();
     const unsigned px0 = (blockIdx.x * kBlock + (threadIdx.x & ~31u)) * PXT;  // warp's first pixel in the stack
     const unsigned stack_px = n_groups * PXT;
-    float4* out = p.xyzw + out0;
+    float4* outp = p.xyzw + out0 + px0 + lane;
+    // pixel it*32 + lane belongs to owner (it*32 + lane) / PXT, element (it*32 + lane) % PXT
+    const float4* tsrc = tile + (lane / PXT) * kStride + (lane % PXT);
+    if (px0 + 32u * PXT <= stack_px) {
 #pragma unroll
-    for (int it = 0; it < PXT; it++) {
-        const int pidx = it * 32 + lane;                       // pixel inside the warp tile
-        const int owner = pidx / PXT, i = pidx % PXT;
-        const float4 val = tile[owner * PXT + (i ^ swizzle<PXT>(owner))];
-        if (px0 + pidx < stack_px) st_stream_f4(out + px0 + pidx, val);
+        for (int it = 0; it < PXT; it++)
+            st_stream_f4(outp + it * 32, tsrc[(it * 32 / PXT) * kStride]);
+    } else {
+#pragma unroll
+        for (int it = 0; it < PXT; it++)
+            if (px0 + it * 32 + lane < stack_px) st_stream_f4(outp + it * 32, tsrc[(it * 32 / PXT) * kStride]);
     }
 }
 
@@ -274,18 +315,25 @@ reconstruct_scalar_kernel(const __grid_constant__ KParams p)
             c = __fmaf_rn(gk, p.sk[k], c);
         }
     }
-    const float pix = phase_to_pix(fast_atan2_deg(s, c), p.Tf);
+    // the scalar kernel keeps the compiler's full-range div.rn (it doubles as a cross-check
+    // of the vector kernel's safe-range divisions)
+    const float pix = phase_to_pix<true>(fast_atan2_deg<true>(s, c), p.Tf);
     bool mod_ok = true;
     if (p.use_mod) mod_ok = __fadd_rn(__fmul_rn(s, s), __fmul_rn(c, c)) >= p.thr2;
     PixelResult r;
-    unwrap_and_triangulate(p, kbin, pix, mod_ok, u, v, r);
-    p.xyzw[idx] = make_float4(r.x, r.y, r.z, r.w);
-    p.mask[idx] = (uint8_t)r.valid;
+    const RowConst rc = make_row_const(p, v);
+    if (p.z_fp64) unwrap_and_triangulate<true, true>(p, rc, kbin, pix, mod_ok, (float)u, r);
+    else unwrap_and_triangulate<true, false>(p, rc, kbin, pix, mod_ok, (float)u, r);
+    float4 outv = make_float4(r.x, r.y, r.z, r.w);
+    int ok = r.valid ? 1 : 0;
+    if (r.need64) outv = resolve_f64(p, r.gint, pix, u, v, &ok);
+    p.xyzw[idx] = outv;
+    p.mask[idx] = (uint8_t)ok;
     if (PARITY) {
         if (p.kbin) p.kbin[idx] = (int16_t)kbin;
         if (p.corr) p.corr[idx] = (int8_t)r.corr;
-        if (p.phase_pix) p.phase_pix[idx] = r.pix;
-        if (p.proj_u) p.proj_u[idx] = __dadd_rn((double)r.gint, (double)r.pix);
+        if (p.phase_pix) p.phase_pix[idx] = pix;
+        if (p.proj_u) p.proj_u[idx] = __dadd_rn((double)r.gint, (double)pix);
     }
 }
 
@@ -343,7 +391,7 @@ decode_phase_kernel(const __grid_constant__ KParams p, const uint8_t* __restrict
             c = __fmaf_rn(gk, p.sk[k], c);
         }
     }
-    phase_pix[idx] = (double)phase_to_pix(fast_atan2_deg(s, c), p.Tf);
+    phase_pix[idx] = (double)phase_to_pix<true>(fast_atan2_deg<true>(s, c), p.Tf);
     if (mod_out) {
         const bool ok = !p.use_mod || (__fadd_rn(__fmul_rn(s, s), __fmul_rn(c, c)) >= p.thr2);
         mod_out[idx] = ok ? 1 : 0;
@@ -378,26 +426,27 @@ triangulate_kernel(const __grid_constant__ KParams p, const double* __restrict__
 // ---------------------------------------------------------------------------
 using VecKernel = void (*)(const KParams);
 
-struct VecEntry { int G, N, pxt; bool parity; VecKernel fn; };
+struct VecEntry { int G, N, pxt, mode; VecKernel fn; };
 
 #define SLC_VEC(PXT, G, N) \
-    { G, N, PXT, false, reconstruct_vec_kernel<PXT, G, N, false> }, \
-    { G, N, PXT, true,  reconstruct_vec_kernel<PXT, G, N, true> }
+    { G, N, PXT, 0, reconstruct_vec_kernel<PXT, G, N, 0> }, \
+    { G, N, PXT, 1, reconstruct_vec_kernel<PXT, G, N, 1> }, \
+    { G, N, PXT, 2, reconstruct_vec_kernel<PXT, G, N, 2> }
 
 // Specialised <G, N> instances: the reference default and BASELINE.json's
 // configurations; anything else runs the generic (0, 0) instance.
 const VecEntry kVecTable[] = {
-    SLC_VEC(8, 6, 4),   SLC_VEC(8, 7, 4),   SLC_VEC(8, 8, 4),  SLC_VEC(8, 9, 4),
+    SLC_VEC(8, 6, 4),   SLC_VEC(8, 7, 4),   SLC_VEC(8, 9, 4),
     SLC_VEC(8, 8, 8),   SLC_VEC(8, 10, 12), SLC_VEC(8, 0, 0),
-    SLC_VEC(16, 9, 4),  SLC_VEC(16, 8, 8),  SLC_VEC(16, 10, 12), SLC_VEC(16, 0, 0),
+    SLC_VEC(16, 9, 4),  SLC_VEC(16, 0, 0),
     SLC_VEC(4, 9, 4),   SLC_VEC(4, 0, 0),
 };
 
-const VecEntry* find_vec(int G, int N, int pxt, bool parity, bool* specialised)
+const VecEntry* find_vec(int G, int N, int pxt, int mode, bool* specialised)
 {
     const VecEntry* generic = nullptr;
     for (const VecEntry& e : kVecTable) {
-        if (e.pxt != pxt || e.parity != parity) continue;
+        if (e.pxt != pxt || e.mode != mode) continue;
         if (e.G == G && e.N == N) { *specialised = true; return &e; }
         if (e.G == 0 && e.N == 0) generic = &e;
     }
@@ -424,16 +473,20 @@ bool vector_kernel_applicable(const KParams& p, int pxt)
 cudaError_t launch_reconstruct(KParams p, bool force_scalar, cudaStream_t stream, LaunchInfo* info)
 {
     const bool parity = p.kbin || p.corr || p.phase_pix || p.proj_u;
+    const int mode = (parity || p.lut != nullptr || p.z_fp64) ? 2 : (p.use_mod ? 1 : 0);
+    // v = off / W by multiplication: exact while off * W < 2^40 (split_row_col)
+    p.row_magic = ((unsigned long long)p.npx * (unsigned long long)p.W < (1ull << 40))
+                      ? ((1ull << 40) / (unsigned long long)p.W + 1ull) : 0ull;
     int pxt = g_default_pxt;
     while (pxt >= 4 && p.W % pxt != 0) pxt >>= 1;   // groups must not straddle rows
     if (pxt < 4) pxt = 0;
     if (!force_scalar && pxt != 0 && vector_kernel_applicable(p, pxt)) {
         bool spec = false;
-        const VecEntry* e = find_vec(p.G, p.N, pxt, parity, &spec);
+        const VecEntry* e = find_vec(p.G, p.N, pxt, mode, &spec);
         if (e != nullptr) {
             p.n_groups = p.npx / pxt;
             const long long blocks = (p.n_groups + kBlock - 1) / kBlock;
-            const int smem = kBlock * pxt * (int)sizeof(float4);
+            const int smem = (kBlock / 32) * 32 * (pxt + 1) * (int)sizeof(float4);
             if (blocks > 0x7fffffffLL || p.n_stacks > 65535 || p.npx > 0x7fffffffLL)
                 return cudaErrorInvalidConfiguration;
             cudaError_t err = cudaFuncSetAttribute(e->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
