@@ -206,8 +206,8 @@ def main():
     ap.add_argument("--batch", type=int, default=256, help="frame sets per step (device-resident batch)")
     ap.add_argument("--pool", type=int, default=4, help="distinct rendered stacks tiled into the batch")
     ap.add_argument("--e2e-stacks", type=int, default=24, help="frame sets per end-to-end step")
-    ap.add_argument("--e2e-chunk", type=int, default=4, help="frame sets per upload/launch/download chunk")
-    ap.add_argument("--e2e-slots", type=int, default=3)
+    ap.add_argument("--e2e-chunk", type=int, default=2, help="frame sets per upload/launch/download chunk")
+    ap.add_argument("--e2e-slots", type=int, default=4)
     ap.add_argument("--pxt", type=int, default=0, help="tuning: pixels per thread (4/8/16)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ref-stacks-per-step", type=int, default=2)

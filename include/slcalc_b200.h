@@ -183,6 +183,12 @@ int slc_decode_phase_host(slc_context *ctx, const uint8_t *h_phase_planes,
 int slc_triangulate_host(slc_context *ctx, const double *h_proj_u,
                          float *h_xyzw, uint8_t *h_mask);
 
+/* Parity hook for the arctangent of CDecodePhase.cpp:67-75 alone: evaluates
+ * cvFastArctan(sin, cos) in degrees and the in-period offset on the device, with
+ * exactly the arithmetic of the fused kernel, for n caller-supplied pairs. */
+int slc_eval_phase_host(slc_context *ctx, const float *h_sin, const float *h_cos, int64_t n,
+                        float *h_deg, float *h_pix);
+
 /* ---- measurement ------------------------------------------------------ */
 /* Launch the fused kernel `iters` times back to back on the context stream and
  * report the average duration per launch in milliseconds, measured with CUDA

@@ -67,6 +67,41 @@ void slo_fast_atan2_array(const float *y, const float *x, float *out, size_t n)
     for (size_t i = 0; i < n; i++) out[i] = slo_fast_atan2(y[i], x[i]);
 }
 
+/* CDecodePhase.cpp:69-75 for an array of angles (degrees) */
+void slo_phase_pix_array(const float *deg, float *pix, size_t n, int m_pixPeroid)
+{
+    for (size_t i = 0; i < n; i++) {
+        float p = (deg[i]) / (360) * (double)(m_pixPeroid);
+        p += 0.5;
+        if (p > m_pixPeroid) p -= m_pixPeroid;
+        pix[i] = p;
+    }
+}
+
+/* Property the CUDA kernel relies on (csrc/slc_device.cuh div360_rn): for every
+ * f32 x in [lo, hi] the FMA sequence q0 = x*y, r = fma(-q0, 360, x),
+ * q = fma(r, y, q0) with y = RN(1/360) equals the IEEE quotient x / 360.
+ * Returns the number of mismatches. */
+unsigned long long slo_check_div360(float lo, float hi, unsigned long long *checked)
+{
+    const float y = 1.0f / 360.0f;
+    uint32_t ulo, uhi;
+    unsigned long long bad = 0, n = 0;
+    memcpy(&ulo, &lo, 4);
+    memcpy(&uhi, &hi, 4);
+    for (uint32_t u = ulo; u <= uhi; u++) {
+        float x;
+        memcpy(&x, &u, 4);
+        const float q0 = x * y;
+        const float r = fmaf(-q0, 360.f, x);
+        const float q = fmaf(r, y, q0);
+        if (q != x / 360.f) bad++;
+        n++;
+    }
+    if (checked) *checked = n;
+    return bad;
+}
+
 void slo_default_gray_lut(int n_digits, int16_t *lut)
 {
     /* Patterns/vGrayCode.txt rows are "bin gray" with gray = bin^(bin>>1);

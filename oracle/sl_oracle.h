@@ -67,6 +67,8 @@ typedef struct {
 
 /* OpenCV cv::fastAtan2(y, x) (== cvFastArctan) restated; degrees in [0,360). */
 float slo_fast_atan2(float y, float x);
+void slo_phase_pix_array(const float *deg, float *pix, size_t n, int m_pixPeroid);
+unsigned long long slo_check_div360(float lo, float hi, unsigned long long *checked);
 void slo_fast_atan2_array(const float *y, const float *x, float *out, size_t n);
 
 /* gray2bin table for a reflected binary Gray code with n_digits bits, in the

@@ -76,6 +76,9 @@ def lib():
         L.slo_fast_atan2.restype = C.c_float
         L.slo_fast_atan2.argtypes = [C.c_float, C.c_float]
         L.slo_fast_atan2_array.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
+        L.slo_phase_pix_array.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]
+        L.slo_check_div360.argtypes = [C.c_float, C.c_float, C.POINTER(C.c_ulonglong)]
+        L.slo_check_div360.restype = C.c_ulonglong
         L.slo_default_gray_lut.argtypes = [C.c_int, C.c_void_p]
         L.slo_gray_period.argtypes = [C.POINTER(SloConfig)]
         L.slo_phase_period.argtypes = [C.POINTER(SloConfig)]
@@ -118,6 +121,19 @@ def fast_atan2(y, x) -> np.ndarray:
     out = np.empty(yb.shape, dtype=np.float32)
     L.slo_fast_atan2_array(yb.ctypes.data, xb.ctypes.data, out.ctypes.data, out.size)
     return out
+
+
+def phase_pix(deg, period: int) -> np.ndarray:
+    deg = np.ascontiguousarray(deg, dtype=np.float32)
+    out = np.empty(deg.shape, np.float32)
+    lib().slo_phase_pix_array(deg.ctypes.data, out.ctypes.data, out.size, int(period))
+    return out
+
+
+def check_div360(lo: float, hi: float):
+    n = C.c_ulonglong()
+    bad = lib().slo_check_div360(lo, hi, C.byref(n))
+    return int(bad), int(n.value)
 
 
 def default_gray_lut(n_digits: int) -> np.ndarray:

@@ -111,6 +111,7 @@ def load_library():
     L.slc_decode_gray_host.argtypes = [vp, vp, vp, vp]
     L.slc_decode_phase_host.argtypes = [vp, vp, vp, vp]
     L.slc_triangulate_host.argtypes = [vp, vp, vp, vp]
+    L.slc_eval_phase_host.argtypes = [vp, vp, vp, C.c_int64, vp, vp]
     L.slc_time_reconstruct_device.argtypes = [vp, vp, i32, vp, vp, i32, C.POINTER(C.c_float)]
     L.slc_launch_count.argtypes = [vp]
     L.slc_launch_count.restype = C.c_int64
@@ -297,6 +298,17 @@ class Reconstructor:
         mask = np.empty((cfg.height, cfg.width), np.uint8)
         self._check(self.lib.slc_triangulate_host(self.h, proj_u.ctypes.data, xyzw.ctypes.data, mask.ctypes.data))
         return xyzw, mask
+
+    def eval_phase(self, s: np.ndarray, c: np.ndarray):
+        """Device cvFastArctan + in-period offset for arbitrary (sin, cos) sums."""
+        s = np.ascontiguousarray(s, dtype=np.float32).reshape(-1)
+        c = np.ascontiguousarray(c, dtype=np.float32).reshape(-1)
+        assert s.size == c.size
+        deg = np.empty(s.size, np.float32)
+        pix = np.empty(s.size, np.float32)
+        self._check(self.lib.slc_eval_phase_host(self.h, s.ctypes.data, c.ctypes.data, s.size, deg.ctypes.data,
+                                                 pix.ctypes.data))
+        return deg, pix
 
     # -- measurement -------------------------------------------------------
     def time_device(self, d_stack: int, n_stacks: int, d_xyzw: int, d_mask: int, iters: int) -> float:

@@ -632,6 +632,31 @@ int slc_triangulate_host(slc_context* ctx, const double* h_proj_u, float* h_xyzw
     return SLC_OK;
 }
 
+int slc_eval_phase_host(slc_context* ctx, const float* h_sin, const float* h_cos, int64_t n, float* h_deg,
+                        float* h_pix)
+{
+    if (!ctx) return SLC_ERR_INVALID_ARG;
+    if (!h_sin || !h_cos || !h_deg || !h_pix || n < 0) return fail(ctx, SLC_ERR_INVALID_ARG, "NULL buffer or n < 0");
+    if (n == 0) return SLC_OK;
+    SLC_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+    const size_t bytes = (size_t)n * sizeof(float);
+    int rc = ensure_scratch(ctx, &ctx->d_scratch_in, &ctx->scratch_in_bytes, 2 * bytes);
+    if (rc == SLC_OK) rc = ensure_scratch(ctx, &ctx->d_scratch_out, &ctx->scratch_out_bytes, 2 * bytes);
+    if (rc != SLC_OK) return rc;
+    float* d_s = (float*)ctx->d_scratch_in;
+    float* d_c = d_s + n;
+    float* d_deg = (float*)ctx->d_scratch_out;
+    float* d_pix = d_deg + n;
+    SLC_CUDA(ctx, cudaMemcpyAsync(d_s, h_sin, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    SLC_CUDA(ctx, cudaMemcpyAsync(d_c, h_cos, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    SLC_CUDA(ctx, slc::launch_eval_phase(d_s, d_c, n, ctx->kp.Tf, d_deg, d_pix, ctx->stream));
+    ctx->launches++;
+    SLC_CUDA(ctx, cudaMemcpyAsync(h_deg, d_deg, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    SLC_CUDA(ctx, cudaMemcpyAsync(h_pix, d_pix, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    SLC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SLC_OK;
+}
+
 /* ---- measurement ------------------------------------------------------ */
 int slc_time_reconstruct_device(slc_context* ctx, const uint8_t* d_stack, int32_t n_stacks, float* d_xyzw,
                                 uint8_t* d_mask, int32_t iters, float* ms_per_launch)

@@ -423,6 +423,19 @@ triangulate_kernel(const __grid_constant__ KParams p, const double* __restrict__
     mask[idx] = (uint8_t)valid;
 }
 
+// Parity hook: the vector kernel's arctangent + offset arithmetic (safe-range
+// divisions) on caller-supplied (sin, cos) sums.
+__global__ void __launch_bounds__(kBlock)
+eval_phase_kernel(const float* __restrict__ s, const float* __restrict__ c, long long n, float Tf,
+                  float* __restrict__ deg, float* __restrict__ pix)
+{
+    const long long idx = (long long)blockIdx.x * kBlock + threadIdx.x;
+    if (idx >= n) return;
+    const float a = fast_atan2_deg<false>(s[idx], c[idx]);
+    deg[idx] = a;
+    pix[idx] = phase_to_pix<false>(a, Tf);
+}
+
 // ---------------------------------------------------------------------------
 using VecKernel = void (*)(const KParams);
 
@@ -538,6 +551,15 @@ cudaError_t launch_decode_phase(const KParams& p, const uint8_t* d_planes, doubl
 {
     const long long blocks = (p.npx + kBlock - 1) / kBlock;
     decode_phase_kernel<<<(unsigned)blocks, kBlock, 0, stream>>>(p, d_planes, d_phase_pix, d_mod_ok);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_eval_phase(const float* d_s, const float* d_c, long long n, float Tf, float* d_deg, float* d_pix,
+                              cudaStream_t stream)
+{
+    const long long blocks = (n + kBlock - 1) / kBlock;
+    if (blocks <= 0) return cudaSuccess;
+    eval_phase_kernel<<<(unsigned)blocks, kBlock, 0, stream>>>(d_s, d_c, n, Tf, d_deg, d_pix);
     return cudaGetLastError();
 }
 

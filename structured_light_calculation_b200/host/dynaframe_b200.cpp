@@ -473,8 +473,8 @@ bool CCalculation::Result(std::string fileName, int i)
     for (int u = 0; u < sp_.CAMERA_RESLINE; u++) {
         for (int v = 0; v < sp_.CAMERA_RESROW; v++) {
             const float* p = &m_xyzw.at<float>(v, 4 * u);
-            const double valZ = p[2];
-            if ((valZ < sp_.FOV_MIN_DISTANCE) || (valZ > sp_.FOV_MAX_DISTANCE)) continue;
+            // the reference filters on the f64 z (:341-345); the mask is that same f64 decision
+            if (m_mask.at<uint8_t>(v, u) == 0) continue;
             file << (double)p[0] << ' ';
             file << (double)p[1] << ' ';
             file << (double)p[2] << std::endl;

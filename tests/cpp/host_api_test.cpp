@@ -1,0 +1,116 @@
+// host_api_test.cpp -- reference-style host code on the re-hosted classes.
+//
+// Mirrors what main.cpp:42-45 and CCalculation::FillFirstProjectorU
+// (CCalculation.cpp:536-559) do: feed Gray and phase images to the decoders,
+// Decode(), GetResult(); Init(), CalculateFirst(), Result().  Driven by
+// tests/test_cpp_host_api.py, which supplies the planes and checks the outputs
+// against the CPU oracle.
+//
+//   host_api_test <dir> <W> <H> <PW> <G> <N>
+// reads  <dir>/planes.u8 (2G+N planes), <dir>/parameters.yml, <dir>/vGrayCode.txt
+// writes <dir>/gray.f64 <dir>/phase.f64 <dir>/xyzw.f32 <dir>/mask.u8 <dir>/projU.f64 <dir>/cloud.txt
+#include <cstdio>
+#include <cstdlib>
+#include <fstream>
+#include <string>
+#include <vector>
+
+#include "dynaframe_b200.hpp"
+
+using namespace dynaframe;
+
+static bool write_file(const std::string& path, const void* data, size_t bytes)
+{
+    std::ofstream f(path, std::ios::binary);
+    f.write(static_cast<const char*>(data), (std::streamsize)bytes);
+    return (bool)f;
+}
+
+#define CHECK(cond)                                                        \
+    do {                                                                   \
+        if (!(cond)) {                                                     \
+            std::fprintf(stderr, "CHECK failed line %d: %s\n", __LINE__, #cond); \
+            return 1;                                                      \
+        }                                                                  \
+    } while (0)
+
+int main(int argc, char** argv)
+{
+    if (argc < 7) { std::fprintf(stderr, "usage\n"); return 2; }
+    const std::string dir = argv[1];
+    StaticParameters sp;
+    sp.CAMERA_RESLINE = std::atoi(argv[2]);
+    sp.CAMERA_RESROW = std::atoi(argv[3]);
+    sp.PROJECTOR_RESLINE = std::atoi(argv[4]);
+    sp.GRAY_V_NUMDIGIT = std::atoi(argv[5]);
+    sp.PHASE_NUMDIGIT = std::atoi(argv[6]);
+    sp.DATA_PATH = dir + "/";
+    const int W = sp.CAMERA_RESLINE, H = sp.CAMERA_RESROW, G = sp.GRAY_V_NUMDIGIT, N = sp.PHASE_NUMDIGIT;
+    const size_t npx = (size_t)W * H;
+
+    std::vector<uint8_t> planes((size_t)(2 * G + N) * npx);
+    {
+        std::ifstream f(dir + "/planes.u8", std::ios::binary);
+        f.read(reinterpret_cast<char*>(planes.data()), (std::streamsize)planes.size());
+        CHECK((size_t)f.gcount() == planes.size());
+    }
+    auto plane = [&](int i) { return Mat(H, W, CV_8UC1, planes.data() + (size_t)i * npx); };
+
+    // ---- error behaviour of the decoder objects (CDecodeGray.cpp:26-40, CDecodePhase.cpp:109-123)
+    {
+        CDecodeGray g(sp);
+        CHECK(!g.SetMat(0, plane(0)));                 // before SetNumDigit
+        CHECK(!g.SetNumDigit(0, true));
+        CHECK(!g.SetNumDigit(17, true));
+        CDecodePhase ph(sp);
+        CHECK(!ph.SetMat(0, plane(0)));                // before SetNumMat
+        CHECK(!ph.SetNumMat(0, 16));
+    }
+
+    // ---- CDecodeGray: CCalculation.cpp:537-546
+    CDecodeGray gray(sp);
+    CHECK(gray.SetNumDigit(G, true));
+    CHECK(gray.SetMatFileName(dir + "/", "missing.txt"));
+    for (int i = 0; i < 2 * G; i++) CHECK(gray.SetMat(i, plane(i)));
+    CHECK(!gray.Decode());                             // "Gray Decode->Open file error."
+    CHECK(LastErrorMessage() == "Gray Decode->Open file error.");
+    CHECK(gray.SetMatFileName(dir + "/", "vGrayCode.txt"));
+    CHECK(gray.Decode());
+    Mat vGrayMat = gray.GetResult();
+    CHECK(vGrayMat.type() == CV_64FC1 && vGrayMat.rows == H && vGrayMat.cols == W);
+    CHECK(write_file(dir + "/gray.f64", vGrayMat.ptr(), npx * 8));
+
+    // ---- CDecodePhase: CCalculation.cpp:550-559
+    const int v_pixPeriod = sp.PROJECTOR_RESLINE / (1 << (G - 1));
+    CDecodePhase phase(sp);
+    CHECK(phase.SetNumMat(N, v_pixPeriod));
+    for (int i = 0; i < N; i++) CHECK(phase.SetMat(i, plane(2 * G + i)));
+    CHECK(phase.Decode());
+    Mat vPhaseMat = phase.GetResult();
+    CHECK(write_file(dir + "/phase.f64", vPhaseMat.ptr(), npx * 8));
+    // GetResult hands out deep copies (CDecodePhase.cpp:99-104)
+    vPhaseMat.at<double>(0, 0) = -1.0;
+    CHECK(phase.GetResult().at<double>(0, 0) != -1.0);
+
+    // ---- CCalculation: main.cpp:42-44
+    CCalculation calc(sp);
+    CHECK(!calc.CalculateFirst());                     // before Init (CCalculation.cpp:176-181)
+    calc.SetParameterFile("parameters.yml");
+    calc.SetGrayCodeFile(dir + "/", "vGrayCode.txt");
+    CHECK(calc.Init());
+    CHECK(!calc.Init());                               // twice (CCalculation.cpp:80-83)
+    for (int i = 0; i < 2 * G; i++) CHECK(calc.Sensor()->StoreDatas(0, i, plane(i)));
+    for (int i = 0; i < N; i++) CHECK(calc.Sensor()->StoreDatas(1, i, plane(2 * G + i)));
+    CHECK(calc.CalculateFirst());
+    CHECK(!calc.CalculateOther());                     // dynamic frames: not on this path
+    CHECK(calc.PointMap().type() == CV_32FC4 && calc.ValidMask().type() == CV_8UC1);
+    CHECK(write_file(dir + "/xyzw.f32", calc.PointMap().ptr(), npx * 16));
+    CHECK(write_file(dir + "/mask.u8", calc.ValidMask().ptr(), npx));
+    Mat U = calc.GetProjectorU();
+    CHECK(write_file(dir + "/projU.f64", U.ptr(), npx * 8));
+    CHECK(calc.Result(dir + "/cloud.txt", 0));
+    Mat z = calc.GetZ();
+    CHECK(z.type() == CV_64FC1 && z.at<double>(H / 2, W / 2) == (double)calc.PointMap().at<float>(H / 2, 4 * (W / 2) + 2));
+    std::printf("host_api_test ok\n");
+    return 0;
+}

@@ -179,3 +179,12 @@ def test_invalid_configurations_rejected(oracle):
         with pytest.raises(ValueError):
             oracle.reconstruct(cfg, cal, np.zeros((2 * max(kw["gray_digits"], 0) + kw["phase_steps"], 1, 16), np.uint8))
     del planes
+
+
+def test_div360_fma_sequence_equals_ieee_division(oracle):
+    """The CUDA kernel divides the angle by 360 with q0 = x*y, r = fma(-q0, 360, x),
+    q = fma(r, y, q0), y = RN(1/360) (csrc/slc_device.cuh div360_rn).  Exhaustive proof that
+    this equals the reference's IEEE `x / 360` for every f32 angle in [1e-30, 360.5]."""
+    bad, n = oracle.check_div360(1e-30, 360.5)
+    assert n > 900_000_000 and bad == 0
+    assert np.float32(1.0) / np.float32(360.0) == np.float32(float.fromhex("0x1.6c16c2p-9"))

@@ -58,6 +58,14 @@ def check_parity(got, want, cfg, stack=0):
     return errs, phase_err
 
 
+def check_fast_modes(rec, planes, got_parity):
+    """The kernel instances without parity planes (MODE 0 / 1, the ones bench.py times)
+    must produce exactly what the parity-checked instance (MODE 2) produced."""
+    fast = rec.reconstruct(planes, parity=False)
+    assert bits_equal(fast["xyzw"], got_parity["xyzw"]), "MODE 0/1 xyzw differs from MODE 2"
+    assert bits_equal(fast["mask"], got_parity["mask"]), "MODE 0/1 mask differs from MODE 2"
+
+
 CASES = [
     # (name, G, N, PW, W, H, noise, modulation)
     ("ref_default", 6, 4, 1280, 256, 96, 1.0, 0.0),
@@ -88,6 +96,7 @@ def test_fused_kernel_matches_oracle(built_library, oracle, base_calibration, ca
         got = rec.reconstruct(planes, parity=True)
         assert rec.launch_count() == 1
         assert rec.info().kernel_variant in (0, 1)
+        check_fast_modes(rec, planes, got)
         rec.close()
     finally:
         built_library.slc_tune_pixels_per_thread(8)
@@ -190,10 +199,57 @@ def test_all_4step_phase_inputs_bit_exact(built_library, oracle):
         planes[2 * b + 1] = np.where(bit, 40, 180)
     rec = _reconstructor(cfg, cal)
     got = rec.reconstruct(planes, parity=True)
+    check_fast_modes(rec, planes, got)
     rec.close()
     want = oracle_run(oracle, cfg, cal, planes)
     check_parity(got, want, cfg)
     assert set(np.unique(want["corr"])) == {-1, 0, 1}
+
+
+def test_device_arctan_and_offset_bit_exact(built_library, oracle):
+    """cvFastArctan + the offset arithmetic on the device (safe-range divisions, no FCHK
+    slow path) against the oracle's IEEE path: every 4-step pair, every N-step-like sum of
+    u8 differences we can draw, plus adversarial magnitudes."""
+    from structured_light_calculation_b200 import capi
+    from structured_light_calculation_b200.configs import StackConfig
+    rng = np.random.Generator(np.random.PCG64(2024))
+    v = (np.arange(-255, 256) / 2).astype(np.float32)
+    s4, c4 = [a.ravel() for a in np.meshgrid(v, v, indexing="ij")]
+    # N-step sums: sum_k d_k * f32(cos(2 pi k / N)) with integer d_k in [-255, 255]
+    parts_s, parts_c = [s4], [c4]
+    for N in (6, 8, 12, 16, 5, 7):
+        n_terms = N // 2 if N % 2 == 0 else N
+        k = np.arange(n_terms)
+        ck = np.cos(2 * np.pi * k / N).astype(np.float32)
+        sk = np.sin(2 * np.pi * k / N).astype(np.float32)
+        d = rng.integers(-255, 256, (400_000, n_terms)).astype(np.float32)
+        ss = np.zeros(d.shape[0], np.float32)
+        cc = np.zeros(d.shape[0], np.float32)
+        for j in range(n_terms):   # f32 accumulation (rounding differs from fmaf; any f32 value is fair input)
+            ss = (ss + d[:, j] * ck[j]).astype(np.float32)
+            cc = (cc + d[:, j] * sk[j]).astype(np.float32)
+        parts_s.append(ss)
+        parts_c.append(cc)
+    # adversarial: tiny / huge ratios, equal magnitudes, zeros, signed zeros
+    extra = np.array([0.0, -0.0, 1e-7, -1e-7, 1e-3, 0.5, 1.0, 127.5, 255.0, 16320.0, -16320.0, 3e-5, 65000.0],
+                     np.float32)
+    es, ec = [a.ravel() for a in np.meshgrid(extra, extra, indexing="ij")]
+    parts_s.append(es)
+    parts_c.append(ec)
+    log_s = (rng.choice([-1, 1], 500_000) * np.exp(rng.uniform(np.log(1e-6), np.log(7e4), 500_000))).astype(np.float32)
+    log_c = (rng.choice([-1, 1], 500_000) * np.exp(rng.uniform(np.log(1e-6), np.log(7e4), 500_000))).astype(np.float32)
+    parts_s.append(log_s)
+    parts_c.append(log_c)
+    s = np.concatenate(parts_s)
+    c = np.concatenate(parts_c)
+    for T in (40, 10, 8, 16, 2):
+        cfg = StackConfig(64, 16, T, 1, 4)      # G = 1: phase period == projector width == T
+        rec = capi.Reconstructor(cfg, device=0)
+        deg, pix = rec.eval_phase(s, c)
+        rec.close()
+        want_deg = oracle.fast_atan2(s, c)
+        assert bits_equal(deg, want_deg), f"arctan differs in {(deg.view(np.uint32) != want_deg.view(np.uint32)).sum()} of {s.size}"
+        assert bits_equal(pix, oracle.phase_pix(want_deg, T)), "offset arithmetic differs"
 
 
 def test_fov_boundary_mask_is_bit_exact(built_library, oracle, base_calibration):
