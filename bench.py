@@ -126,6 +126,15 @@ class ClockSampler:
         return out
 
 
+def host_threads() -> int:
+    """Host threads the CPU path may use: the cores this process may run on (torchrun
+    exports OMP_NUM_THREADS=1, which the oracle's explicit num_threads() overrides)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def build_inputs(cfg, pool: int):
     base = load_calibration(os.path.join(ROOT, "tests", "golden", "Result.yml"))
     cal = synth.synthetic_calibration(cfg, base)
@@ -140,7 +149,7 @@ def run_reference(args, cfg):
     if rank != 0:
         return 0
     from oracle import sl_oracle as O
-    threads = O.max_threads()
+    threads = host_threads()
     cal, _, stacks = build_inputs(cfg, 1)
     ocfg = O.make_config(cfg.width, cfg.height, cfg.projector_width, cfg.gray_digits, cfg.phase_steps,
                          cfg.fov_min, cfg.fov_max, cfg.modulation_min, threads)
@@ -177,7 +186,7 @@ def workload_name(cfg):
 def cpu_baseline(cfg, cal, stack):
     from oracle import sl_oracle as O
     ocal = O.make_calib(cal.cam, cal.pro, cal.R, cal.T)
-    threads = O.max_threads()
+    threads = host_threads()
 
     def timed(nthreads, reps):
         ocfg = O.make_config(cfg.width, cfg.height, cfg.projector_width, cfg.gray_digits, cfg.phase_steps,
@@ -210,6 +219,7 @@ def main():
     ap.add_argument("--e2e-slots", type=int, default=4)
     ap.add_argument("--pxt", type=int, default=0, help="tuning: pixels per thread (4/8/16)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-numa-bind", action="store_true")
     ap.add_argument("--ref-stacks-per-step", type=int, default=2)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else max(args.warmup, 1)
@@ -227,6 +237,8 @@ def main():
                          "(use --impl reference for the CPU path)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    orig_affinity = os.sched_getaffinity(0)
+    numa = D.bind_to_gpu_numa_node(local_rank) if not args.no_numa_bind else {"bound": False}
     if world > 1:
         D.init_process_group("nccl")
     if args.pxt:
@@ -301,13 +313,14 @@ def main():
     e2e_value = world * E * e2e_steps / e2e_s_max
     clocks = sampler.stop() if rank == 0 else None
 
+    os.sched_setaffinity(0, orig_affinity)   # the CPU baseline below may use every core again
     # ---- spot check of what was just computed (not timed) ----
     checked = None
     cpu = None
     if rank == 0:
         from oracle import sl_oracle as O   # checker + CPU baseline only
         ocfg = O.make_config(cfg.width, cfg.height, cfg.projector_width, cfg.gray_digits, cfg.phase_steps,
-                             cfg.fov_min, cfg.fov_max, cfg.modulation_min, O.max_threads())
+                             cfg.fov_min, cfg.fov_max, cfg.modulation_min, host_threads())
         want = O.reconstruct(ocfg, O.make_calib(cal.cam, cal.pro, cal.R, cal.T), stacks[0])
         z_dev = d_xyzw[0, :, :, 2].cpu().numpy()
         m_dev = d_mask[0].cpu().numpy()
@@ -351,6 +364,7 @@ def main():
             "kernel": {"variant": info.kernel_variant, "regs": info.kernel_regs, "block": info.kernel_block,
                        "smem": info.kernel_smem},
             "checked_against_oracle": checked,
+            "numa": numa,
         }
         print(json.dumps(line), flush=True)
     rec.close()

@@ -63,3 +63,47 @@ def sum_over_ranks(value: float, device=None) -> float:
     t = torch.tensor([float(value)], dtype=torch.float64, device=device)
     dist.all_reduce(t, op=dist.ReduceOp.SUM)
     return float(t.item())
+
+
+def _parse_cpulist(text: str) -> set[int]:
+    cpus: set[int] = set()
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        if "-" in part:
+            a, b = part.split("-")
+            cpus.update(range(int(a), int(b) + 1))
+        else:
+            cpus.add(int(part))
+    return cpus
+
+
+def gpu_local_cpus(pci_domain: int, pci_bus: int, pci_device: int) -> set[int]:
+    """CPUs of the NUMA node the GPU hangs off (sysfs local_cpulist); empty if unknown."""
+    path = f"/sys/bus/pci/devices/{pci_domain:04x}:{pci_bus:02x}:{pci_device:02x}.0/local_cpulist"
+    try:
+        with open(path) as f:
+            return _parse_cpulist(f.read())
+    except OSError:
+        return set()
+
+
+def bind_to_gpu_numa_node(local_rank: int) -> dict:
+    """Pin this process to the cores next to its GPU, so that the pinned staging buffers
+    it allocates afterwards are first-touched on that NUMA node and the H2D/D2H copies do
+    not cross the socket interconnect (SURVEY hard part 8).  Returns what was done."""
+    import torch
+    info = {"bound": False}
+    try:
+        props = torch.cuda.get_device_properties(local_rank)
+        cpus = gpu_local_cpus(props.pci_domain_id, props.pci_bus_id, props.pci_device_id)
+        allowed = os.sched_getaffinity(0)
+        target = cpus & allowed
+        info.update(pci=f"{props.pci_domain_id:04x}:{props.pci_bus_id:02x}:{props.pci_device_id:02x}.0",
+                    local_cpus=len(cpus), allowed=len(allowed))
+        if target and target != allowed:
+            os.sched_setaffinity(0, target)
+            info.update(bound=True, cpus=len(target))
+    except Exception as e:  # best effort: never fail a run because of placement
+        info["error"] = repr(e)
+    return info
