@@ -205,6 +205,114 @@ def cpu_baseline(cfg, cal, stack):
     }
 
 
+def run_dynamic(args):
+    """--path dynamic: the reference's CalculateOther mode -- a sequence of
+    single stripe images tracked frame to frame (StripRegression + FillOtherDeltaProU +
+    FillCoordinate), at the reference's own geometry (1280x1024, 100 frames, window 21).
+    A step is `--batch` sequences; every sequence is two kernel launches."""
+    import torch
+    from structured_light_calculation_b200 import capi
+    from oracle import sl_oracle as O   # U0 for the synthetic sequence + CPU baseline only
+
+    rank, local_rank, world = D.env_rank_world()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        D.init_process_group("nccl")
+    cfg = CONFIGS["reference_default"]
+    F, window, S = args.dyna_frames, 21, max(1, args.batch // 64)
+    base = load_calibration(os.path.join(ROOT, "tests", "golden", "Result.yml"))
+    cal = synth.synthetic_calibration(cfg, base)
+    scene = synth.make_scene(cfg, cal)
+    stack = synth.render_stack(cfg, scene, noise_sigma=1.0, seed=77)
+    pool = synth.render_dyna_frames(cfg, cal, 8, stripe_period=20.0, z_step=0.3, noise_sigma=1.5)
+    # 8 rendered positions visited back and forth (0..7,6..1,0..): the plane oscillates
+    order = [k if k < 8 else 14 - k for k in (f % 14 for f in range(F))]
+    frames = np.stack([pool[k] for k in order])
+    rec = capi.Reconstructor(cfg, device=local_rank, max_batch=1, num_slots=1)
+    rec.set_calibration(cal)
+    u0 = rec.reconstruct(stack, parity=True)["proj_u"][0]
+    npx = cfg.pixels
+    d_frames = torch.empty((S, F, cfg.height, cfg.width), dtype=torch.uint8, device=dev)
+    for i in range(S):
+        d_frames[i].copy_(torch.from_numpy(np.roll(frames, i, axis=0)))
+    d_u0 = torch.from_numpy(u0).to(dev)
+    d_xyzw = torch.empty((S, F - 1, cfg.height, cfg.width, 4), dtype=torch.float32, device=dev)
+    d_mask = torch.empty((S, F - 1, cfg.height, cfg.width), dtype=torch.uint8, device=dev)
+    d_dz = torch.empty((S, F - 1, cfg.height, cfg.width), dtype=torch.float32, device=dev)
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+
+    def step():
+        for i in range(S):
+            rec.dyna_track_device(d_frames[i].data_ptr(), F, d_u0.data_ptr(), d_xyzw[i].data_ptr(),
+                                  d_mask[i].data_ptr(), d_dz[i].data_ptr(), window, stream.cuda_stream)
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    launches0 = rec.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    D.barrier()
+    torch.cuda.synchronize()
+    e0.record(stream)
+    for _ in range(args.steps):
+        step()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    D.barrier()
+    ms = D.max_over_ranks(e0.elapsed_time(e1), dev)
+    launches = int(D.sum_over_ranks(rec.launch_count() - launches0, dev))
+    value = world * S * (F - 1) * args.steps / (ms * 1e-3)
+
+    # end to end: host frames in, host maps out (one blocking call per sequence)
+    t0 = time.perf_counter()
+    e2e_reps = 3
+    out = None
+    for _ in range(e2e_reps):
+        out = rec.dyna_track(frames[: args.dyna_e2e_frames], u0, window=window)
+    e2e_s = D.max_over_ranks(time.perf_counter() - t0, dev)
+    e2e_value = world * e2e_reps * (args.dyna_e2e_frames - 1) / e2e_s
+
+    if rank == 0:
+        ocfg = O.make_config(cfg.width, cfg.height, cfg.projector_width, cfg.gray_digits, cfg.phase_steps)
+        ocal = O.make_calib(cal.cam, cal.pro, cal.R, cal.T)
+        first = O.reconstruct(ocfg, ocal, stack)
+        t0 = time.perf_counter()
+        want = O.dyna_sequence(ocfg, ocal, first["proj_u"], first["z"], frames[:4], window)
+        cpu_s = (time.perf_counter() - t0) / 3
+        tol = 1e-5 * (cfg.fov_max - cfg.fov_min)
+        checked = all(np.array_equal(out["mask"][f], want[f]["mask"]) and
+                      np.array_equal(out["xyzw"][f, ..., 3], want[f]["proj_u"].astype(np.float32)) and
+                      np.abs(out["xyzw"][f, ..., 2] - want[f]["z"]).max() <= tol for f in range(3))
+        peak, peak_kind = hbm_peak()
+        alg = 26 * npx * (F - 1) * S          # 1 B image + 2 B strips written + 2 B strips read + 16 + 1 + 4 B out
+        achieved = alg / (ms * 1e-3 / args.steps) / 1e9
+        line = {
+            "metric": "dynamic_frames_per_sec", "value": value, "unit": "frames/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"dynamic sequence: {F} stripe images {cfg.width}x{cfg.height}, window {window} "
+                                   f"(reference CalculateOther), {S} sequence(s) per step"},
+            "mpix_per_s": value * npx / 1e6,
+            "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": args.dyna_e2e_frames * npx,
+                    "d2h_bytes_per_step": (args.dyna_e2e_frames - 1) * npx * 21},
+            "gpu_launches": launches,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_kind": f"of {peak_kind}",
+                         "kernel": "strip_regression_kernel + dyna_track_kernel (per sequence)",
+                         "algorithmic_bytes_per_step": alg},
+            "cpu_baseline": {"value": 1.0 / cpu_s, "unit": "frames/s", "cores": 1, "kind": "port",
+                             "sample": "3 dynamic frames, oracle port, 1 thread"},
+            "checked_against_oracle": bool(checked),
+        }
+        print(json.dumps(line), flush=True)
+    rec.close()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -220,6 +328,10 @@ def main():
     ap.add_argument("--pxt", type=int, default=0, help="tuning: pixels per thread (4/8/16)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-numa-bind", action="store_true")
+    ap.add_argument("--path", default="first", choices=["first", "dynamic"],
+                    help="first = the headline first-frame path; dynamic = CalculateOther sequences")
+    ap.add_argument("--dyna-frames", type=int, default=100)
+    ap.add_argument("--dyna-e2e-frames", type=int, default=24)
     ap.add_argument("--ref-stacks-per-step", type=int, default=2)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else max(args.warmup, 1)
@@ -227,6 +339,8 @@ def main():
 
     if args.impl == "reference":
         return run_reference(args, cfg)
+    if args.path == "dynamic":
+        return run_dynamic(args)
 
     import torch
     from structured_light_calculation_b200 import capi

@@ -176,13 +176,19 @@ public:
 
     bool Init();
     bool CalculateFirst();
-    bool CalculateOther();      // dynamic-frame tracker: not part of this path, returns false
+    bool CalculateOther();      // dynamic frames 1 .. DYNAFRAME_MAXNUM-1 (CCalculation.cpp:208-320)
     bool Result(std::string fileName, int i);
+    void SetDynamicPointCloudPrefix(const std::string& prefix) { m_pcDynaPrefix = prefix; }   // "cFrame" + idx + ".txt"
 
     // results of frame 0 (valid after CalculateFirst): CV_32FC4 (x,y,z,U) and CV_8UC1 mask,
     // plus the reference's separate planes on request
     const Mat& PointMap() const { return m_xyzw; }
     const Mat& ValidMask() const { return m_mask; }
+    // dynamic frames (valid after CalculateOther); i in 1 .. FrameCount()-1
+    int FrameCount() const { return 1 + (int)m_dynXyzw.size(); }
+    const Mat& PointMap(int i) const { return i == 0 ? m_xyzw : m_dynXyzw.at((size_t)i - 1); }
+    const Mat& ValidMask(int i) const { return i == 0 ? m_mask : m_dynMask.at((size_t)i - 1); }
+    const Mat& DeltaZ(int i) const { return m_dynDeltaZ.at((size_t)i - 1); }                     // CV_32FC1, m_deltaZ[i]
     Mat GetX() const;   // CV_64FC1 views of m_xMat[0] / m_yMat[0] / m_zMat[0] / m_ProjectorU[0]
     Mat GetY() const;
     Mat GetZ() const;
@@ -199,6 +205,8 @@ private:
     std::string m_pcFile = "iFrame.txt";
     uint8_t* pinned_stack_ = nullptr;
     Mat m_xyzw, m_mask, m_projU;
+    std::vector<Mat> m_dynXyzw, m_dynMask, m_dynDeltaZ;
+    std::string m_pcDynaPrefix;
     bool calibrated_ = false;
 };
 

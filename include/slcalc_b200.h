@@ -183,6 +183,28 @@ int slc_decode_phase_host(slc_context *ctx, const uint8_t *h_phase_planes,
 int slc_triangulate_host(slc_context *ctx, const double *h_proj_u,
                          float *h_xyzw, uint8_t *h_mask);
 
+/* ---- dynamic frames ("next" row: CCalculation::CalculateOther) ----------- */
+/* Optional parity planes of the dynamic path.  NULL members are skipped. */
+typedef struct {
+    int8_t *strips;      /* [n_frames][H][W][2] = (stripB, stripW) offsets, StripRegression (CCalculation.cpp:886-887) */
+    float  *delta_p;     /* [n_frames-1][H][W] blurred deltaP (CCalculation.cpp:650) */
+    double *proj_u;      /* [n_frames-1][H][W] ProjectorU[f] (CCalculation.cpp:656-658) */
+} slc_dyna_parity;
+
+/* replaces: the per-frame body of CCalculation::CalculateOther (CCalculation.cpp:221-243):
+ * StripRegression(f) (:789-892), FillOtherDeltaProU(f) (:595-663) and FillCoordinate(f)
+ * (:666-775) for f = 1 .. n_frames-1.  frames is uint8 [n_frames][H][W] (the dynaCam images;
+ * frames[0] is the one StripRegression(0) sees at CCalculation.cpp:201), window is
+ * RECO_WINDOW_SIZE (StaticParameters.cpp:38, odd, <= 33), u0 is ProjectorU[0] (f64 [H][W], e.g.
+ * the proj_u parity plane of the first-frame call).  Outputs hold n_frames-1 maps: xyzw, mask,
+ * and optionally deltaZ (m_deltaZ, :772-775).  Two kernel launches for the whole sequence. */
+int slc_dyna_track_device(slc_context *ctx, const uint8_t *d_frames, int32_t n_frames, int32_t window,
+                          const double *d_u0, float *d_xyzw, uint8_t *d_mask, float *d_delta_z,
+                          const slc_dyna_parity *d_parity, void *cuda_stream);
+int slc_dyna_track_host(slc_context *ctx, const uint8_t *h_frames, int32_t n_frames, int32_t window,
+                        const double *h_u0, float *h_xyzw, uint8_t *h_mask, float *h_delta_z,
+                        const slc_dyna_parity *h_parity);
+
 /* Parity hook for the arctangent of CDecodePhase.cpp:67-75 alone: evaluates
  * cvFastArctan(sin, cos) in degrees and the in-period offset on the device, with
  * exactly the arithmetic of the fused kernel, for n caller-supplied pairs. */

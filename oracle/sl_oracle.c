@@ -535,3 +535,122 @@ int slo_time_reconstruct(const slo_config *cfg, const slo_calib *cal,
     ws_free(&w);
     return 0;
 }
+
+
+/* ======================================================================== */
+/* Dynamic frames ("next" row):
+ *   StripRegression       CCalculation.cpp:789-892
+ *   FillOtherDeltaProU    CCalculation.cpp:595-663   (cv::blur 3x3, BORDER_REFLECT_101)
+ *   FillCoordinate(i>0)   CCalculation.cpp:666-775   (incl. deltaZ)
+ * cv::blur on CV_32F sums in double and stores (float)(sum * (1./9)) -- pinned
+ * against the container's cv2.blur in tests/golden/make_golden.py. */
+
+void slo_strip_regression(const slo_config *cfg, int window, const uint8_t *CamMat,
+                          float *stripB, float *stripW)
+{
+    const int W = cfg->width, H = cfg->height;
+    const int RECO_WINDOW_SIZE = window;
+    const int half = RECO_WINDOW_SIZE / 2;
+    const size_t npx = (size_t)W * H;
+    const int nt = n_threads(cfg);
+    (void)nt;
+    float *valSum = (float *)calloc(npx, sizeof(float));            /* :798-800 */
+    /* :801-812 first row of sums */
+    for (int w = half; w < W - half; w++) {
+        float sum = 0;
+        for (int hc = 0; hc < RECO_WINDOW_SIZE; hc++) sum += (float)CamMat[(size_t)hc * W + w];
+        valSum[(size_t)half * W + w] = sum;
+    }
+    /* :814-823 running update down the rows */
+    for (int h = half + 1; h < H - half; h++)
+        for (int w = half; w < W - half; w++)
+            valSum[(size_t)h * W + w] = valSum[(size_t)(h - 1) * W + w]
+                - (float)CamMat[(size_t)(h - half - 1) * W + w]
+                + (float)CamMat[(size_t)(h + half) * W + w];
+    /* :826-889 */
+    memset(stripB, 0, npx * sizeof(float));
+    memset(stripW, 0, npx * sizeof(float));
+#pragma omp parallel for num_threads(nt) schedule(static)
+    for (int h = half; h < H - half; h++) {
+        for (int w = half; w < W - half; w++) {
+            float max = valSum[(size_t)h * W + w];
+            float maxIdx = 0;
+            float min = valSum[(size_t)h * W + w];
+            float minIdx = 0;
+            for (int i = -half; i < half; i++) {
+                float value = valSum[(size_t)h * W + w + i];
+                if (value > max) { max = value; maxIdx = i; }
+                if (value < min) { min = value; minIdx = i; }
+            }
+            stripB[(size_t)h * W + w] = minIdx;
+            stripW[(size_t)h * W + w] = maxIdx;
+        }
+    }
+    free(valSum);
+}
+
+static int reflect101(int p, int n)
+{
+    if (n == 1) return 0;
+    while (p < 0 || p >= n) {
+        if (p < 0) p = -p;
+        else p = 2 * (n - 1) - p;
+    }
+    return p;
+}
+
+/* :599-650: nearer-of-two delta, then blur(temp, deltaP, Size(3,3)) */
+void slo_delta_p(const slo_config *cfg, const float *B0, const float *W0, const float *B1, const float *W1,
+                 float *deltaP)
+{
+    const int W = cfg->width, H = cfg->height;
+    const size_t npx = (size_t)W * H;
+    const int nt = n_threads(cfg);
+    (void)nt;
+    float *temp = (float *)malloc(npx * sizeof(float));
+#pragma omp parallel for num_threads(nt) schedule(static)
+    for (int h = 0; h < H; h++)
+        for (int w = 0; w < W; w++) {
+            const size_t p = (size_t)h * W + w;
+            float f0W = W0[p], f0B = B0[p], f1W = W1[p], f1B = B1[p];
+            float fBbias = fabsf(f0B - f1B);
+            float fWbias = fabsf(f0W - f1W);
+            temp[p] = (fBbias < fWbias) ? (f0B - f1B) : (f0W - f1W);
+        }
+    const double scale = 1. / 9;
+#pragma omp parallel for num_threads(nt) schedule(static)
+    for (int h = 0; h < H; h++)
+        for (int w = 0; w < W; w++) {
+            double sum = 0;
+            for (int dy = -1; dy <= 1; dy++) {
+                const int hh = reflect101(h + dy, H);
+                double rs = 0;
+                for (int dx = -1; dx <= 1; dx++) rs += (double)temp[(size_t)hh * W + reflect101(w + dx, W)];
+                sum += rs;
+            }
+            deltaP[(size_t)h * W + w] = (float)(sum * scale);
+        }
+    free(temp);
+}
+
+/* One dynamic frame: U1 = U0 + deltaP (:652-660), FillCoordinate (:672-771), deltaZ (:772-775).
+ * z0 is the previous frame's z plane.  Outputs may alias nothing. */
+void slo_dyna_frame(const slo_config *cfg, const slo_calib *cal, const double *U0, const float *deltaP,
+                    const double *z0, double *U1, double *x, double *y, double *z, double *deltaZ,
+                    uint8_t *mask)
+{
+    const int W = cfg->width, H = cfg->height;
+    const size_t npx = (size_t)W * H;
+    double A, B;
+    double *cC = (double *)malloc(npx * sizeof(double));
+    double *cD = (double *)malloc(npx * sizeof(double));
+    slo_calibration(cfg, cal, &A, &B, cC, cD, NULL);
+    for (size_t p = 0; p < npx; p++) U1[p] = U0[p] + deltaP[p];
+    slo_config c1 = *cfg;
+    c1.modulation_min = 0.f;
+    coordinate_stage(&c1, cal, A, B, cC, cD, U1, NULL, x, y, z, mask);
+    if (deltaZ)
+        for (size_t p = 0; p < npx; p++) deltaZ[p] = z[p] - z0[p];
+    free(cC);
+    free(cD);
+}

@@ -105,6 +105,16 @@ int slo_decode_phase(const slo_config *cfg, const uint8_t *phase_planes,
 int slo_time_reconstruct(const slo_config *cfg, const slo_calib *cal,
                          const uint8_t *planes, int reps, double *secs);
 
+/* Dynamic frames: StripRegression (CCalculation.cpp:789-892),
+ * FillOtherDeltaProU (:595-663), FillCoordinate(i>0) + deltaZ (:666-775). */
+void slo_strip_regression(const slo_config *cfg, int window, const uint8_t *CamMat,
+                          float *stripB, float *stripW);
+void slo_delta_p(const slo_config *cfg, const float *B0, const float *W0, const float *B1, const float *W1,
+                 float *deltaP);
+void slo_dyna_frame(const slo_config *cfg, const slo_calib *cal, const double *U0, const float *deltaP,
+                    const double *z0, double *U1, double *x, double *y, double *z, double *deltaZ,
+                    uint8_t *mask);
+
 int slo_max_threads(void);
 
 #ifdef __cplusplus

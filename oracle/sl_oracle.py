@@ -90,6 +90,9 @@ def lib():
         L.slo_decode_phase.argtypes = [C.POINTER(SloConfig), C.c_void_p, C.c_void_p, C.c_void_p]
         L.slo_time_reconstruct.argtypes = [C.POINTER(SloConfig), C.POINTER(SloCalib), C.c_void_p, C.c_int,
                                            C.c_void_p]
+        L.slo_strip_regression.argtypes = [C.POINTER(SloConfig), C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.slo_delta_p.argtypes = [C.POINTER(SloConfig)] + [C.c_void_p] * 5
+        L.slo_dyna_frame.argtypes = [C.POINTER(SloConfig), C.POINTER(SloCalib)] + [C.c_void_p] * 9
         L.slo_max_threads.restype = C.c_int
         _lib = L
     return _lib
@@ -225,3 +228,50 @@ def time_reconstruct(cfg: SloConfig, cal: SloCalib, planes: np.ndarray, reps: in
 
 def max_threads() -> int:
     return int(lib().slo_max_threads())
+
+
+# ---- dynamic frames --------------------------------------------------------
+def strip_regression(cfg: SloConfig, image: np.ndarray, window: int = 21):
+    image = np.ascontiguousarray(image, dtype=np.uint8)
+    assert image.shape == (cfg.height, cfg.width)
+    B = np.empty(image.shape, np.float32)
+    W = np.empty(image.shape, np.float32)
+    lib().slo_strip_regression(C.byref(cfg), window, image.ctypes.data, B.ctypes.data, W.ctypes.data)
+    return B, W
+
+
+def delta_p(cfg: SloConfig, B0, W0, B1, W1) -> np.ndarray:
+    arrs = [np.ascontiguousarray(a, dtype=np.float32) for a in (B0, W0, B1, W1)]
+    out = np.empty((cfg.height, cfg.width), np.float32)
+    lib().slo_delta_p(C.byref(cfg), *[a.ctypes.data for a in arrs], out.ctypes.data)
+    return out
+
+
+def dyna_frame(cfg: SloConfig, cal: SloCalib, U0: np.ndarray, dP: np.ndarray, z0: np.ndarray) -> dict:
+    H, W = cfg.height, cfg.width
+    U0 = np.ascontiguousarray(U0, dtype=np.float64)
+    dP = np.ascontiguousarray(dP, dtype=np.float32)
+    z0 = np.ascontiguousarray(z0, dtype=np.float64)
+    res = {k: np.empty((H, W), np.float64) for k in ("proj_u", "x", "y", "z", "delta_z")}
+    res["mask"] = np.empty((H, W), np.uint8)
+    lib().slo_dyna_frame(C.byref(cfg), C.byref(cal), U0.ctypes.data, dP.ctypes.data, z0.ctypes.data,
+                         res["proj_u"].ctypes.data, res["x"].ctypes.data, res["y"].ctypes.data,
+                         res["z"].ctypes.data, res["delta_z"].ctypes.data, res["mask"].ctypes.data)
+    return res
+
+
+def dyna_sequence(cfg: SloConfig, cal: SloCalib, U0: np.ndarray, z0: np.ndarray, frames: np.ndarray,
+                  window: int = 21) -> list:
+    """CalculateOther (CCalculation.cpp:221-317) over frames[1:], frames[0] being the image
+    StripRegression(0) saw at the end of CalculateFirst (:201)."""
+    B0, W0 = strip_regression(cfg, frames[0], window)
+    out = []
+    U, z = U0, z0
+    for f in range(1, frames.shape[0]):
+        B1, W1 = strip_regression(cfg, frames[f], window)
+        dP = delta_p(cfg, B0, W0, B1, W1)
+        r = dyna_frame(cfg, cal, U, dP, z)
+        r.update(strip_b=B1, strip_w=W1, delta_p=dP)
+        out.append(r)
+        U, z, B0, W0 = r["proj_u"], r["z"], B1, W1
+    return out

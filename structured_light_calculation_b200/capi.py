@@ -55,6 +55,10 @@ class SlcInfo(C.Structure):
     ]
 
 
+class SlcDynaParity(C.Structure):
+    _fields_ = [("strips", C.c_void_p), ("delta_p", C.c_void_p), ("proj_u", C.c_void_p)]
+
+
 class SlcParityPlanes(C.Structure):
     _fields_ = [("kbin", C.c_void_p), ("corr", C.c_void_p), ("phase_pix", C.c_void_p), ("proj_u", C.c_void_p)]
 
@@ -111,6 +115,8 @@ def load_library():
     L.slc_decode_gray_host.argtypes = [vp, vp, vp, vp]
     L.slc_decode_phase_host.argtypes = [vp, vp, vp, vp]
     L.slc_triangulate_host.argtypes = [vp, vp, vp, vp]
+    L.slc_dyna_track_device.argtypes = [vp, vp, i32, i32, vp, vp, vp, vp, C.POINTER(SlcDynaParity), vp]
+    L.slc_dyna_track_host.argtypes = [vp, vp, i32, i32, vp, vp, vp, vp, C.POINTER(SlcDynaParity)]
     L.slc_eval_phase_host.argtypes = [vp, vp, vp, C.c_int64, vp, vp]
     L.slc_time_reconstruct_device.argtypes = [vp, vp, i32, vp, vp, i32, C.POINTER(C.c_float)]
     L.slc_launch_count.argtypes = [vp]
@@ -298,6 +304,35 @@ class Reconstructor:
         mask = np.empty((cfg.height, cfg.width), np.uint8)
         self._check(self.lib.slc_triangulate_host(self.h, proj_u.ctypes.data, xyzw.ctypes.data, mask.ctypes.data))
         return xyzw, mask
+
+    # -- dynamic frames -----------------------------------------------------
+    def dyna_track(self, frames: np.ndarray, u0: np.ndarray, window: int = 21, parity: bool = False) -> dict:
+        """CalculateOther over frames[1:] (frames[0] = the image StripRegression(0) saw)."""
+        cfg = self.cfg
+        frames = np.ascontiguousarray(frames, dtype=np.uint8)
+        u0 = np.ascontiguousarray(u0, dtype=np.float64)
+        n = frames.shape[0]
+        assert frames.shape[1:] == (cfg.height, cfg.width) and u0.shape == (cfg.height, cfg.width)
+        out = {
+            "xyzw": np.empty((n - 1, cfg.height, cfg.width, 4), np.float32),
+            "mask": np.empty((n - 1, cfg.height, cfg.width), np.uint8),
+            "delta_z": np.empty((n - 1, cfg.height, cfg.width), np.float32),
+        }
+        par = None
+        if parity:
+            out["strips"] = np.empty((n, cfg.height, cfg.width, 2), np.int8)
+            out["delta_p"] = np.empty((n - 1, cfg.height, cfg.width), np.float32)
+            out["proj_u"] = np.empty((n - 1, cfg.height, cfg.width), np.float64)
+            par = SlcDynaParity(out["strips"].ctypes.data, out["delta_p"].ctypes.data, out["proj_u"].ctypes.data)
+        self._check(self.lib.slc_dyna_track_host(self.h, frames.ctypes.data, n, window, u0.ctypes.data,
+                                                 out["xyzw"].ctypes.data, out["mask"].ctypes.data,
+                                                 out["delta_z"].ctypes.data, C.byref(par) if par else None))
+        return out
+
+    def dyna_track_device(self, d_frames: int, n_frames: int, d_u0: int, d_xyzw: int, d_mask: int,
+                          d_delta_z: int | None = None, window: int = 21, stream: int | None = None):
+        self._check(self.lib.slc_dyna_track_device(self.h, d_frames, n_frames, window, d_u0, d_xyzw, d_mask,
+                                                   d_delta_z, None, stream))
 
     def eval_phase(self, s: np.ndarray, c: np.ndarray):
         """Device cvFastArctan + in-period offset for arbitrary (sin, cos) sums."""

@@ -50,6 +50,8 @@ struct slc_context {
     void* d_scratch_in = nullptr;  size_t scratch_in_bytes = 0;
     void* d_scratch_out = nullptr; size_t scratch_out_bytes = 0;
     void* d_scratch_aux = nullptr; size_t scratch_aux_bytes = 0;
+    void* d_strips = nullptr;      size_t strips_bytes = 0;      // dynamic frames: (stripB, stripW) per frame
+    void* d_dyna = nullptr;        size_t dyna_bytes = 0;        // dynamic frames: staging for the host entry point
     long long launches = 0;
     std::string err;
 };
@@ -311,6 +313,7 @@ void slc_destroy(slc_context* ctx)
     if (ctx->stream) { cudaStreamSynchronize(ctx->stream); cudaStreamDestroy(ctx->stream); }
     cudaFree(ctx->d_lut);
     cudaFree(ctx->d_scratch_in); cudaFree(ctx->d_scratch_out); cudaFree(ctx->d_scratch_aux);
+    cudaFree(ctx->d_strips); cudaFree(ctx->d_dyna);
     delete ctx;
 }
 
@@ -629,6 +632,87 @@ int slc_triangulate_host(slc_context* ctx, const double* h_proj_u, float* h_xyzw
     SLC_CUDA(ctx, cudaMemcpyAsync(h_xyzw, ctx->d_scratch_out, npx * 16, cudaMemcpyDeviceToHost, ctx->stream));
     SLC_CUDA(ctx, cudaMemcpyAsync(h_mask, ctx->d_scratch_aux, npx, cudaMemcpyDeviceToHost, ctx->stream));
     SLC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SLC_OK;
+}
+
+/* ---- dynamic frames ---------------------------------------------------- */
+int slc_dyna_track_device(slc_context* ctx, const uint8_t* d_frames, int32_t n_frames, int32_t window,
+                          const double* d_u0, float* d_xyzw, uint8_t* d_mask, float* d_delta_z,
+                          const slc_dyna_parity* d_parity, void* cuda_stream)
+{
+    int rc = check_ready(ctx, d_frames, d_xyzw, d_mask, n_frames);
+    if (rc != SLC_OK) return rc;
+    if (!d_u0) return fail(ctx, SLC_ERR_INVALID_ARG, "NULL ProjectorU[0]");
+    if (n_frames < 1 || n_frames > 65535) return fail(ctx, SLC_ERR_INVALID_ARG, "n_frames %d outside 1..65535", n_frames);
+    if (window < 3 || window > 33 || (window & 1) == 0)
+        return fail(ctx, SLC_ERR_INVALID_ARG, "window %d must be odd and in 3..33 (RECO_WINDOW_SIZE)", window);
+    if (ctx->kp.W <= window || ctx->kp.H <= window)
+        return fail(ctx, SLC_ERR_INVALID_ARG, "camera %dx%d smaller than the %d-pixel window", ctx->kp.W, ctx->kp.H, window);
+    SLC_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+    cudaStream_t st = cuda_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : ctx->stream;
+    const size_t npx = (size_t)ctx->kp.npx;
+    signed char* strips = d_parity && d_parity->strips ? reinterpret_cast<signed char*>(d_parity->strips) : nullptr;
+    if (!strips) {
+        rc = ensure_scratch(ctx, &ctx->d_strips, &ctx->strips_bytes, 2 * npx * (size_t)n_frames);
+        if (rc != SLC_OK) return rc;
+        strips = static_cast<signed char*>(ctx->d_strips);
+    }
+    SLC_CUDA(ctx, slc::launch_strip_regression(d_frames, n_frames, ctx->kp.W, ctx->kp.H, window, strips, st));
+    ctx->launches++;
+    if (n_frames > 1) {
+        SLC_CUDA(ctx, slc::launch_dyna_track(ctx->kp, strips, n_frames, d_u0, d_xyzw, d_mask, d_delta_z,
+                                             d_parity ? d_parity->delta_p : nullptr,
+                                             d_parity ? d_parity->proj_u : nullptr, nullptr, st));
+        ctx->launches++;
+    }
+    return SLC_OK;
+}
+
+int slc_dyna_track_host(slc_context* ctx, const uint8_t* h_frames, int32_t n_frames, int32_t window,
+                        const double* h_u0, float* h_xyzw, uint8_t* h_mask, float* h_delta_z,
+                        const slc_dyna_parity* h_parity)
+{
+    int rc = check_ready(ctx, h_frames, h_xyzw, h_mask, n_frames);
+    if (rc != SLC_OK) return rc;
+    if (!h_u0 || n_frames < 1) return fail(ctx, SLC_ERR_INVALID_ARG, "NULL ProjectorU[0] or n_frames < 1");
+    SLC_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+    const size_t npx = (size_t)ctx->kp.npx;
+    const size_t nf = (size_t)n_frames, no = nf - 1;
+    // one staging block: frames | u0 | xyzw | mask | deltaZ | strips | deltaP | projU
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
+    const size_t o_fr = take(nf * npx), o_u0 = take(npx * 8), o_xyzw = take(no * npx * 16), o_mask = take(no * npx),
+                 o_dz = take(h_delta_z ? no * npx * 4 : 0),
+                 o_st = take(nf * npx * 2),
+                 o_dp = take(h_parity && h_parity->delta_p ? no * npx * 4 : 0),
+                 o_pu = take(h_parity && h_parity->proj_u ? no * npx * 8 : 0);
+    rc = ensure_scratch(ctx, &ctx->d_dyna, &ctx->dyna_bytes, off);
+    if (rc != SLC_OK) return rc;
+    char* base = static_cast<char*>(ctx->d_dyna);
+    cudaStream_t st = ctx->stream;
+    SLC_CUDA(ctx, cudaMemcpyAsync(base + o_fr, h_frames, nf * npx, cudaMemcpyHostToDevice, st));
+    SLC_CUDA(ctx, cudaMemcpyAsync(base + o_u0, h_u0, npx * 8, cudaMemcpyHostToDevice, st));
+    slc_dyna_parity dpar{};
+    dpar.strips = reinterpret_cast<int8_t*>(base + o_st);
+    dpar.delta_p = (h_parity && h_parity->delta_p) ? reinterpret_cast<float*>(base + o_dp) : nullptr;
+    dpar.proj_u = (h_parity && h_parity->proj_u) ? reinterpret_cast<double*>(base + o_pu) : nullptr;
+    rc = slc_dyna_track_device(ctx, reinterpret_cast<uint8_t*>(base + o_fr), n_frames, window,
+                               reinterpret_cast<double*>(base + o_u0), reinterpret_cast<float*>(base + o_xyzw),
+                               reinterpret_cast<uint8_t*>(base + o_mask),
+                               h_delta_z ? reinterpret_cast<float*>(base + o_dz) : nullptr, &dpar, st);
+    if (rc != SLC_OK) return rc;
+    if (no > 0) {
+        SLC_CUDA(ctx, cudaMemcpyAsync(h_xyzw, base + o_xyzw, no * npx * 16, cudaMemcpyDeviceToHost, st));
+        SLC_CUDA(ctx, cudaMemcpyAsync(h_mask, base + o_mask, no * npx, cudaMemcpyDeviceToHost, st));
+        if (h_delta_z) SLC_CUDA(ctx, cudaMemcpyAsync(h_delta_z, base + o_dz, no * npx * 4, cudaMemcpyDeviceToHost, st));
+        if (dpar.delta_p)
+            SLC_CUDA(ctx, cudaMemcpyAsync(h_parity->delta_p, dpar.delta_p, no * npx * 4, cudaMemcpyDeviceToHost, st));
+        if (dpar.proj_u)
+            SLC_CUDA(ctx, cudaMemcpyAsync(h_parity->proj_u, dpar.proj_u, no * npx * 8, cudaMemcpyDeviceToHost, st));
+    }
+    if (h_parity && h_parity->strips)
+        SLC_CUDA(ctx, cudaMemcpyAsync(h_parity->strips, dpar.strips, nf * npx * 2, cudaMemcpyDeviceToHost, st));
+    SLC_CUDA(ctx, cudaStreamSynchronize(st));
     return SLC_OK;
 }
 

@@ -454,16 +454,56 @@ bool CCalculation::CalculateFirst()
 
 bool CCalculation::CalculateOther()
 {
-    // The dynamic-frame tracker (CCalculation.cpp:208-320) is a different algorithm
-    // with a frame-to-frame recurrence; it is outside this drop-in's path.
-    ErrorHandling("CCalculation::CalculateOther()->dynamic frames are not part of the B200 first-frame path.");
-    return false;
+    if (m_sensor == nullptr) return false;                          // CCalculation.cpp:213-214
+    if (ctx_ == nullptr) return false;                              // :215-216
+    if (!calibrated_ || m_projU.empty()) return false;              // :217-218 (+ needs ProjectorU[0])
+    const size_t npx = (size_t)sp_.CAMERA_RESROW * sp_.CAMERA_RESLINE;
+    // :791-795 the dyna images through the sensor (group 2), frame 0 included (StripRegression(0), :201)
+    m_sensor->LoadDatas(2);
+    int n = 0;
+    while (n < sp_.DYNAFRAME_MAXNUM && m_sensor->SetProPicture(n)) n++;
+    if (n < 2) { ErrorHandling("CCalculation::CalculateOther()->fewer than two dynamic frames loaded."); return false; }
+    uint8_t* frames = static_cast<uint8_t*>(slc_host_alloc((size_t)n * npx));
+    if (!frames) { ErrorHandling("CCalculation::CalculateOther()->pinned allocation failed."); return false; }
+    for (int i = 0; i < n; i++) {
+        m_sensor->SetProPicture(i);
+        Mat img = m_sensor->GetCamPicture();
+        if (!copy_plane(img, sp_, frames + (size_t)i * npx, "CCalculation::StripRegression")) { slc_host_free(frames); return false; }
+    }
+    const size_t no = (size_t)n - 1;
+    std::vector<float> xyzw(no * npx * 4), dz(no * npx);
+    std::vector<uint8_t> mask(no * npx);
+    // StripRegression + FillOtherDeltaProU + FillCoordinate for every frame: two launches
+    const int rc = slc_dyna_track_host(ctx_, frames, n, sp_.RECO_WINDOW_SIZE, reinterpret_cast<const double*>(m_projU.ptr()),
+                                       xyzw.data(), mask.data(), dz.data(), nullptr);
+    slc_host_free(frames);
+    if (rc != SLC_OK) {
+        ErrorHandling(std::string("CCalculation::CalculateOther()->") + slc_last_error(ctx_));
+        return false;
+    }
+    m_dynXyzw.assign(no, Mat());
+    m_dynMask.assign(no, Mat());
+    m_dynDeltaZ.assign(no, Mat());
+    for (size_t f = 0; f < no; f++) {
+        std::cout << "Frame: " << (f + 1) << " begin." << std::endl;       // :228
+        Mat(sp_.CAMERA_RESROW, sp_.CAMERA_RESLINE, CV_32FC4, xyzw.data() + f * npx * 4).copyTo(m_dynXyzw[f]);
+        Mat(sp_.CAMERA_RESROW, sp_.CAMERA_RESLINE, CV_8UC1, mask.data() + f * npx).copyTo(m_dynMask[f]);
+        Mat(sp_.CAMERA_RESROW, sp_.CAMERA_RESLINE, CV_32FC1, dz.data() + f * npx).copyTo(m_dynDeltaZ[f]);
+        if (!m_pcDynaPrefix.empty()) {                                      // :309-315
+            std::ostringstream name;
+            name << sp_.DATA_PATH << m_pcDynaPrefix << (f + 1) << ".txt";
+            Result(name.str(), (int)f + 1);
+        }
+    }
+    return true;
 }
 
 bool CCalculation::Result(std::string fileName, int i)
 {
     // CCalculation.cpp:323-357: "x y z\n" per in-FOV pixel, u outer / v inner
-    if (i != 0 || m_xyzw.empty()) return false;
+    if (i < 0 || i >= FrameCount() || m_xyzw.empty()) return false;
+    const Mat& xyzw = PointMap(i);
+    const Mat& maskm = ValidMask(i);
     std::fstream file;
     file.open(fileName.c_str(), std::ios::out);
     if (!file) {
@@ -472,9 +512,9 @@ bool CCalculation::Result(std::string fileName, int i)
     }
     for (int u = 0; u < sp_.CAMERA_RESLINE; u++) {
         for (int v = 0; v < sp_.CAMERA_RESROW; v++) {
-            const float* p = &m_xyzw.at<float>(v, 4 * u);
+            const float* p = &xyzw.at<float>(v, 4 * u);
             // the reference filters on the f64 z (:341-345); the mask is that same f64 decision
-            if (m_mask.at<uint8_t>(v, u) == 0) continue;
+            if (maskm.at<uint8_t>(v, u) == 0) continue;
             file << (double)p[0] << ' ';
             file << (double)p[1] << ' ';
             file << (double)p[2] << std::endl;

@@ -31,7 +31,7 @@ class Scene:
     albedo: np.ndarray   # [H,W] f64 in (0,1]
 
 
-def make_scene(cfg: StackConfig, cal: Calibration) -> Scene:
+def make_scene(cfg: StackConfig, cal: Calibration, plane_z: float = 60.0) -> Scene:
     H, W = cfg.height, cfg.width
     fu, fv, cu, cv = cal.cam[0, 0], cal.cam[1, 1], cal.cam[0, 2], cal.cam[1, 2]
     u = np.arange(W, dtype=np.float64)[None, :]
@@ -39,7 +39,7 @@ def make_scene(cfg: StackConfig, cal: Calibration) -> Scene:
     dx = (u - cu) / fu
     dy = (v - cv) / fv
     # tilted plane n.X = d0 with n = (0.06, -0.04, 1): z = d0 / (n . d)
-    z = 60.0 / (0.06 * dx - 0.04 * dy + 1.0)
+    z = plane_z / (0.06 * dx - 0.04 * dy + 1.0)
     z = np.broadcast_to(z, (H, W)).copy()
     # step: everything right of 62% width is 3 units closer
     z[:, int(0.62 * W):] -= 3.0
@@ -111,3 +111,17 @@ def render_stack(cfg: StackConfig, scene: Scene, noise_sigma: float = 1.0, seed:
 def synthetic_calibration(cfg: StackConfig, base: Calibration) -> Calibration:
     """Result.yml (a 640x512 camera, 1280-wide projector) scaled to cfg."""
     return base.scaled(cfg.width / 640.0, cfg.projector_width / 1280.0)
+
+
+def render_dyna_frames(cfg: StackConfig, cal: Calibration, n_frames: int, stripe_period: float = 20.0,
+                       z_step: float = 0.05, noise_sigma: float = 1.0, seed: int = 4321) -> np.ndarray:
+    """The dynamic-mode input (`dynaCam{i}.bmp` in the reference): one camera image per frame
+    of a static sinusoidal stripe pattern while the scene's plane recedes by z_step per frame."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    frames = np.empty((n_frames, cfg.height, cfg.width), np.uint8)
+    for f in range(n_frames):
+        sc = make_scene(cfg, cal, plane_z=60.0 + z_step * f)
+        img = 6.0 + sc.albedo * (117.0 + 105.0 * np.sin(2.0 * np.pi * sc.U / stripe_period))
+        img = np.where(sc.lit, img, 6.0) + rng.standard_normal(img.shape) * noise_sigma
+        frames[f] = np.clip(np.rint(img), 0, 255).astype(np.uint8)
+    return frames

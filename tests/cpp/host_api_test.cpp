@@ -102,7 +102,28 @@ int main(int argc, char** argv)
     for (int i = 0; i < 2 * G; i++) CHECK(calc.Sensor()->StoreDatas(0, i, plane(i)));
     for (int i = 0; i < N; i++) CHECK(calc.Sensor()->StoreDatas(1, i, plane(2 * G + i)));
     CHECK(calc.CalculateFirst());
-    CHECK(!calc.CalculateOther());                     // dynamic frames: not on this path
+    CHECK(!calc.CalculateOther());                     // no dynamic frames stored yet
+    {   // dynamic frames (optional input <dir>/dyna.u8 = n images)
+        std::ifstream f(dir + "/dyna.u8", std::ios::binary | std::ios::ate);
+        if (f) {
+            const size_t bytes = (size_t)f.tellg();
+            const int n = (int)(bytes / npx);
+            std::vector<uint8_t> dyn(bytes);
+            f.seekg(0);
+            f.read(reinterpret_cast<char*>(dyn.data()), (std::streamsize)bytes);
+            for (int i = 0; i < n; i++) CHECK(calc.Sensor()->StoreDatas(2, i, Mat(H, W, CV_8UC1, dyn.data() + (size_t)i * npx)));
+            CHECK(calc.CalculateOther());
+            CHECK(calc.FrameCount() == n);
+            std::ofstream o(dir + "/dyna_xyzw.f32", std::ios::binary), m(dir + "/dyna_mask.u8", std::ios::binary),
+                dz(dir + "/dyna_dz.f32", std::ios::binary);
+            for (int i = 1; i < n; i++) {
+                o.write(reinterpret_cast<const char*>(calc.PointMap(i).ptr()), (std::streamsize)(npx * 16));
+                m.write(reinterpret_cast<const char*>(calc.ValidMask(i).ptr()), (std::streamsize)npx);
+                dz.write(reinterpret_cast<const char*>(calc.DeltaZ(i).ptr()), (std::streamsize)(npx * 4));
+            }
+            CHECK(calc.Result(dir + "/cloud_dyn1.txt", 1));
+        }
+    }
     CHECK(calc.PointMap().type() == CV_32FC4 && calc.ValidMask().type() == CV_8UC1);
     CHECK(write_file(dir + "/xyzw.f32", calc.PointMap().ptr(), npx * 16));
     CHECK(write_file(dir + "/mask.u8", calc.ValidMask().ptr(), npx));

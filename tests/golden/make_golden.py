@@ -16,7 +16,9 @@ The reference ships no tests or golden vectors and cannot be compiled here
                           (cv2.subtract for the saturating difference,
                           cv2.fastAtan2 for the arctangent, cv2.gemm for P),
                           with every intermediate plane stored;
-  4. kat.npz           -- the hand-derived known-answer tables of SURVEY.md 8(c).
+  4. dyna_g6.npz       -- the dynamic-frame path (StripRegression, FillOtherDeltaProU) restated
+                          with numpy cumsum/argmin and cv2.blur;
+  5. kat.npz           -- the hand-derived known-answer tables of SURVEY.md 8(c).
 Nothing here imports the oracle: the fixtures are independent of it.
 """
 import hashlib
@@ -151,6 +153,52 @@ def golden_pipeline():
         print(name, "valid", out["mask"].mean(), "corr", np.unique(out["corr"], return_counts=True))
 
 
+def numpy_cv2_dyna(frames: np.ndarray, U0: np.ndarray, window: int = 21) -> dict:
+    """StripRegression + FillOtherDeltaProU + U accumulation with numpy cumsum / cv2.blur
+    (CCalculation.cpp:789-892, 595-663), independent of the oracle."""
+    F, H, W = frames.shape
+    half = window // 2
+    strips = np.zeros((F, H, W, 2), np.float32)
+    for f in range(F):
+        cs = np.cumsum(np.vstack([np.zeros((1, W), np.int64), frames[f].astype(np.int64)]), axis=0)
+        S = np.zeros((H, W), np.float32)
+        for h in range(half, H - half):
+            S[h, half:W - half] = (cs[h + half + 1] - cs[h - half])[half:W - half]
+        for h in range(half, H - half):
+            for w in range(half, W - half):
+                win = S[h, w - half:w + half]
+                M, m = win.max(), win.min()
+                strips[f, h, w, 1] = 0 if S[h, w] == M else np.argmax(win) - half
+                strips[f, h, w, 0] = 0 if S[h, w] == m else np.argmin(win) - half
+    dps, Us = [], []
+    U = U0.copy()
+    for f in range(1, F):
+        dB = strips[f - 1, ..., 0] - strips[f, ..., 0]
+        dW = strips[f - 1, ..., 1] - strips[f, ..., 1]
+        t = np.where(np.abs(dB) < np.abs(dW), dB, dW).astype(np.float32)
+        dP = cv2.blur(t, (3, 3))
+        U = U + dP.astype(np.float64)
+        dps.append(dP)
+        Us.append(U.copy())
+    return dict(strips=strips, delta_p=np.stack(dps), proj_u=np.stack(Us))
+
+
+def golden_dyna():
+    base = load_calibration(os.path.join(HERE, "Result.yml"))
+    cfg = StackConfig(96, 72, 1280, 6, 4)
+    cal = synth.synthetic_calibration(cfg, base)
+    scene = synth.make_scene(cfg, cal)
+    planes = synth.render_stack(cfg, scene, noise_sigma=1.0, seed=21)
+    first = numpy_cv2_pipeline(cfg, cal, planes)
+    frames = synth.render_dyna_frames(cfg, cal, 4, stripe_period=14.0, z_step=0.4, noise_sigma=1.5)
+    out = numpy_cv2_dyna(frames, first["proj_u"])
+    np.savez_compressed(os.path.join(HERE, "dyna_g6.npz"),
+                        cfg=np.array([cfg.width, cfg.height, cfg.projector_width, cfg.gray_digits, cfg.phase_steps]),
+                        cam=cal.cam, pro=cal.pro, R=cal.R, T=cal.T, frames=frames, U0=first["proj_u"], z0=first["z"],
+                        **out)
+    print("dyna: nonzero deltaP", [(d != 0).mean() for d in out["delta_p"]])
+
+
 def golden_kat():
     # SURVEY.md 8(c) KAT-E (G=6, PW=1280, T=40, gp=20) and KAT-T (Result.yml)
     kat_e = np.array([
@@ -179,4 +227,5 @@ if __name__ == "__main__":
     if os.path.isdir(REF):
         golden_gray_code()
     golden_pipeline()
+    golden_dyna()
     golden_kat()

@@ -51,6 +51,9 @@ def test_cpp_host_api_matches_oracle(tmp_path, built_library, oracle, base_calib
     with open(d / "vGrayCode.txt", "w") as f:
         for b in range(1 << G):
             f.write(f"{b} {b ^ (b >> 1)}\n")
+    from structured_light_calculation_b200 import synth
+    frames = synth.render_dyna_frames(cfg, cal, 4, stripe_period=14.0, z_step=0.4, noise_sigma=1.5)
+    frames.tofile(d / "dyna.u8")
     res = subprocess.run([exe, str(d), str(W), str(H), str(PW), str(G), str(N)], stdout=subprocess.PIPE,
                          stderr=subprocess.STDOUT, text=True)
     assert res.returncode == 0, res.stdout
@@ -72,3 +75,15 @@ def test_cpp_host_api_matches_oracle(tmp_path, built_library, oracle, base_calib
     assert cloud.shape[0] == int(want["mask"].sum())
     ref = np.stack([want["x"][vv, uu], want["y"][vv, uu], want["z"][vv, uu]], axis=1)
     assert np.allclose(cloud, ref, rtol=2e-5, atol=1e-4)
+    # CalculateOther(): dynamic frames through the class API
+    ocfg = oracle.make_config(W, H, PW, G, N)
+    seq = oracle.dyna_sequence(ocfg, oracle.make_calib(cal.cam, cal.pro, cal.R, cal.T), want["proj_u"], want["z"], frames)
+    dxyzw = np.fromfile(d / "dyna_xyzw.f32", np.float32).reshape(3, H, W, 4)
+    dmask = np.fromfile(d / "dyna_mask.u8", np.uint8).reshape(3, H, W)
+    ddz = np.fromfile(d / "dyna_dz.f32", np.float32).reshape(3, H, W)
+    for f, r in enumerate(seq):
+        assert bits_equal(dmask[f], r["mask"])
+        assert bits_equal(dxyzw[f, ..., 3], r["proj_u"].astype(np.float32))
+        assert np.abs(dxyzw[f, ..., 2] - r["z"]).max() <= tol
+        assert np.abs(ddz[f] - r["delta_z"]).max() <= 2 * tol
+    assert np.loadtxt(d / "cloud_dyn1.txt").reshape(-1, 3).shape[0] == int(seq[0]["mask"].sum())

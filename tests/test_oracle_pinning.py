@@ -188,3 +188,23 @@ def test_div360_fma_sequence_equals_ieee_division(oracle):
     bad, n = oracle.check_div360(1e-30, 360.5)
     assert n > 900_000_000 and bad == 0
     assert np.float32(1.0) / np.float32(360.0) == np.float32(float.fromhex("0x1.6c16c2p-9"))
+
+
+def test_dynamic_frame_golden_bit_exact(oracle):
+    """StripRegression / FillOtherDeltaProU / U accumulation against the numpy + cv2.blur fixture."""
+    g = np.load(os.path.join(GOLDEN, "dyna_g6.npz"))
+    W, H, PW, G, N = [int(v) for v in g["cfg"]]
+    cfg = oracle.make_config(W, H, PW, G, N)
+    cal = oracle.make_calib(g["cam"], g["pro"], g["R"], g["T"])
+    frames = g["frames"]
+    B0, W0 = oracle.strip_regression(cfg, frames[0])
+    assert bits_equal(B0, g["strips"][0, ..., 0]) and bits_equal(W0, g["strips"][0, ..., 1])
+    seq = oracle.dyna_sequence(cfg, cal, g["U0"], g["z0"], frames)
+    assert len(seq) == frames.shape[0] - 1
+    for f, r in enumerate(seq):
+        assert bits_equal(r["strip_b"], g["strips"][f + 1, ..., 0]) and bits_equal(r["strip_w"], g["strips"][f + 1, ..., 1])
+        assert bits_equal(r["delta_p"], g["delta_p"][f])
+        assert bits_equal(r["proj_u"], g["proj_u"][f])
+    # U accumulates exactly: every addend is a multiple of 2^-27 far inside a double
+    total = g["U0"] + g["delta_p"].astype(np.float64).sum(axis=0)
+    assert bits_equal(seq[-1]["proj_u"], total)

@@ -429,6 +429,47 @@ def test_full_size_properties(built_library, oracle, base_calibration, name):
     rec.close()
 
 
+@pytest.mark.parametrize("W,H,window,n_frames", [(320, 128, 21, 6), (200, 75, 21, 4), (96, 64, 9, 5), (64, 48, 33, 3)])
+def test_dynamic_frames_match_oracle(built_library, oracle, base_calibration, W, H, window, n_frames):
+    """CalculateOther (StripRegression + FillOtherDeltaProU + FillCoordinate + deltaZ): strips,
+    blurred deltaP and the accumulated ProjectorU bit-exact, mask bit-exact, XYZ / deltaZ in tolerance."""
+    from structured_light_calculation_b200 import synth
+    from structured_light_calculation_b200.configs import StackConfig
+    cfg = StackConfig(W, H, 1280, 6, 4)
+    cal, scene, planes = make_case(cfg, base_calibration, noise=1.0, seed=9)
+    first = oracle_run(oracle, cfg, cal, planes)
+    frames = synth.render_dyna_frames(cfg, cal, n_frames, stripe_period=14.0, z_step=0.4, noise_sigma=1.5)
+    if window == 33:   # exercise ties: large flat regions
+        frames[:, : H // 2, :] = 100
+    ocfg = oracle.make_config(W, H, cfg.projector_width, cfg.gray_digits, cfg.phase_steps)
+    ocal = oracle.make_calib(cal.cam, cal.pro, cal.R, cal.T)
+    want = oracle.dyna_sequence(ocfg, ocal, first["proj_u"], first["z"], frames, window)
+    rec = _reconstructor(cfg, cal)
+    got = rec.dyna_track(frames, first["proj_u"], window=window, parity=True)
+    plain = rec.dyna_track(frames, first["proj_u"], window=window, parity=False)
+    assert rec.launch_count() == 4      # 2 kernels per sequence
+    rec.close()
+    assert bits_equal(plain["xyzw"], got["xyzw"]) and bits_equal(plain["mask"], got["mask"])
+    B0, W0 = oracle.strip_regression(ocfg, frames[0], window)
+    assert bits_equal(got["strips"][0, ..., 0].astype(np.float32), B0)
+    assert bits_equal(got["strips"][0, ..., 1].astype(np.float32), W0)
+    tol = XYZ_REL_TOL * (cfg.fov_max - cfg.fov_min)
+    moved = 0
+    for f, w in enumerate(want):
+        assert bits_equal(got["strips"][f + 1, ..., 0].astype(np.float32), w["strip_b"]), f"stripB frame {f + 1}"
+        assert bits_equal(got["strips"][f + 1, ..., 1].astype(np.float32), w["strip_w"]), f"stripW frame {f + 1}"
+        assert bits_equal(got["delta_p"][f], w["delta_p"]), f"deltaP frame {f + 1}"
+        assert bits_equal(got["proj_u"][f], w["proj_u"]), f"ProjectorU frame {f + 1}"
+        assert bits_equal(got["mask"][f], w["mask"]), f"mask frame {f + 1}"
+        assert bits_equal(got["xyzw"][f, ..., 3], w["proj_u"].astype(np.float32))
+        for ch, key in enumerate("xyz"):
+            assert np.abs(got["xyzw"][f, ..., ch] - w[key]).max() <= tol, (f, key)
+        assert np.abs(got["delta_z"][f] - w["delta_z"]).max() <= 2 * tol, f"deltaZ frame {f + 1}"
+        moved += int((w["delta_p"] != 0).sum())
+    if window == 21:
+        assert moved > 0     # the tracker saw motion
+
+
 def test_smoke_entry_point(built_library):
     import __graft_entry__
     __graft_entry__.smoke()
