@@ -51,6 +51,7 @@ struct slc_context {
     void* d_scratch_out = nullptr; size_t scratch_out_bytes = 0;
     void* d_scratch_aux = nullptr; size_t scratch_aux_bytes = 0;
     void* d_strips = nullptr;      size_t strips_bytes = 0;      // dynamic frames: (stripB, stripW) per frame
+    void* d_dsums = nullptr;       size_t dsums_bytes = 0;       // dynamic frames: 3x3 sums of the nearer delta
     void* d_dyna = nullptr;        size_t dyna_bytes = 0;        // dynamic frames: staging for the host entry point
     long long launches = 0;
     std::string err;
@@ -313,7 +314,7 @@ void slc_destroy(slc_context* ctx)
     if (ctx->stream) { cudaStreamSynchronize(ctx->stream); cudaStreamDestroy(ctx->stream); }
     cudaFree(ctx->d_lut);
     cudaFree(ctx->d_scratch_in); cudaFree(ctx->d_scratch_out); cudaFree(ctx->d_scratch_aux);
-    cudaFree(ctx->d_strips); cudaFree(ctx->d_dyna);
+    cudaFree(ctx->d_strips); cudaFree(ctx->d_dsums); cudaFree(ctx->d_dyna);
     delete ctx;
 }
 
@@ -660,7 +661,12 @@ int slc_dyna_track_device(slc_context* ctx, const uint8_t* d_frames, int32_t n_f
     SLC_CUDA(ctx, slc::launch_strip_regression(d_frames, n_frames, ctx->kp.W, ctx->kp.H, window, strips, st));
     ctx->launches++;
     if (n_frames > 1) {
-        SLC_CUDA(ctx, slc::launch_dyna_track(ctx->kp, strips, n_frames, d_u0, d_xyzw, d_mask, d_delta_z,
+        rc = ensure_scratch(ctx, &ctx->d_dsums, &ctx->dsums_bytes, 2 * npx * (size_t)(n_frames - 1));
+        if (rc != SLC_OK) return rc;
+        unsigned short* sums = static_cast<unsigned short*>(ctx->d_dsums);
+        SLC_CUDA(ctx, slc::launch_delta_sum(strips, n_frames, ctx->kp.W, ctx->kp.H, sums, st));
+        ctx->launches++;
+        SLC_CUDA(ctx, slc::launch_dyna_track(ctx->kp, sums, n_frames, d_u0, d_xyzw, d_mask, d_delta_z,
                                              d_parity ? d_parity->delta_p : nullptr,
                                              d_parity ? d_parity->proj_u : nullptr, nullptr, st));
         ctx->launches++;

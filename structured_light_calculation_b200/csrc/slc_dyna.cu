@@ -89,6 +89,304 @@ strip_regression_kernel(const uint8_t* __restrict__ frames, char2* __restrict__ 
     }
 }
 
+// ---- StripRegression, window 21 (the reference's RECO_WINDOW_SIZE), fast path ----------
+// Tile: 160 output columns x 32 rows per block.
+//  Phase 1 (184 threads): a thread owns 4 adjacent columns (one 32-bit load per image row) and
+//    8 consecutive rows; the 21-row sums live as 16-bit lanes of two registers (<= 5355, no
+//    carries), built once from 21 rows and then slid down 7 times.  Each sum goes to shared
+//    memory as a key  sum << 9 | 0x100 | tile_column.
+//  Phase 2 (256 threads): a thread owns 20 consecutive outputs of one row.  Their 20-column
+//    windows [w-10, w+9] all straddle one boundary between two 20-element blocks, so the window
+//    minimum is min(suffix-minimum of block 1, prefix-minimum of block 2) (van Herk / Gil-Werman):
+//    3 min ops per output instead of 19.  The maximum is the minimum of the complemented key
+//    (8191 - sum) << 9 | 0x100 | tile_column, so for both the smaller column wins a tie -- the
+//    first occurrence in the reference's left-to-right scan (CCalculation.cpp:833-849).  The scan
+//    starts from the centre with offset 0 and replaces on strict </> only, i.e. the centre wins
+//    every tie: a third candidate, the centre's key with bit 8 cleared, does that in the same
+//    3-input min, and its column field decodes to offset 0.
+constexpr int kVhW = 160, kVhH = 64, kVhHalf = 10, kVhPad = 12;
+constexpr int kVhCols = kVhW + 2 * kVhPad;        // 184 key columns: tile column tc <-> image column x0 - 12 + tc
+constexpr int kVhQuads = kVhCols / 4;             // 46
+constexpr int kVhSeg = 16;                        // rows per phase-1 thread
+constexpr int kVhStride = kVhCols + 2;            // 186 words: conflict-free 8-byte reads in phase 2
+constexpr int kVhOut = 20;                        // outputs per phase-2 thread (= window - 1)
+constexpr unsigned kVhFlag = 0x100u;
+constexpr unsigned kVhInv = 8191u << 9;
+
+// kInterior: every load is in bounds, every sum is valid and every output is inside the
+// reference's [10, H-10) x [10, W-10) region -- no predicates anywhere.
+template <bool kInterior>
+__device__ __forceinline__ void strip21_tile(const uint8_t* __restrict__ img, char2* __restrict__ out, int W, int H,
+                                             int x0, int y0, uint32_t (*s_key)[kVhStride])
+{
+    const int t = threadIdx.x;
+    if (t < kVhQuads * (kVhH / kVhSeg)) {
+        const int q = t % kVhQuads, seg = t / kVhQuads;
+        const int c0 = x0 - kVhPad + 4 * q;               // W % 4 == 0: the quad is inside or outside as a whole
+        const int hb = y0 + seg * kVhSeg;
+        const bool col_in = kInterior || ((c0 >= 0) && (c0 < W));
+        const uint8_t* colp = img + c0;
+        auto ld = [&](int row) -> uint32_t {
+            if (kInterior) return __ldg(reinterpret_cast<const uint32_t*>(colp + (long long)row * W));
+            return (col_in && row >= 0 && row < H)
+                       ? __ldg(reinterpret_cast<const uint32_t*>(colp + (long long)row * W)) : 0u;
+        };
+        uint32_t lo = 0, hi = 0;                          // 16-bit lanes: (col0, col2) and (col1, col3)
+#pragma unroll
+        for (int k = -kVhHalf; k <= kVhHalf; k++) {
+            const uint32_t w = ld(hb + k);
+            lo += w & 0x00FF00FFu;
+            hi += __byte_perm(w, 0u, 0x4341);
+        }
+        // valSum is 0 outside [10, H-10) x [10, W-10) (the zero-initialised Mat, CCalculation.cpp:801-823)
+        bool cok[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) cok[j] = kInterior || ((unsigned)(c0 + j - kVhHalf) < (unsigned)(W - 2 * kVhHalf));
+        const uint32_t kbase = kVhFlag | (unsigned)(4 * q);
+#pragma unroll
+        for (int r = 0; r < kVhSeg; r++) {
+            const int h = hb + r;
+            if (r > 0) {
+                const uint32_t wa = ld(h + kVhHalf), ws = ld(h - kVhHalf - 1);
+                lo = lo + (wa & 0x00FF00FFu) - (ws & 0x00FF00FFu);
+                hi = hi + __byte_perm(wa, 0u, 0x4341) - __byte_perm(ws, 0u, 0x4341);
+            }
+            const bool row_ok = kInterior || ((h >= kVhHalf) && (h < H - kVhHalf));
+            const uint32_t sv[4] = {lo & 0xFFFFu, hi & 0xFFFFu, lo >> 16, hi >> 16};
+            uint32_t key[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                key[j] = ((row_ok && cok[j]) ? sv[j] : 0u) * 512u + (kbase + (unsigned)j);
+            uint2* dst = reinterpret_cast<uint2*>(&s_key[seg * kVhSeg + r][4 * q]);
+            dst[0] = make_uint2(key[0], key[1]);
+            dst[1] = make_uint2(key[2], key[3]);
+        }
+    }
+    __syncthreads();
+
+    const int g = t & 7;
+    const int wbase = x0 + kVhOut * g;
+    const int cb = kVhOut * g + 2;                        // tile column of window element j = 0  (= wbase - 10)
+    const uint32_t K2 = kVhInv + 2u * (kVhFlag + (unsigned)cb);   // complemented key of element j:  K2 + 2j - key_j
+    const uint32_t negc = (uint32_t)(-(cb + kVhHalf));    // -(tile column of output 0)
+#pragma unroll 1
+    for (int r = t >> 3; r < kVhH; r += 32) {
+        const int h = y0 + r;
+        if (!kInterior && (h >= H || wbase >= W)) break;
+        const uint2* rowp = reinterpret_cast<const uint2*>(&s_key[r][cb]);
+        uint32_t smn[kVhOut], smx[kVhOut];                // suffix minima of block 1 (j = 0..19)
+        uint32_t cmn[kVhOut], cmx[kVhOut];                // centre candidates: element j = i + 10, bit 8 cleared
+#pragma unroll
+        for (int j2 = 0; j2 < kVhOut / 2; j2++) {
+            const uint2 e = rowp[j2];
+            smn[2 * j2] = e.x;
+            smn[2 * j2 + 1] = e.y;
+        }
+#pragma unroll
+        for (int j = 0; j < kVhOut; j++) smx[j] = K2 + 2u * (unsigned)j - smn[j];
+#pragma unroll
+        for (int j = kVhHalf; j < kVhOut; j++) {
+            cmn[j - kVhHalf] = smn[j] - kVhFlag;
+            cmx[j - kVhHalf] = smx[j] - kVhFlag;
+        }
+#pragma unroll
+        for (int j = kVhOut - 2; j >= 0; j--) {
+            smn[j] = min(smn[j], smn[j + 1]);
+            smx[j] = min(smx[j], smx[j + 1]);
+        }
+        uint32_t e2[kVhOut];                              // block 2 (j = 20..39; j = 39 is never used)
+#pragma unroll
+        for (int j2 = 0; j2 < kVhOut / 2; j2++) {
+            const uint2 e = rowp[kVhOut / 2 + j2];
+            e2[2 * j2] = e.x;
+            e2[2 * j2 + 1] = e.y;
+        }
+        uint32_t pmn = 0xFFFFFFFFu, pmx = 0xFFFFFFFFu;
+        uint32_t bn[kVhOut], bx[kVhOut];                  // low byte = offset of the minimum / maximum
+#pragma unroll
+        for (int i = 0; i < kVhOut; i++) {
+            if (i >= 1) {
+                const int j = kVhOut - 1 + i;             // newest element of the window
+                const uint32_t ej = e2[j - kVhOut];
+                const uint32_t xj = K2 + 2u * (unsigned)j - ej;
+                pmn = min(pmn, ej);
+                pmx = min(pmx, xj);
+                if (j < kVhOut + kVhHalf) {
+                    cmn[j - kVhHalf] = ej - kVhFlag;
+                    cmx[j - kVhHalf] = xj - kVhFlag;
+                }
+            }
+            const uint32_t kn = min(min(smn[i], pmn), cmn[i]);
+            const uint32_t kx = min(min(smx[i], pmx), cmx[i]);
+            bn[i] = kn + negc - (unsigned)i;              // column field - column of output i
+            bx[i] = kx + negc - (unsigned)i;
+        }
+        uint32_t packed[kVhOut / 2];                      // two pixels per word: (B, W, B, W)
+#pragma unroll
+        for (int m = 0; m < kVhOut / 2; m++) {
+            const uint32_t nn = __byte_perm(bn[2 * m], bn[2 * m + 1], 0x0040);   // (B0, B1, ., .)
+            const uint32_t xx = __byte_perm(bx[2 * m], bx[2 * m + 1], 0x0040);   // (W0, W1, ., .)
+            packed[m] = __byte_perm(nn, xx, 0x5140);
+        }
+        char2* dst = out + (long long)h * W + wbase;
+        const bool row_in = (h >= kVhHalf) && (h < H - kVhHalf);
+        if (kInterior || (row_in && (wbase >= kVhHalf) && (wbase + kVhOut <= W - kVhHalf))) {
+#pragma unroll
+            for (int m = 0; m < kVhOut / 4; m++)
+                reinterpret_cast<uint2*>(dst)[m] = make_uint2(packed[2 * m], packed[2 * m + 1]);
+        } else {
+#pragma unroll
+            for (int i = 0; i < kVhOut; i++) {
+                const int w = wbase + i;
+                if (w < W) {
+                    const bool in = row_in && (w >= kVhHalf) && (w < W - kVhHalf);
+                    const uint32_t pr = in ? ((packed[i >> 1] >> ((i & 1) * 16)) & 0xFFFFu) : 0u;
+                    dst[i] = make_char2((signed char)(pr & 0xFFu), (signed char)(pr >> 8));
+                }
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256, 3)
+strip_regression21_kernel(const uint8_t* __restrict__ frames, char2* __restrict__ strips, int W, int H)
+{
+    __shared__ __align__(16) uint32_t s_key[kVhH][kVhStride];
+    const long long npx = (long long)W * H;
+    const uint8_t* img = frames + (long long)blockIdx.z * npx;
+    char2* out = strips + (long long)blockIdx.z * npx;
+    const int x0 = blockIdx.x * kVhW, y0 = blockIdx.y * kVhH;
+    const bool interior = (x0 >= kVhPad + kVhHalf) && (x0 + kVhW + kVhPad + kVhHalf <= W) &&
+                          (y0 >= kVhHalf) && (y0 + kVhH + kVhHalf <= H);
+    if (interior) strip21_tile<true>(img, out, W, H, x0, y0, s_key);
+    else strip21_tile<false>(img, out, W, H, x0, y0, s_key);
+}
+
+// ---- FillOtherDeltaProU up to the blur's 3x3 sum (CCalculation.cpp:603-650) ----------------
+// sums[f-1](h,w) = 576 + the sum over the 3x3 neighbourhood (BORDER_REFLECT_101) of the
+// nearer-of-two delta between frames f-1 and f (each in [-19, 19]), stored as u16.  grid.z = f - 1.
+constexpr int kDsBias = 64, kDsBias9 = 9 * kDsBias;
+
+// generic path: any width / alignment
+constexpr int kDgW = 128, kDgH = 8;
+
+__global__ void __launch_bounds__(256)
+delta_sum_generic_kernel(const char2* __restrict__ strips, unsigned short* __restrict__ sums, int W, int H)
+{
+    __shared__ short s_t[kDgH + 2][kDgW + 2];
+    const long long npx = (long long)W * H;
+    const char2* s0 = strips + (long long)blockIdx.z * npx;
+    const char2* s1 = s0 + npx;
+    const int x0 = blockIdx.x * kDgW, y0 = blockIdx.y * kDgH;
+    for (int e = threadIdx.x; e < (kDgH + 2) * (kDgW + 2); e += 256) {
+        const int ry = e / (kDgW + 2), rx = e % (kDgW + 2);
+        const int y = reflect101(min(y0 + ry - 1, H), H), x = reflect101(min(x0 + rx - 1, W), W);
+        const char2 a = s0[(long long)y * W + x], b = s1[(long long)y * W + x];
+        const int dB = (int)a.x - (int)b.x;       // f0B - f1B   (CCalculation.cpp:603-617)
+        const int dW = (int)a.y - (int)b.y;       // f0W - f1W
+        s_t[ry][rx] = (short)((abs(dB) < abs(dW)) ? dB : dW);
+    }
+    __syncthreads();
+    unsigned short* dst = sums + (long long)blockIdx.z * npx;
+    for (int e = threadIdx.x; e < kDgH * kDgW; e += 256) {
+        const int ry = e / kDgW, rx = e % kDgW;
+        const int y = y0 + ry, x = x0 + rx;
+        if (y >= H || x >= W) continue;
+        int s = kDsBias9;
+#pragma unroll
+        for (int dy = 0; dy < 3; dy++)
+#pragma unroll
+            for (int dx = 0; dx < 3; dx++) s += s_t[ry + dy][rx + dx];
+        dst[(long long)y * W + x] = (unsigned short)s;
+    }
+}
+
+// fast path (W % 8 == 0): byte / 16-bit-lane SIMD throughout.
+//  producer: 4 pixels per item; per 32-bit word (2 pixels x (B, W)):  D = a - b + 64 per byte,
+//    |d| by VABSDIFF4, the nearer of (dB, dW) picked per 16-bit lane -> biased delta in [45, 83];
+//  consumer: 8 pixels per thread; vertical 3-sum = one 3-input add per word, horizontal 3-sum =
+//    two funnel shifts + one 3-input add per word (16-bit lanes, <= 747, no carries).
+constexpr int kDsW = 128, kDsH = 16;
+constexpr int kDsLead = 4;                          // smem index of image column x is x - x0 + 4
+constexpr int kDsCols = kDsW + 8;                   // x0-4 .. x0+131
+constexpr int kDsQuads = kDsCols / 4;               // 34
+constexpr int kDsRows = kDsH + 2;
+
+__device__ __forceinline__ uint32_t nearer_delta_lanes(uint32_t a, uint32_t b)
+{
+    // a, b: (B0, W0, B1, W1) signed bytes of frame f-1 and frame f, each in [-10, 9]
+    const uint32_t D = (a ^ 0x80808080u) + 0x40404040u - (b ^ 0x80808080u);   // d + 64 per byte, no borrows
+    const uint32_t ab = __vabsdiffu4(D, 0x40404040u);                          // |d| per byte
+    const uint32_t absB = ab & 0x00FF00FFu, absW = __byte_perm(ab, 0u, 0x4341);
+    const uint32_t Z = absB + 0x00800080u - absW;        // bit 7 of a lane set <=> |dB| >= |dW| -> take dW
+    uint32_t sel;
+    asm("prmt.b32 %0, %1, %2, 0x4a48;" : "=r"(sel) : "r"(Z), "r"(0u));   // 0x00FF per lane whose bit 7 is set
+    const uint32_t DB = D & 0x00FF00FFu, DW = __byte_perm(D, 0u, 0x4341);
+    return DB ^ ((DB ^ DW) & sel);                       // (abs(dB) < abs(dW)) ? dB : dW   (CCalculation.cpp:603-617)
+}
+
+__global__ void __launch_bounds__(256)
+delta_sum_kernel(const char2* __restrict__ strips, unsigned short* __restrict__ sums, int W, int H)
+{
+    __shared__ __align__(16) unsigned short s_d[kDsRows][kDsCols];
+    const long long npx = (long long)W * H;
+    const char2* s0 = strips + (long long)blockIdx.z * npx;
+    const char2* s1 = s0 + npx;
+    const int x0 = blockIdx.x * kDsW, y0 = blockIdx.y * kDsH;
+    const int t = threadIdx.x;
+
+    for (int e = t; e < kDsRows * kDsQuads; e += 256) {
+        const int ry = e / kDsQuads, qx = e - ry * kDsQuads;
+        const int y = y0 + ry - 1, x = x0 - kDsLead + 4 * qx;
+        uint2 res = make_uint2(0x00400040u, 0x00400040u);
+        if (y >= 0 && y < H && x >= 0 && x < W) {
+            const uint2 a = __ldg(reinterpret_cast<const uint2*>(s0 + (long long)y * W + x));
+            const uint2 b = __ldg(reinterpret_cast<const uint2*>(s1 + (long long)y * W + x));
+            res.x = nearer_delta_lanes(a.x, b.x);
+            res.y = nearer_delta_lanes(a.y, b.y);
+        }
+        *reinterpret_cast<uint2*>(&s_d[ry][4 * qx]) = res;
+    }
+    __syncthreads();
+    // cv::blur's default border (BORDER_REFLECT_101): column -1 = column 1, column W = column W-2,
+    // then the same for rows (so the corners mirror on both axes)
+    const bool left = (x0 == 0), right = (W - x0 <= kDsW);
+    const bool top = (y0 == 0), bottom = (H - y0 <= kDsH);
+    if (left || right || top || bottom) {
+        if (t < kDsRows) {
+            if (left) s_d[t][kDsLead - 1] = s_d[t][kDsLead + 1];
+            if (right) s_d[t][W - x0 + kDsLead] = s_d[t][W - 2 - x0 + kDsLead];
+        }
+        __syncthreads();
+        if (t < kDsCols) {
+            if (top) s_d[0][t] = s_d[2][t];
+            if (bottom) s_d[H - y0 + 1][t] = s_d[H - y0 - 1][t];
+        }
+        __syncthreads();
+    }
+    const int k = t & 15, ry = t >> 4;
+    const int y = y0 + ry, c = x0 + 8 * k;
+    if (y >= H || c >= W) return;
+    uint32_t V[8];
+#pragma unroll
+    for (int rr = 0; rr < 3; rr++) {
+        const uint4 lo = *reinterpret_cast<const uint4*>(&s_d[ry + rr][8 * k]);        // columns c-4 .. c+3
+        const uint4 hi = *reinterpret_cast<const uint4*>(&s_d[ry + rr][8 * k + 8]);    // columns c+4 .. c+11
+        const uint32_t w[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+#pragma unroll
+        for (int i = 1; i < 7; i++) V[i] = (rr == 0) ? w[i] : V[i] + w[i];
+    }
+    uint32_t S[4];
+#pragma unroll
+    for (int m = 0; m < 4; m++) {
+        const uint32_t L = __funnelshift_l(V[m + 1], V[m + 2], 16);     // columns (c+2m-1, c+2m)
+        const uint32_t R = __funnelshift_l(V[m + 2], V[m + 3], 16);     // columns (c+2m+1, c+2m+2)
+        S[m] = L + V[m + 2] + R;
+    }
+    unsigned short* dst = sums + (long long)blockIdx.z * npx + (long long)y * W + c;
+    *reinterpret_cast<uint4*>(dst) = make_uint4(S[0], S[1], S[2], S[3]);
+}
+
 // z_exact + FOV test for a projector column held in f64
 static __device__ __noinline__ float4 resolve_f64_u(const KParams& p, double U, int u, int v, int* valid_out)
 {
@@ -108,8 +406,10 @@ struct DynaOut {
     double* u_final;    // optional: U after the last frame (state for a following call)
 };
 
+// The frame-to-frame recurrence U[f] = U[f-1] + deltaP[f] (CCalculation.cpp:656-658) is per
+// pixel: one thread walks all frames of its pixel, then FillCoordinate (:672-775) per frame.
 __global__ void __launch_bounds__(256)
-dyna_track_kernel(const __grid_constant__ KParams p, const char2* __restrict__ strips, int n_frames,
+dyna_track_kernel(const __grid_constant__ KParams p, const unsigned short* __restrict__ sums, int n_frames,
                   const double* __restrict__ u0, const DynaOut o)
 {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -118,18 +418,6 @@ dyna_track_kernel(const __grid_constant__ KParams p, const char2* __restrict__ s
     split_row_col(p, (unsigned)idx, v, u);
     const RowConst rc = make_row_const(p, v);
     const float uf = (float)u;
-
-    // the 3x3 neighbourhood with cv::blur's default border (BORDER_REFLECT_101)
-    int nb[9];
-#pragma unroll
-    for (int dy = -1; dy <= 1; dy++)
-#pragma unroll
-        for (int dx = -1; dx <= 1; dx++)
-            nb[(dy + 1) * 3 + (dx + 1)] = reflect101(v + dy, p.H) * p.W + reflect101(u + dx, p.W);
-
-    char2 prev[9];
-#pragma unroll
-    for (int k = 0; k < 9; k++) prev[k] = strips[nb[k]];
 
     double U = u0[idx];
     // z of the frame before the first dynamic one: FillCoordinate(0) on U0 (CCalculation.cpp:189)
@@ -140,36 +428,35 @@ dyna_track_kernel(const __grid_constant__ KParams p, const char2* __restrict__ s
         if (U != 0.0) r0 = resolve_f64_u(p, U, u, v, &ok);
         z_prev = r0.z;
     }
-
-    for (int f = 1; f < n_frames; f++) {
-        const char2* cur_plane = strips + (long long)f * p.npx;
-        int s = 0;
+    constexpr int kAhead = 4;
+    for (int f0 = 1; f0 < n_frames; f0 += kAhead) {
+        unsigned short sv[kAhead];
 #pragma unroll
-        for (int k = 0; k < 9; k++) {
-            const char2 c = cur_plane[nb[k]];
-            const int dB = (int)prev[k].x - (int)c.x;       // f0B - f1B   (CCalculation.cpp:603-617)
-            const int dW = (int)prev[k].y - (int)c.y;       // f0W - f1W
-            s += (abs(dB) < abs(dW)) ? dB : dW;
-            prev[k] = c;
+        for (int k = 0; k < kAhead; k++)
+            sv[k] = (f0 + k < n_frames) ? __ldcs(sums + (long long)(f0 + k - 1) * p.npx + idx) : (unsigned short)kDsBias9;
+#pragma unroll
+        for (int k = 0; k < kAhead; k++) {
+            const int f = f0 + k;
+            if (f >= n_frames) break;
+            // cv::blur on CV_32F: double sum, * (1./9), narrowed to float (:650)
+            const float dP = (float)__dmul_rn((double)((int)sv[k] - kDsBias9), 1.0 / 9.0);
+            U = __dadd_rn(U, (double)dP);                        // :656-658
+            // FillCoordinate (:672-771): f32 solve on U split exactly into two floats
+            const float a = (float)U;
+            const float b = (float)(U - (double)a);
+            PixelResult r;
+            triangulate_split<false>(p, rc, a, b, U != 0.0, uf, r);
+            float4 outv = make_float4(r.x, r.y, r.z, r.w);
+            int ok = r.valid ? 1 : 0;
+            if (r.need64) outv = resolve_f64_u(p, U, u, v, &ok);
+            const long long q = (long long)(f - 1) * p.npx + idx;
+            st_stream_f4(o.xyzw + q, outv);
+            o.mask[q] = (uint8_t)ok;
+            if (o.delta_z) o.delta_z[q] = outv.z - z_prev;       // :772-775
+            if (o.delta_p) o.delta_p[q] = dP;
+            if (o.proj_u) o.proj_u[q] = U;
+            z_prev = outv.z;
         }
-        // cv::blur on CV_32F: double sum, * (1./9), narrowed to float (:650)
-        const float dP = (float)__dmul_rn((double)s, 1.0 / 9.0);
-        U = __dadd_rn(U, (double)dP);                        // :656-658
-        // FillCoordinate (:672-771): f32 solve on U split exactly into two floats
-        const float a = (float)U;
-        const float b = (float)(U - (double)a);
-        PixelResult r;
-        triangulate_split<false>(p, rc, a, b, U != 0.0, uf, r);
-        float4 outv = make_float4(r.x, r.y, r.z, r.w);
-        int ok = r.valid ? 1 : 0;
-        if (r.need64) outv = resolve_f64_u(p, U, u, v, &ok);
-        const long long q = (long long)(f - 1) * p.npx + idx;
-        o.xyzw[q] = outv;
-        o.mask[q] = (uint8_t)ok;
-        if (o.delta_z) o.delta_z[q] = outv.z - z_prev;       // :772-775
-        if (o.delta_p) o.delta_p[q] = dP;
-        if (o.proj_u) o.proj_u[q] = U;
-        z_prev = outv.z;
     }
     if (o.u_final) o.u_final[idx] = U;
 }
@@ -181,12 +468,35 @@ cudaError_t launch_strip_regression(const uint8_t* d_frames, int n_frames, int W
 {
     const int half = window / 2;
     if (half < 1 || half > kSrMaxHalf || n_frames < 1 || n_frames > 65535) return cudaErrorInvalidValue;
-    dim3 grid((W + kSrTileW - 1) / kSrTileW, (H + kSrTileH - 1) / kSrTileH, n_frames);
-    strip_regression_kernel<<<grid, 256, 0, stream>>>(d_frames, reinterpret_cast<char2*>(d_strips), W, H, half);
+    const bool aligned = (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(d_frames) & 3) == 0) &&
+                         ((reinterpret_cast<uintptr_t>(d_strips) & 7) == 0);
+    if (half == kVhHalf && aligned) {
+        dim3 grid((W + kVhW - 1) / kVhW, (H + kVhH - 1) / kVhH, n_frames);
+        strip_regression21_kernel<<<grid, 256, 0, stream>>>(d_frames, reinterpret_cast<char2*>(d_strips), W, H);
+    } else {
+        dim3 grid((W + kSrTileW - 1) / kSrTileW, (H + kSrTileH - 1) / kSrTileH, n_frames);
+        strip_regression_kernel<<<grid, 256, 0, stream>>>(d_frames, reinterpret_cast<char2*>(d_strips), W, H, half);
+    }
     return cudaGetLastError();
 }
 
-cudaError_t launch_dyna_track(KParams p, const signed char* d_strips, int n_frames, const double* d_u0,
+cudaError_t launch_delta_sum(const signed char* d_strips, int n_frames, int W, int H, unsigned short* d_sums,
+                             cudaStream_t stream)
+{
+    if (n_frames < 2) return cudaSuccess;
+    const bool aligned = (W % 8 == 0) && ((reinterpret_cast<uintptr_t>(d_strips) & 7) == 0) &&
+                         ((reinterpret_cast<uintptr_t>(d_sums) & 15) == 0);
+    if (aligned) {
+        dim3 grid((W + kDsW - 1) / kDsW, (H + kDsH - 1) / kDsH, n_frames - 1);
+        delta_sum_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const char2*>(d_strips), d_sums, W, H);
+    } else {
+        dim3 grid((W + kDgW - 1) / kDgW, (H + kDgH - 1) / kDgH, n_frames - 1);
+        delta_sum_generic_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const char2*>(d_strips), d_sums, W, H);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_dyna_track(KParams p, const unsigned short* d_sums, int n_frames, const double* d_u0,
                               float* d_xyzw, uint8_t* d_mask, float* d_delta_z, float* d_delta_p,
                               double* d_proj_u, double* d_u_final, cudaStream_t stream)
 {
@@ -194,8 +504,7 @@ cudaError_t launch_dyna_track(KParams p, const signed char* d_strips, int n_fram
                       ? ((1ull << 40) / (unsigned long long)p.W + 1ull) : 0ull;
     DynaOut o{reinterpret_cast<float4*>(d_xyzw), d_mask, d_delta_z, d_delta_p, d_proj_u, d_u_final};
     const long long blocks = (p.npx + 255) / 256;
-    dyna_track_kernel<<<(unsigned)blocks, 256, 0, stream>>>(p, reinterpret_cast<const char2*>(d_strips), n_frames,
-                                                           d_u0, o);
+    dyna_track_kernel<<<(unsigned)blocks, 256, 0, stream>>>(p, d_sums, n_frames, d_u0, o);
     return cudaGetLastError();
 }
 

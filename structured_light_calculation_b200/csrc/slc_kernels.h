@@ -32,7 +32,9 @@ cudaError_t launch_eval_phase(const float* d_s, const float* d_c, long long n, f
 // dynamic frames (slc_dyna.cu)
 cudaError_t launch_strip_regression(const uint8_t* d_frames, int n_frames, int W, int H, int window,
                                     signed char* d_strips, cudaStream_t stream);
-cudaError_t launch_dyna_track(KParams p, const signed char* d_strips, int n_frames, const double* d_u0,
+cudaError_t launch_delta_sum(const signed char* d_strips, int n_frames, int W, int H, unsigned short* d_sums,
+                             cudaStream_t stream);
+cudaError_t launch_dyna_track(KParams p, const unsigned short* d_sums, int n_frames, const double* d_u0,
                               float* d_xyzw, uint8_t* d_mask, float* d_delta_z, float* d_delta_p,
                               double* d_proj_u, double* d_u_final, cudaStream_t stream);
 

@@ -429,7 +429,10 @@ def test_full_size_properties(built_library, oracle, base_calibration, name):
     rec.close()
 
 
-@pytest.mark.parametrize("W,H,window,n_frames", [(320, 128, 21, 6), (200, 75, 21, 4), (96, 64, 9, 5), (64, 48, 33, 3)])
+@pytest.mark.parametrize("W,H,window,n_frames", [(320, 128, 21, 6), (200, 75, 21, 4), (96, 64, 9, 5), (64, 48, 33, 3),
+                                                 (512, 160, 21, 4),    # interior tiles of the window-21 fast path
+                                                 (204, 70, 21, 3),     # W % 8 != 0: generic 3x3-sum kernel
+                                                 (202, 66, 21, 3)])    # W % 4 != 0: generic strip kernel
 def test_dynamic_frames_match_oracle(built_library, oracle, base_calibration, W, H, window, n_frames):
     """CalculateOther (StripRegression + FillOtherDeltaProU + FillCoordinate + deltaZ): strips,
     blurred deltaP and the accumulated ProjectorU bit-exact, mask bit-exact, XYZ / deltaZ in tolerance."""
@@ -441,13 +444,18 @@ def test_dynamic_frames_match_oracle(built_library, oracle, base_calibration, W,
     frames = synth.render_dyna_frames(cfg, cal, n_frames, stripe_period=14.0, z_step=0.4, noise_sigma=1.5)
     if window == 33:   # exercise ties: large flat regions
         frames[:, : H // 2, :] = 100
+    if W in (512, 204):  # ties inside the fast path: flat, saturated and two-level regions
+        frames[:, : H // 3, : W // 2] = 255
+        frames[1:, H // 3: H // 2, W // 4:] = 0
+        frames[:, H // 2: H // 2 + 30, ::7] = 17
+        frames[:, H // 2: H // 2 + 30, 1::7] = 17
     ocfg = oracle.make_config(W, H, cfg.projector_width, cfg.gray_digits, cfg.phase_steps)
     ocal = oracle.make_calib(cal.cam, cal.pro, cal.R, cal.T)
     want = oracle.dyna_sequence(ocfg, ocal, first["proj_u"], first["z"], frames, window)
     rec = _reconstructor(cfg, cal)
     got = rec.dyna_track(frames, first["proj_u"], window=window, parity=True)
     plain = rec.dyna_track(frames, first["proj_u"], window=window, parity=False)
-    assert rec.launch_count() == 4      # 2 kernels per sequence
+    assert rec.launch_count() == 6      # 3 kernels per sequence
     rec.close()
     assert bits_equal(plain["xyzw"], got["xyzw"]) and bits_equal(plain["mask"], got["mask"])
     B0, W0 = oracle.strip_regression(ocfg, frames[0], window)
