@@ -177,7 +177,10 @@ public:
     bool Init();
     bool CalculateFirst();
     bool CalculateOther();      // dynamic frames 1 .. DYNAFRAME_MAXNUM-1 (CCalculation.cpp:208-320)
-    bool Result(std::string fileName, int i);
+    bool Result(std::string fileName, int i);       // the reference's text cloud, formatted on the device
+    bool ResultPly(std::string fileName, int i);    // binary little-endian PLY of the same points
+    // line ends / exponent digits of Result(): crlf + exp3 reproduce a Windows MSVC 2013 run byte for byte
+    void SetResultTextStyle(bool crlf, bool exp3) { m_textFlags = (crlf ? SLC_TEXT_CRLF : 0u) | (exp3 ? SLC_TEXT_EXP3 : 0u); }
     void SetDynamicPointCloudPrefix(const std::string& prefix) { m_pcDynaPrefix = prefix; }   // "cFrame" + idx + ".txt"
 
     // results of frame 0 (valid after CalculateFirst): CV_32FC4 (x,y,z,U) and CV_8UC1 mask,
@@ -205,7 +208,8 @@ private:
     std::string m_pcFile = "iFrame.txt";
     uint8_t* pinned_stack_ = nullptr;
     Mat m_xyzw, m_mask, m_projU;
-    std::vector<Mat> m_dynXyzw, m_dynMask, m_dynDeltaZ;
+    std::vector<Mat> m_dynXyzw, m_dynMask, m_dynDeltaZ, m_dynProjU;
+    uint32_t m_textFlags = 0;
     std::string m_pcDynaPrefix;
     bool calibrated_ = false;
 };

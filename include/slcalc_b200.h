@@ -205,6 +205,36 @@ int slc_dyna_track_host(slc_context *ctx, const uint8_t *h_frames, int32_t n_fra
                         const double *h_u0, float *h_xyzw, uint8_t *h_mask, float *h_delta_z,
                         const slc_dyna_parity *h_parity);
 
+/* ---- point-cloud output ("next" row: CCalculation::Result) ----------------- */
+#define SLC_ORDER_ROW_MAJOR 0   /* v outer, u inner: the memory order of the maps */
+#define SLC_ORDER_REFERENCE 1   /* u outer, v inner: the order Result() walks (CCalculation.cpp:336-338) */
+#define SLC_TEXT_CRLF (1u << 0) /* "\r\n" line ends: what the reference's text-mode fstream writes on its platform */
+#define SLC_TEXT_EXP3 (1u << 1) /* three exponent digits (the MSVC 2013 CRT of the reference build) instead of two */
+
+/* replaces: CCalculation::Result (CCalculation.cpp:323-357).  The text the reference writes for one
+ * frame -- "x y z\n" per pixel with FOV_MIN <= z <= FOV_MAX, u outer / v inner, each number as
+ * `ostream << double` prints it (printf "%g", precision 6) -- produced on the device: x, y, z are
+ * recomputed in f64 from the f64 ProjectorU plane in the reference's operation order
+ * (:686-687, :761-767), formatted with exact round-half-even decimal conversion, and compacted
+ * into one contiguous buffer.  text must be 16-byte aligned; *bytes receives the size of the
+ * whole text even when it exceeds capacity (then nothing past capacity is written and the call
+ * returns SLC_ERR_INVALID_ARG); *points the number of lines.  Worst case 43 bytes per pixel.
+ * The _device call synchronises the stream to return the two totals. */
+int slc_pointcloud_text_device(slc_context *ctx, const double *d_proj_u, uint32_t flags, char *d_text,
+                               int64_t capacity, int64_t *bytes, int64_t *points, void *cuda_stream);
+int slc_pointcloud_text_host(slc_context *ctx, const double *h_proj_u, uint32_t flags, char *h_text,
+                             int64_t capacity, int64_t *bytes, int64_t *points);
+/* Binary cloud: float[points][3] = (x, y, z) of the pixels with mask != 0 of one (xyzw, mask) map,
+ * in SLC_ORDER_ROW_MAJOR or SLC_ORDER_REFERENCE order.  capacity_points bounds d_xyz. */
+int slc_pointcloud_compact_device(slc_context *ctx, const float *d_xyzw, const uint8_t *d_mask, int32_t order,
+                                  float *d_xyz, int64_t capacity_points, int64_t *points, void *cuda_stream);
+int slc_pointcloud_compact_host(slc_context *ctx, const float *h_xyzw, const uint8_t *h_mask, int32_t order,
+                                float *h_xyz, int64_t capacity_points, int64_t *points);
+/* Parity hook for the number formatting alone: n doubles -> n slots of 16 chars (zero padded) and
+ * their lengths, exactly as the text kernel formats them. */
+int slc_format_g6_host(slc_context *ctx, const double *h_values, int64_t n, uint32_t flags, char *h_text16,
+                       uint8_t *h_len);
+
 /* Parity hook for the arctangent of CDecodePhase.cpp:67-75 alone: evaluates
  * cvFastArctan(sin, cos) in degrees and the in-period offset on the device, with
  * exactly the arithmetic of the fused kernel, for n caller-supplied pairs. */

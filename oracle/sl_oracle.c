@@ -22,6 +22,7 @@
 
 #include <float.h>
 #include <math.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 #include <time.h>
@@ -130,6 +131,53 @@ static int cfg_ok(const slo_config *cfg)
     if (cfg->phase_steps < 3) return 0;
     if (slo_gray_period(cfg) < 1) return 0; /* else :570 divides by zero */
     return 1;
+}
+
+/* ---- point-cloud text: CCalculation::Result (CCalculation.cpp:323-357) ------------------ */
+/* `file << double` with default stream flags is printf("%g") with precision 6 (C++ [ostream.inserters.arithmetic]
+ * -> num_put -> printf conversion %g).  glibc's printf converts exactly (round-half-even on the
+ * binary value).  The MSVC 2013 CRT the reference was built with prints three exponent digits. */
+int slo_format_g6(double v, unsigned flags, char *out)
+{
+    char buf[40];
+    int n = snprintf(buf, sizeof buf, "%g", v);
+    if (flags & 2u) {
+        char *e = strchr(buf, 'e');
+        if (e && strlen(e + 2) == 2) {          /* e+XX -> e+0XX */
+            memmove(e + 3, e + 2, 3);
+            e[2] = '0';
+            n++;
+        }
+    }
+    memcpy(out, buf, (size_t)n);
+    return n;
+}
+
+long long slo_result_text(const slo_config *cfg, const double *x, const double *y, const double *z,
+                          unsigned flags, char *out, long long cap, long long *n_points)
+{
+    const int W = cfg->width, H = cfg->height;
+    long long n = 0, pts = 0;
+    for (int u = 0; u < W; u++) {                     /* :336 */
+        for (int v = 0; v < H; v++) {                 /* :338 */
+            const size_t i = (size_t)v * W + u;
+            const double valZ = z[i];
+            if ((valZ < cfg->fov_min) || (valZ > cfg->fov_max)) continue;   /* :341-345 */
+            char line[64];
+            int l = slo_format_g6(x[i], flags, line);                       /* :348-350 */
+            line[l++] = ' ';
+            l += slo_format_g6(y[i], flags, line + l);
+            line[l++] = ' ';
+            l += slo_format_g6(z[i], flags, line + l);
+            if (flags & 1u) line[l++] = '\r';
+            line[l++] = '\n';
+            if (n + l <= cap) memcpy(out + n, line, (size_t)l);
+            n += l;
+            pts++;
+        }
+    }
+    if (n_points) *n_points = pts;
+    return n;
 }
 
 int slo_max_threads(void)

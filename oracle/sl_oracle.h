@@ -115,6 +115,17 @@ void slo_dyna_frame(const slo_config *cfg, const slo_calib *cal, const double *U
                     const double *z0, double *U1, double *x, double *y, double *z, double *deltaZ,
                     uint8_t *mask);
 
+/* Point-cloud text: CCalculation::Result (CCalculation.cpp:323-357) --
+ * u outer / v inner, pixels with z outside [fov_min, fov_max] skipped, "x y z" + line end with
+ * each number as `ostream << double` prints it, i.e. printf("%g") (precision 6).  flags bit 0:
+ * "\r\n" line ends (text-mode fstream on the reference's platform); bit 1: three exponent
+ * digits (MSVC 2013 CRT).  Writes at most cap bytes; returns the size of the whole text;
+ * *n_points = number of lines. */
+long long slo_result_text(const slo_config *cfg, const double *x, const double *y, const double *z,
+                          unsigned flags, char *out, long long cap, long long *n_points);
+/* One number as above into out (>= 16 chars); returns its length. */
+int slo_format_g6(double v, unsigned flags, char *out);
+
 int slo_max_threads(void);
 
 #ifdef __cplusplus

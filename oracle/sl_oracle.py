@@ -94,6 +94,11 @@ def lib():
         L.slo_delta_p.argtypes = [C.POINTER(SloConfig)] + [C.c_void_p] * 5
         L.slo_dyna_frame.argtypes = [C.POINTER(SloConfig), C.POINTER(SloCalib)] + [C.c_void_p] * 9
         L.slo_max_threads.restype = C.c_int
+        L.slo_result_text.argtypes = [C.POINTER(SloConfig), C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint, C.c_void_p,
+                                      C.c_longlong, C.POINTER(C.c_longlong)]
+        L.slo_result_text.restype = C.c_longlong
+        L.slo_format_g6.argtypes = [C.c_double, C.c_uint, C.c_char_p]
+        L.slo_format_g6.restype = C.c_int
         _lib = L
     return _lib
 
@@ -275,3 +280,25 @@ def dyna_sequence(cfg: SloConfig, cal: SloCalib, U0: np.ndarray, z0: np.ndarray,
         out.append(r)
         U, z, B0, W0 = r["proj_u"], r["z"], B1, W1
     return out
+
+
+TEXT_CRLF, TEXT_EXP3 = 1, 2
+
+
+def result_text(cfg: SloConfig, x: np.ndarray, y: np.ndarray, z: np.ndarray, flags: int = 0):
+    """CCalculation::Result (CCalculation.cpp:323-357) on f64 x, y, z planes -> (bytes, n_points)."""
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    y = np.ascontiguousarray(y, dtype=np.float64)
+    z = np.ascontiguousarray(z, dtype=np.float64)
+    cap = 44 * x.size + 16
+    buf = np.empty(cap, dtype=np.uint8)
+    pts = C.c_longlong(0)
+    n = lib().slo_result_text(C.byref(cfg), x.ctypes.data, y.ctypes.data, z.ctypes.data, flags, buf.ctypes.data, cap,
+                              C.byref(pts))
+    return buf[:n].tobytes(), int(pts.value)
+
+
+def format_g6(v: float, flags: int = 0) -> bytes:
+    out = C.create_string_buffer(40)
+    n = lib().slo_format_g6(float(v), flags, out)
+    return out.raw[:n]

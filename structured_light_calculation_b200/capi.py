@@ -28,6 +28,11 @@ SLC_ERR_STATE = 6
 SLC_FLAG_Z_FP64 = 1 << 0
 SLC_FLAG_SCALAR_KERNEL = 1 << 1
 
+SLC_ORDER_ROW_MAJOR = 0
+SLC_ORDER_REFERENCE = 1
+SLC_TEXT_CRLF = 1 << 0
+SLC_TEXT_EXP3 = 1 << 1
+
 
 class SlcError(RuntimeError):
     def __init__(self, status: int, message: str):
@@ -118,6 +123,12 @@ def load_library():
     L.slc_dyna_track_device.argtypes = [vp, vp, i32, i32, vp, vp, vp, vp, C.POINTER(SlcDynaParity), vp]
     L.slc_dyna_track_host.argtypes = [vp, vp, i32, i32, vp, vp, vp, vp, C.POINTER(SlcDynaParity)]
     L.slc_eval_phase_host.argtypes = [vp, vp, vp, C.c_int64, vp, vp]
+    i64p = C.POINTER(C.c_int64)
+    L.slc_pointcloud_text_device.argtypes = [vp, vp, C.c_uint32, vp, C.c_int64, i64p, i64p, vp]
+    L.slc_pointcloud_text_host.argtypes = [vp, vp, C.c_uint32, vp, C.c_int64, i64p, i64p]
+    L.slc_pointcloud_compact_device.argtypes = [vp, vp, vp, i32, vp, C.c_int64, i64p, vp]
+    L.slc_pointcloud_compact_host.argtypes = [vp, vp, vp, i32, vp, C.c_int64, i64p]
+    L.slc_format_g6_host.argtypes = [vp, vp, C.c_int64, C.c_uint32, vp, vp]
     L.slc_time_reconstruct_device.argtypes = [vp, vp, i32, vp, vp, i32, C.POINTER(C.c_float)]
     L.slc_launch_count.argtypes = [vp]
     L.slc_launch_count.restype = C.c_int64
@@ -333,6 +344,53 @@ class Reconstructor:
                           d_delta_z: int | None = None, window: int = 21, stream: int | None = None):
         self._check(self.lib.slc_dyna_track_device(self.h, d_frames, n_frames, window, d_u0, d_xyzw, d_mask,
                                                    d_delta_z, None, stream))
+
+    # -- point-cloud output ----------------------------------------------------
+    def pointcloud_text(self, proj_u: np.ndarray, flags: int = 0, capacity: int | None = None):
+        """CCalculation::Result's text for one f64 ProjectorU plane -> (bytes, n_points)."""
+        cfg = self.cfg
+        proj_u = np.ascontiguousarray(proj_u, dtype=np.float64)
+        assert proj_u.shape == (cfg.height, cfg.width)
+        cap = 43 * proj_u.size + 16 if capacity is None else capacity
+        buf = np.empty(max(cap, 1), np.uint8)
+        nb, npts = C.c_int64(0), C.c_int64(0)
+        self._check(self.lib.slc_pointcloud_text_host(self.h, proj_u.ctypes.data, flags, buf.ctypes.data, cap,
+                                                      C.byref(nb), C.byref(npts)))
+        return buf[: nb.value].tobytes(), int(npts.value)
+
+    def pointcloud_text_device(self, d_proj_u: int, d_text: int, capacity: int, flags: int = 0,
+                               stream: int | None = None):
+        nb, npts = C.c_int64(0), C.c_int64(0)
+        self._check(self.lib.slc_pointcloud_text_device(self.h, d_proj_u, flags, d_text, capacity, C.byref(nb),
+                                                        C.byref(npts), stream))
+        return int(nb.value), int(npts.value)
+
+    def pointcloud_compact(self, xyzw: np.ndarray, mask: np.ndarray, order: int = SLC_ORDER_ROW_MAJOR) -> np.ndarray:
+        """float32 [n_points][3] of the valid pixels of one (xyzw, mask) map."""
+        cfg = self.cfg
+        xyzw = np.ascontiguousarray(xyzw, dtype=np.float32)
+        mask = np.ascontiguousarray(mask, dtype=np.uint8)
+        assert xyzw.shape == (cfg.height, cfg.width, 4) and mask.shape == (cfg.height, cfg.width)
+        out = np.empty((mask.size, 3), np.float32)
+        n = C.c_int64(0)
+        self._check(self.lib.slc_pointcloud_compact_host(self.h, xyzw.ctypes.data, mask.ctypes.data, order,
+                                                         out.ctypes.data, mask.size, C.byref(n)))
+        return out[: n.value].copy()
+
+    def pointcloud_compact_device(self, d_xyzw: int, d_mask: int, d_xyz: int, capacity_points: int,
+                                  order: int = SLC_ORDER_ROW_MAJOR, stream: int | None = None) -> int:
+        n = C.c_int64(0)
+        self._check(self.lib.slc_pointcloud_compact_device(self.h, d_xyzw, d_mask, order, d_xyz, capacity_points,
+                                                           C.byref(n), stream))
+        return int(n.value)
+
+    def format_g6(self, values: np.ndarray, flags: int = 0) -> list[bytes]:
+        """Device number formatting (printf "%g") of each value."""
+        v = np.ascontiguousarray(values, dtype=np.float64).reshape(-1)
+        text = np.zeros((v.size, 16), np.uint8)
+        ln = np.zeros(v.size, np.uint8)
+        self._check(self.lib.slc_format_g6_host(self.h, v.ctypes.data, v.size, flags, text.ctypes.data, ln.ctypes.data))
+        return [text[i, : ln[i]].tobytes() for i in range(v.size)]
 
     def eval_phase(self, s: np.ndarray, c: np.ndarray):
         """Device cvFastArctan + in-period offset for arbitrary (sin, cos) sums."""

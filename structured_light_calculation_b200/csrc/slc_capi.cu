@@ -52,6 +52,9 @@ struct slc_context {
     void* d_scratch_aux = nullptr; size_t scratch_aux_bytes = 0;
     void* d_strips = nullptr;      size_t strips_bytes = 0;      // dynamic frames: (stripB, stripW) per frame
     void* d_dsums = nullptr;       size_t dsums_bytes = 0;       // dynamic frames: 3x3 sums of the nearer delta
+    void* d_pc_scratch = nullptr;  size_t pc_scratch_bytes = 0;  // point cloud: block sums
+    void* d_pc_in = nullptr;       size_t pc_in_bytes = 0;       // point cloud: staging for the host entry points
+    void* d_pc_out = nullptr;      size_t pc_out_bytes = 0;
     void* d_dyna = nullptr;        size_t dyna_bytes = 0;        // dynamic frames: staging for the host entry point
     long long launches = 0;
     std::string err;
@@ -315,6 +318,7 @@ void slc_destroy(slc_context* ctx)
     cudaFree(ctx->d_lut);
     cudaFree(ctx->d_scratch_in); cudaFree(ctx->d_scratch_out); cudaFree(ctx->d_scratch_aux);
     cudaFree(ctx->d_strips); cudaFree(ctx->d_dsums); cudaFree(ctx->d_dyna);
+    cudaFree(ctx->d_pc_scratch); cudaFree(ctx->d_pc_in); cudaFree(ctx->d_pc_out);
     delete ctx;
 }
 
@@ -719,6 +723,128 @@ int slc_dyna_track_host(slc_context* ctx, const uint8_t* h_frames, int32_t n_fra
     if (h_parity && h_parity->strips)
         SLC_CUDA(ctx, cudaMemcpyAsync(h_parity->strips, dpar.strips, nf * npx * 2, cudaMemcpyDeviceToHost, st));
     SLC_CUDA(ctx, cudaStreamSynchronize(st));
+    return SLC_OK;
+}
+
+/* ---- point-cloud output ------------------------------------------------ */
+namespace {
+
+int pointcloud_run(slc_context* ctx, int mode, int order, uint32_t flags, const double* d_proj_u, const float* d_xyzw,
+                   const uint8_t* d_mask, void* d_out, int64_t capacity_bytes, int64_t* bytes, int64_t* records,
+                   cudaStream_t st)
+{
+    if (!ctx->calibrated) return fail(ctx, SLC_ERR_NOT_INITIALISED, "calibration not set (CCalculation.cpp:176-181)");
+    if (capacity_bytes < 0 || !d_out) return fail(ctx, SLC_ERR_INVALID_ARG, "NULL output or negative capacity");
+    if (order != SLC_ORDER_ROW_MAJOR && order != SLC_ORDER_REFERENCE)
+        return fail(ctx, SLC_ERR_INVALID_ARG, "order %d is neither SLC_ORDER_ROW_MAJOR nor SLC_ORDER_REFERENCE", order);
+    if (reinterpret_cast<uintptr_t>(d_out) & 15) return fail(ctx, SLC_ERR_INVALID_ARG, "output buffer must be 16-byte aligned");
+    int rc = ensure_scratch(ctx, &ctx->d_pc_scratch, &ctx->pc_scratch_bytes, slc::pointcloud_scratch_bytes(ctx->kp.npx));
+    if (rc != SLC_OK) return rc;
+    const unsigned long long* d_totals = nullptr;
+    SLC_CUDA(ctx, slc::launch_pointcloud(ctx->kp, mode, order, flags, d_proj_u, d_xyzw, d_mask, d_out,
+                                         (unsigned long long)capacity_bytes, ctx->d_pc_scratch, &d_totals, st));
+    ctx->launches += 3;
+    unsigned long long totals[2] = {0, 0};
+    SLC_CUDA(ctx, cudaMemcpyAsync(totals, d_totals, sizeof(totals), cudaMemcpyDeviceToHost, st));
+    SLC_CUDA(ctx, cudaStreamSynchronize(st));
+    if (bytes) *bytes = (int64_t)totals[0];
+    if (records) *records = (int64_t)totals[1];
+    if ((int64_t)totals[0] > capacity_bytes)
+        return fail(ctx, SLC_ERR_INVALID_ARG, "point cloud needs %lld bytes, buffer holds %lld", (long long)totals[0],
+                    (long long)capacity_bytes);
+    return SLC_OK;
+}
+
+}  // namespace
+
+int slc_pointcloud_text_device(slc_context* ctx, const double* d_proj_u, uint32_t flags, char* d_text,
+                               int64_t capacity, int64_t* bytes, int64_t* points, void* cuda_stream)
+{
+    if (!ctx) return SLC_ERR_INVALID_ARG;
+    if (!d_proj_u) return fail(ctx, SLC_ERR_INVALID_ARG, "NULL ProjectorU plane");
+    SLC_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+    cudaStream_t st = cuda_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : ctx->stream;
+    return pointcloud_run(ctx, 0, SLC_ORDER_REFERENCE, flags, d_proj_u, nullptr, nullptr, d_text, capacity, bytes,
+                          points, st);
+}
+
+int slc_pointcloud_text_host(slc_context* ctx, const double* h_proj_u, uint32_t flags, char* h_text,
+                             int64_t capacity, int64_t* bytes, int64_t* points)
+{
+    if (!ctx) return SLC_ERR_INVALID_ARG;
+    if (!h_proj_u || !h_text || capacity < 0) return fail(ctx, SLC_ERR_INVALID_ARG, "NULL buffer or negative capacity");
+    SLC_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+    const size_t npx = (size_t)ctx->kp.npx;
+    const size_t worst = npx * 43 + 16;
+    const size_t cap = (size_t)capacity < worst ? (size_t)capacity : worst;
+    int rc = ensure_scratch(ctx, &ctx->d_pc_in, &ctx->pc_in_bytes, npx * sizeof(double));
+    if (rc == SLC_OK) rc = ensure_scratch(ctx, &ctx->d_pc_out, &ctx->pc_out_bytes, cap + 16);
+    if (rc != SLC_OK) return rc;
+    SLC_CUDA(ctx, cudaMemcpyAsync(ctx->d_pc_in, h_proj_u, npx * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    int64_t nb = 0;
+    rc = pointcloud_run(ctx, 0, SLC_ORDER_REFERENCE, flags, static_cast<const double*>(ctx->d_pc_in), nullptr, nullptr,
+                        ctx->d_pc_out, (int64_t)cap, &nb, points, ctx->stream);
+    if (bytes) *bytes = nb;
+    if (rc != SLC_OK) return rc;
+    SLC_CUDA(ctx, cudaMemcpyAsync(h_text, ctx->d_pc_out, (size_t)nb, cudaMemcpyDeviceToHost, ctx->stream));
+    SLC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SLC_OK;
+}
+
+int slc_pointcloud_compact_device(slc_context* ctx, const float* d_xyzw, const uint8_t* d_mask, int32_t order,
+                                  float* d_xyz, int64_t capacity_points, int64_t* points, void* cuda_stream)
+{
+    if (!ctx) return SLC_ERR_INVALID_ARG;
+    if (!d_xyzw || !d_mask) return fail(ctx, SLC_ERR_INVALID_ARG, "NULL map");
+    SLC_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+    cudaStream_t st = cuda_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : ctx->stream;
+    return pointcloud_run(ctx, 1, order, 0u, nullptr, d_xyzw, d_mask, d_xyz, capacity_points * 12, nullptr, points, st);
+}
+
+int slc_pointcloud_compact_host(slc_context* ctx, const float* h_xyzw, const uint8_t* h_mask, int32_t order,
+                                float* h_xyz, int64_t capacity_points, int64_t* points)
+{
+    if (!ctx) return SLC_ERR_INVALID_ARG;
+    if (!h_xyzw || !h_mask || !h_xyz || capacity_points < 0)
+        return fail(ctx, SLC_ERR_INVALID_ARG, "NULL buffer or negative capacity");
+    SLC_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+    const size_t npx = (size_t)ctx->kp.npx;
+    const size_t cap_pts = (size_t)capacity_points < npx ? (size_t)capacity_points : npx;
+    int rc = ensure_scratch(ctx, &ctx->d_pc_in, &ctx->pc_in_bytes, npx * 17);
+    if (rc == SLC_OK) rc = ensure_scratch(ctx, &ctx->d_pc_out, &ctx->pc_out_bytes, cap_pts * 12 + 16);
+    if (rc != SLC_OK) return rc;
+    float* d_xyzw = static_cast<float*>(ctx->d_pc_in);
+    uint8_t* d_mask = static_cast<uint8_t*>(ctx->d_pc_in) + npx * 16;
+    SLC_CUDA(ctx, cudaMemcpyAsync(d_xyzw, h_xyzw, npx * 16, cudaMemcpyHostToDevice, ctx->stream));
+    SLC_CUDA(ctx, cudaMemcpyAsync(d_mask, h_mask, npx, cudaMemcpyHostToDevice, ctx->stream));
+    int64_t n = 0;
+    rc = pointcloud_run(ctx, 1, order, 0u, nullptr, d_xyzw, d_mask, ctx->d_pc_out, (int64_t)(cap_pts * 12), nullptr, &n,
+                        ctx->stream);
+    if (points) *points = n;
+    if (rc != SLC_OK) return rc;
+    SLC_CUDA(ctx, cudaMemcpyAsync(h_xyz, ctx->d_pc_out, (size_t)n * 12, cudaMemcpyDeviceToHost, ctx->stream));
+    SLC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SLC_OK;
+}
+
+int slc_format_g6_host(slc_context* ctx, const double* h_values, int64_t n, uint32_t flags, char* h_text16,
+                       uint8_t* h_len)
+{
+    if (!ctx) return SLC_ERR_INVALID_ARG;
+    if (!h_values || !h_text16 || !h_len || n < 0) return fail(ctx, SLC_ERR_INVALID_ARG, "NULL buffer or n < 0");
+    if (n == 0) return SLC_OK;
+    SLC_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+    int rc = ensure_scratch(ctx, &ctx->d_pc_in, &ctx->pc_in_bytes, (size_t)n * 8);
+    if (rc == SLC_OK) rc = ensure_scratch(ctx, &ctx->d_pc_out, &ctx->pc_out_bytes, (size_t)n * 17);
+    if (rc != SLC_OK) return rc;
+    char* d_text = static_cast<char*>(ctx->d_pc_out);
+    uint8_t* d_len = static_cast<uint8_t*>(ctx->d_pc_out) + (size_t)n * 16;
+    SLC_CUDA(ctx, cudaMemcpyAsync(ctx->d_pc_in, h_values, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    SLC_CUDA(ctx, slc::launch_format_g6(static_cast<const double*>(ctx->d_pc_in), n, flags, d_text, d_len, ctx->stream));
+    ctx->launches++;
+    SLC_CUDA(ctx, cudaMemcpyAsync(h_text16, d_text, (size_t)n * 16, cudaMemcpyDeviceToHost, ctx->stream));
+    SLC_CUDA(ctx, cudaMemcpyAsync(h_len, d_len, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    SLC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return SLC_OK;
 }
 

@@ -38,6 +38,14 @@ cudaError_t launch_dyna_track(KParams p, const unsigned short* d_sums, int n_fra
                               float* d_xyzw, uint8_t* d_mask, float* d_delta_z, float* d_delta_p,
                               double* d_proj_u, double* d_u_final, cudaStream_t stream);
 
+// point-cloud output (slc_pointcloud.cu)
+size_t pointcloud_scratch_bytes(long long npx);
+cudaError_t launch_pointcloud(const KParams& p, int mode, int order, unsigned flags, const double* d_proj_u,
+                              const float* d_xyzw, const uint8_t* d_mask, void* d_out, unsigned long long capacity,
+                              void* d_scratch, const unsigned long long** d_totals, cudaStream_t stream);
+cudaError_t launch_format_g6(const double* d_values, long long n, unsigned flags, char* d_text, uint8_t* d_len,
+                             cudaStream_t stream);
+
 // tuning hook (bench / tests): pixels per thread of the vector kernel, 4 / 8 / 16
 void set_default_pixels_per_thread(int pxt);
 

@@ -1,0 +1,339 @@
+// slc_pointcloud.cu -- point-cloud output: CCalculation::Result
+// (CCalculation.cpp:323-357) on the device.
+//
+// The reference walks the image u outer / v inner, skips pixels whose z is outside
+// [FOV_MIN_DISTANCE, FOV_MAX_DISTANCE] and writes "x y z\n" with ostream << double, i.e.
+// printf("%g") with precision 6.  Here that is a variable-length record emission:
+//   pass 1  pc_emit_kernel<MODE, false>  length of every record, summed per block
+//   scan    pc_scan_kernel               exclusive scan of the block sums (one block)
+//   pass 2  pc_emit_kernel<MODE, true>   records again, block-local scan, staged in shared memory
+//                                        at the output's own 16-byte phase, written as uint4
+// MODE 0 records are text lines formatted from f64 x, y, z -- recomputed from the f64
+// ProjectorU plane in the reference's operation order (:686-687, :761-767), so the text is
+// byte-identical to what the reference's doubles print; MODE 1 records are packed float3 xyz
+// of the valid pixels of a float4 map (binary cloud / PLY body).
+#include "slc_kernels.h"
+
+namespace slc {
+
+namespace {
+
+constexpr int kPcThreads = 256;
+constexpr int kPcIters = 8;                      // records per thread
+constexpr int kPcChunk = kPcThreads * kPcIters;  // records per block
+constexpr int kPcMaxNum = 13;                    // "-1.23457e-005"
+constexpr int kPcMaxLine = 3 * kPcMaxNum + 2 + 2;   // two blanks, "\r\n"
+constexpr int kPcSlot = 44;                      // per-thread staging slot (11 words: conflict-free)
+
+__constant__ double c_pow10[23] = {1e0,  1e1,  1e2,  1e3,  1e4,  1e5,  1e6,  1e7,  1e8,  1e9,  1e10, 1e11,
+                                   1e12, 1e13, 1e14, 1e15, 1e16, 1e17, 1e18, 1e19, 1e20, 1e21, 1e22};
+
+// |x| * 10^k as a correctly rounded double p plus what is needed to compare the EXACT product
+// with a half-integer h:  sign(exact - h) = sign(cmp(p - h)).   10^|k| is exact for |k| <= 22.
+struct Scaled {
+    double p, m, aux;
+    int kind;          // 0: p = ax*m, aux = fma(ax, m, -p);  1: p = ax/m, aux = fma(-p, m, ax);  2: approximate
+};
+__device__ __forceinline__ Scaled scale10(double ax, int k)
+{
+    Scaled s;
+    if (k >= 0 && k <= 22) {
+        s.m = c_pow10[k];
+        s.p = __dmul_rn(ax, s.m);
+        s.aux = __fma_rn(ax, s.m, -s.p);
+        s.kind = 0;
+    } else if (k < 0 && k >= -22) {
+        s.m = c_pow10[-k];
+        s.p = __ddiv_rn(ax, s.m);
+        s.aux = __fma_rn(-s.p, s.m, ax);
+        s.kind = 1;
+    } else {            // |x| < 1e-17 or >= 1e28: not a coordinate; last digit not guaranteed
+        double v = ax;
+        int kk = k;
+        while (kk > 22) { v *= 1e22; kk -= 22; }
+        while (kk < -22) { v /= 1e22; kk += 22; }
+        s.m = 1.0;
+        s.p = (kk >= 0) ? v * c_pow10[kk] : v / c_pow10[-kk];
+        s.aux = 0.0;
+        s.kind = 2;
+    }
+    return s;
+}
+
+// printf("%g", x) (precision 6, the C locale) == what `ostream << double` writes with default
+// flags.  exp3: three exponent digits (the MSVC 2013 CRT the reference was built with) instead
+// of two.  Returns the number of characters written (<= 13).
+__device__ int format_g6(double x, char* out, bool exp3)
+{
+    int n = 0;
+    const unsigned long long bits = (unsigned long long)__double_as_longlong(x);
+    if (bits >> 63) out[n++] = '-';
+    const double ax = fabs(x);
+    if (ax == 0.0) { out[n++] = '0'; return n; }
+    const int bexp = (int)((bits >> 52) & 0x7FFu);
+    if (bexp == 0x7FF) {
+        const bool is_nan = (bits & 0xFFFFFFFFFFFFFull) != 0ull;
+        out[n++] = is_nan ? 'n' : 'i'; out[n++] = is_nan ? 'a' : 'n'; out[n++] = is_nan ? 'n' : 'f';
+        return n;
+    }
+    // decimal exponent: 10^E <= |x| < 10^(E+1); the estimate is within one, then one fix-up
+    int E = (int)floor((double)(bexp == 0 ? -1074 + (63 - __clzll((long long)(bits & 0xFFFFFFFFFFFFFull)))
+                                          : bexp - 1023) * 0.30102999566398120);
+    Scaled s = scale10(ax, 5 - E);
+    if (s.p < 1e5) { E--; s = scale10(ax, 5 - E); }
+    else if (s.p > 1e6) { E++; s = scale10(ax, 5 - E); }
+    // D = round-half-even of the exact |x| * 10^(5-E)
+    const double fl = floor(s.p);
+    const double diff = s.p - (fl + 0.5);                       // exact (Sterbenz)
+    const double t = (s.kind == 0) ? diff + s.aux : (s.kind == 1) ? __fma_rn(diff, s.m, s.aux) : diff;
+    unsigned D = (unsigned)fl;
+    if (t > 0.0 || (t == 0.0 && (D & 1u))) D++;
+    if (D >= 1000000u) { D = 100000u; E++; }
+    int nd = 6;                                                 // significant digits left after %g strips zeros
+    { unsigned q = D; while (nd > 1 && q % 10u == 0u) { q /= 10u; nd--; } }
+    auto next_digit = [&]() -> char { const unsigned d = D / 100000u; D = (D - d * 100000u) * 10u; return (char)('0' + d); };
+    if (E < -4 || E >= 6) {
+        out[n++] = next_digit();
+        if (nd > 1) {
+            out[n++] = '.';
+            for (int i = 1; i < nd; i++) out[n++] = next_digit();
+        }
+        out[n++] = 'e';
+        out[n++] = (E < 0) ? '-' : '+';
+        const unsigned ae = (unsigned)(E < 0 ? -E : E);
+        if (exp3 || ae >= 100u) out[n++] = (char)('0' + ae / 100u);
+        out[n++] = (char)('0' + (ae / 10u) % 10u);
+        out[n++] = (char)('0' + ae % 10u);
+    } else if (E >= 0) {
+        for (int i = 0; i <= E; i++) out[n++] = next_digit();   // digits past nd are zeros
+        if (nd > E + 1) {
+            out[n++] = '.';
+            for (int i = E + 1; i < nd; i++) out[n++] = next_digit();
+        }
+    } else {
+        out[n++] = '0';
+        out[n++] = '.';
+        for (int i = 0; i < -E - 1; i++) out[n++] = '0';
+        for (int i = 0; i < nd; i++) out[n++] = next_digit();
+    }
+    return n;
+}
+
+struct PcArgs {
+    int W, H;
+    long long npx;
+    int order;                       // 0 row-major, 1 reference (u outer, v inner: CCalculation.cpp:336-338)
+    const double* proj_u;            // MODE 0
+    const float4* xyzw;              // MODE 1
+    const uint8_t* mask;             // MODE 1
+    unsigned flags;
+    unsigned long long* block_sums;  // [2 * n_blocks + 2]: (bytes, records) per block; after the scan exclusive offsets, totals last
+    unsigned char* out;
+    unsigned long long capacity;     // bytes
+};
+
+// inclusive scan of `v` over the block; returns the exclusive prefix, *total = block sum
+__device__ __forceinline__ int block_exclusive_scan(int v, int* s_warp, int* total)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int o = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+        if (lane >= d) inc += o;
+    }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    int base = 0, tot = 0;
+#pragma unroll
+    for (int w = 0; w < kPcThreads / 32; w++) {
+        const int sw = s_warp[w];
+        if (w < warp) base += sw;
+        tot += sw;
+    }
+    __syncthreads();
+    *total = tot;
+    return base + inc - v;
+}
+
+template <int MODE, bool WRITE>
+__global__ void __launch_bounds__(kPcThreads)
+pc_emit_kernel(const __grid_constant__ KParams p, const PcArgs a)
+{
+    __shared__ __align__(16) unsigned char s_txt[kPcThreads * kPcMaxLine + 32];
+    __shared__ __align__(16) unsigned char s_slot[MODE == 0 ? kPcThreads * kPcSlot : 16];
+    __shared__ int s_warp[kPcThreads / 32];
+    const int t = threadIdx.x;
+    const long long base = (long long)blockIdx.x * kPcChunk;
+    unsigned long long gofs = WRITE ? a.block_sums[2 * blockIdx.x] : 0ull;
+    unsigned long long nbytes = 0ull, nrec = 0ull;
+    const bool crlf = (a.flags & 1u) != 0u, exp3 = (a.flags & 2u) != 0u;
+
+    for (int it = 0; it < kPcIters; it++) {
+        const long long i = base + (long long)it * kPcThreads + t;
+        int len = 0;
+        float3 rec = make_float3(0.f, 0.f, 0.f);
+        unsigned char* slot = &s_slot[MODE == 0 ? t * kPcSlot : 0];
+        if (i < a.npx) {
+            int u, v;
+            if (a.order == 1) { u = (int)(i / a.H); v = (int)(i - (long long)u * a.H); }
+            else { v = (int)(i / a.W); u = (int)(i - (long long)v * a.W); }
+            const long long px = (long long)v * a.W + u;
+            if (MODE == 0) {
+                const double U = a.proj_u[px];
+                if (U != 0.0) {                                            // :678-682
+                    const double z = z_exact(p, U, u, v);                  // :686-687
+                    if (!((z < p.fov_min) || (z > p.fov_max))) {           // :701-704 and :341-345
+                        const double x = __ddiv_rn(__dmul_rn(z, __dsub_rn((double)u, p.cu)), p.fu);   // :766
+                        const double y = __ddiv_rn(__dmul_rn(z, __dsub_rn((double)v, p.cv)), p.fv);   // :767
+                        char* o = reinterpret_cast<char*>(slot);
+                        len = format_g6(x, o, exp3);
+                        o[len++] = ' ';
+                        len += format_g6(y, o + len, exp3);
+                        o[len++] = ' ';
+                        len += format_g6(z, o + len, exp3);
+                        if (crlf) o[len++] = '\r';
+                        o[len++] = '\n';
+                    }
+                }
+            } else {
+                if (a.mask[px] != 0) {
+                    const float4 q = a.xyzw[px];
+                    rec = make_float3(q.x, q.y, q.z);
+                    len = 12;
+                }
+            }
+        }
+        int total;
+        const int excl = block_exclusive_scan(len, s_warp, &total);
+        nbytes += (unsigned long long)len;       // per thread; reduced below
+        nrec += (len > 0) ? 1ull : 0ull;
+        if (WRITE) {
+            const unsigned align = (unsigned)(gofs & 15ull);
+            if (gofs + (unsigned long long)total <= a.capacity) {
+                unsigned char* dst = &s_txt[align + excl];
+                if (MODE == 0) {
+                    for (int j = 0; j < len; j++) dst[j] = slot[j];
+                } else if (len) {
+                    // 12-byte records: align + excl is a multiple of 4 (gofs is a multiple of 12 from a 16-aligned base)
+                    float* d = reinterpret_cast<float*>(dst);
+                    d[0] = rec.x; d[1] = rec.y; d[2] = rec.z;
+                }
+                __syncthreads();
+                unsigned char* g = a.out + (gofs - align);         // 16-byte aligned
+                const int end = (int)align + total;
+                const int body0 = align ? 16 : 0, body1 = end & ~15;
+                for (int j = (int)align + t; j < min(16, end) && align; j += kPcThreads) g[j] = s_txt[j];
+                for (int j = body0 + 16 * t; j < body1; j += 16 * kPcThreads)
+                    *reinterpret_cast<uint4*>(g + j) = *reinterpret_cast<const uint4*>(&s_txt[j]);
+                for (int j = max(body1, body0) + t; j < end; j += kPcThreads) g[j] = s_txt[j];
+                __syncthreads();
+            }
+            gofs += (unsigned long long)total;
+        }
+    }
+    if (!WRITE) {
+        // block totals: reduce the per-thread counters
+        __shared__ unsigned long long s_red[2][kPcThreads / 32];
+        const int lane = t & 31, warp = t >> 5;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            nbytes += __shfl_down_sync(0xFFFFFFFFu, nbytes, d);
+            nrec += __shfl_down_sync(0xFFFFFFFFu, nrec, d);
+        }
+        if (lane == 0) { s_red[0][warp] = nbytes; s_red[1][warp] = nrec; }
+        __syncthreads();
+        if (t == 0) {
+            unsigned long long b = 0, r = 0;
+            for (int w = 0; w < kPcThreads / 32; w++) { b += s_red[0][w]; r += s_red[1][w]; }
+            a.block_sums[2 * blockIdx.x] = b;
+            a.block_sums[2 * blockIdx.x + 1] = r;
+        }
+    }
+}
+
+// exclusive scan of (bytes, records) pairs over the blocks; totals land at index n
+__global__ void __launch_bounds__(1024)
+pc_scan_kernel(unsigned long long* sums, int n)
+{
+    __shared__ unsigned long long s_b[1024], s_r[1024];
+    const int t = threadIdx.x;
+    const int per = (n + 1023) / 1024;
+    const int i0 = t * per, i1 = min(n, i0 + per);
+    unsigned long long b = 0, r = 0;
+    for (int i = i0; i < i1; i++) { b += sums[2 * i]; r += sums[2 * i + 1]; }
+    s_b[t] = b; s_r[t] = r;
+    __syncthreads();
+    if (t == 0) {
+        unsigned long long ab = 0, ar = 0;
+        for (int k = 0; k < 1024; k++) {
+            const unsigned long long vb = s_b[k], vr = s_r[k];
+            s_b[k] = ab; s_r[k] = ar;
+            ab += vb; ar += vr;
+        }
+        sums[2 * n] = ab;
+        sums[2 * n + 1] = ar;
+    }
+    __syncthreads();
+    b = s_b[t]; r = s_r[t];
+    for (int i = i0; i < i1; i++) {
+        const unsigned long long vb = sums[2 * i], vr = sums[2 * i + 1];
+        sums[2 * i] = b; sums[2 * i + 1] = r;
+        b += vb; r += vr;
+    }
+}
+
+__global__ void format_g6_kernel(const double* __restrict__ v, long long n, unsigned flags, char* __restrict__ text,
+                                 uint8_t* __restrict__ len)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    char buf[16];
+    const int l = format_g6(v[i], buf, (flags & 2u) != 0u);
+    for (int j = 0; j < 16; j++) text[i * 16 + j] = (j < l) ? buf[j] : 0;
+    len[i] = (uint8_t)l;
+}
+
+}  // namespace
+
+size_t pointcloud_scratch_bytes(long long npx)
+{
+    const long long blocks = (npx + kPcChunk - 1) / kPcChunk;
+    return (size_t)(2 * blocks + 2) * sizeof(unsigned long long);
+}
+
+// mode 0: text lines from d_proj_u; mode 1: float3 of the valid pixels of (d_xyzw, d_mask).
+// d_totals (inside d_scratch, 2 x u64: bytes, records) is valid once the stream has drained.
+cudaError_t launch_pointcloud(const KParams& p, int mode, int order, unsigned flags, const double* d_proj_u,
+                              const float* d_xyzw, const uint8_t* d_mask, void* d_out, unsigned long long capacity,
+                              void* d_scratch, const unsigned long long** d_totals, cudaStream_t stream)
+{
+    if ((reinterpret_cast<uintptr_t>(d_out) & 15) != 0) return cudaErrorMisalignedAddress;
+    const int blocks = (int)((p.npx + kPcChunk - 1) / kPcChunk);
+    PcArgs a{};
+    a.W = p.W; a.H = p.H; a.npx = p.npx; a.order = order;
+    a.proj_u = d_proj_u;
+    a.xyzw = reinterpret_cast<const float4*>(d_xyzw);
+    a.mask = d_mask;
+    a.flags = flags;
+    a.block_sums = static_cast<unsigned long long*>(d_scratch);
+    a.out = static_cast<unsigned char*>(d_out);
+    a.capacity = capacity;
+    if (mode == 0) pc_emit_kernel<0, false><<<blocks, kPcThreads, 0, stream>>>(p, a);
+    else pc_emit_kernel<1, false><<<blocks, kPcThreads, 0, stream>>>(p, a);
+    pc_scan_kernel<<<1, 1024, 0, stream>>>(a.block_sums, blocks);
+    if (mode == 0) pc_emit_kernel<0, true><<<blocks, kPcThreads, 0, stream>>>(p, a);
+    else pc_emit_kernel<1, true><<<blocks, kPcThreads, 0, stream>>>(p, a);
+    *d_totals = a.block_sums + 2 * blocks;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_format_g6(const double* d_values, long long n, unsigned flags, char* d_text, uint8_t* d_len,
+                             cudaStream_t stream)
+{
+    if (n <= 0) return cudaSuccess;
+    format_g6_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(d_values, n, flags, d_text, d_len);
+    return cudaGetLastError();
+}
+
+}  // namespace slc

@@ -474,8 +474,12 @@ bool CCalculation::CalculateOther()
     std::vector<float> xyzw(no * npx * 4), dz(no * npx);
     std::vector<uint8_t> mask(no * npx);
     // StripRegression + FillOtherDeltaProU + FillCoordinate for every frame: two launches
+    std::vector<double> pu(no * npx);               // m_ProjectorU[f]: Result(f) prints from the f64 plane
+    slc_dyna_parity par;
+    std::memset(&par, 0, sizeof(par));
+    par.proj_u = pu.data();
     const int rc = slc_dyna_track_host(ctx_, frames, n, sp_.RECO_WINDOW_SIZE, reinterpret_cast<const double*>(m_projU.ptr()),
-                                       xyzw.data(), mask.data(), dz.data(), nullptr);
+                                       xyzw.data(), mask.data(), dz.data(), &par);
     slc_host_free(frames);
     if (rc != SLC_OK) {
         ErrorHandling(std::string("CCalculation::CalculateOther()->") + slc_last_error(ctx_));
@@ -484,11 +488,13 @@ bool CCalculation::CalculateOther()
     m_dynXyzw.assign(no, Mat());
     m_dynMask.assign(no, Mat());
     m_dynDeltaZ.assign(no, Mat());
+    m_dynProjU.assign(no, Mat());
     for (size_t f = 0; f < no; f++) {
         std::cout << "Frame: " << (f + 1) << " begin." << std::endl;       // :228
         Mat(sp_.CAMERA_RESROW, sp_.CAMERA_RESLINE, CV_32FC4, xyzw.data() + f * npx * 4).copyTo(m_dynXyzw[f]);
         Mat(sp_.CAMERA_RESROW, sp_.CAMERA_RESLINE, CV_8UC1, mask.data() + f * npx).copyTo(m_dynMask[f]);
         Mat(sp_.CAMERA_RESROW, sp_.CAMERA_RESLINE, CV_32FC1, dz.data() + f * npx).copyTo(m_dynDeltaZ[f]);
+        Mat(sp_.CAMERA_RESROW, sp_.CAMERA_RESLINE, CV_64FC1, pu.data() + f * npx).copyTo(m_dynProjU[f]);
         if (!m_pcDynaPrefix.empty()) {                                      // :309-315
             std::ostringstream name;
             name << sp_.DATA_PATH << m_pcDynaPrefix << (f + 1) << ".txt";
@@ -500,28 +506,58 @@ bool CCalculation::CalculateOther()
 
 bool CCalculation::Result(std::string fileName, int i)
 {
-    // CCalculation.cpp:323-357: "x y z\n" per in-FOV pixel, u outer / v inner
+    // CCalculation.cpp:323-357: "x y z\n" per in-FOV pixel, u outer / v inner, `file << double`.
+    // The text is produced on the device from the f64 ProjectorU plane of frame i (x, y, z
+    // recomputed in f64 in the reference's operation order, formatted like printf "%g") and
+    // written with one fwrite.
     if (i < 0 || i >= FrameCount() || m_xyzw.empty()) return false;
-    const Mat& xyzw = PointMap(i);
-    const Mat& maskm = ValidMask(i);
-    std::fstream file;
-    file.open(fileName.c_str(), std::ios::out);
+    const Mat& U = (i == 0) ? m_projU : m_dynProjU.at((size_t)i - 1);
+    FILE* file = std::fopen(fileName.c_str(), "wb");
     if (!file) {
         ErrorHandling("CCalculation::Result() OpenFile Error:" + fileName);
         return false;
     }
-    for (int u = 0; u < sp_.CAMERA_RESLINE; u++) {
-        for (int v = 0; v < sp_.CAMERA_RESROW; v++) {
-            const float* p = &xyzw.at<float>(v, 4 * u);
-            // the reference filters on the f64 z (:341-345); the mask is that same f64 decision
-            if (maskm.at<uint8_t>(v, u) == 0) continue;
-            file << (double)p[0] << ' ';
-            file << (double)p[1] << ' ';
-            file << (double)p[2] << std::endl;
-        }
+    const size_t npx = (size_t)sp_.CAMERA_RESROW * sp_.CAMERA_RESLINE;
+    const int64_t cap = (int64_t)(npx * 43 + 16);
+    char* text = static_cast<char*>(slc_host_alloc((size_t)cap));
+    bool ok = (text != nullptr);
+    int64_t bytes = 0, points = 0;
+    if (ok && slc_pointcloud_text_host(ctx_, reinterpret_cast<const double*>(U.ptr()), m_textFlags, text, cap, &bytes,
+                                       &points) != SLC_OK) {
+        ErrorHandling(std::string("CCalculation::Result()->") + slc_last_error(ctx_));
+        ok = false;
     }
-    file.close();
-    return true;
+    if (ok && bytes > 0) ok = (std::fwrite(text, 1, (size_t)bytes, file) == (size_t)bytes);
+    if (text) slc_host_free(text);
+    std::fclose(file);
+    return ok;
+}
+
+bool CCalculation::ResultPly(std::string fileName, int i)
+{
+    // binary companion of Result(): the valid points of frame i, same u-outer / v-inner order,
+    // compacted on the device, as a little-endian PLY
+    if (i < 0 || i >= FrameCount() || m_xyzw.empty()) return false;
+    const Mat& xyzw = PointMap(i);
+    const Mat& maskm = ValidMask(i);
+    const size_t npx = (size_t)sp_.CAMERA_RESROW * sp_.CAMERA_RESLINE;
+    std::vector<float> xyz(npx * 3);
+    int64_t points = 0;
+    if (slc_pointcloud_compact_host(ctx_, reinterpret_cast<const float*>(xyzw.ptr()), maskm.ptr(), SLC_ORDER_REFERENCE,
+                                    xyz.data(), (int64_t)npx, &points) != SLC_OK) {
+        ErrorHandling(std::string("CCalculation::ResultPly()->") + slc_last_error(ctx_));
+        return false;
+    }
+    FILE* file = std::fopen(fileName.c_str(), "wb");
+    if (!file) {
+        ErrorHandling("CCalculation::ResultPly() OpenFile Error:" + fileName);
+        return false;
+    }
+    std::fprintf(file, "ply\nformat binary_little_endian 1.0\nelement vertex %lld\nproperty float x\nproperty float y\n"
+                       "property float z\nend_header\n", (long long)points);
+    const bool ok = std::fwrite(xyz.data(), 12, (size_t)points, file) == (size_t)points;
+    std::fclose(file);
+    return ok;
 }
 
 static Mat channel_as_f64(const Mat& xyzw, int ch)

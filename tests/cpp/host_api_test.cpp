@@ -130,6 +130,8 @@ int main(int argc, char** argv)
     Mat U = calc.GetProjectorU();
     CHECK(write_file(dir + "/projU.f64", U.ptr(), npx * 8));
     CHECK(calc.Result(dir + "/cloud.txt", 0));
+    CHECK(calc.ResultPly(dir + "/cloud.ply", 0));
+    CHECK(!calc.Result(dir + "/no/such/dir/cloud.txt", 0));   // open failure (CCalculation.cpp:327-331)
     Mat z = calc.GetZ();
     CHECK(z.type() == CV_64FC1 && z.at<double>(H / 2, W / 2) == (double)calc.PointMap().at<float>(H / 2, 4 * (W / 2) + 2));
     std::printf("host_api_test ok\n");

@@ -75,6 +75,15 @@ def test_cpp_host_api_matches_oracle(tmp_path, built_library, oracle, base_calib
     assert cloud.shape[0] == int(want["mask"].sum())
     ref = np.stack([want["x"][vv, uu], want["y"][vv, uu], want["z"][vv, uu]], axis=1)
     assert np.allclose(cloud, ref, rtol=2e-5, atol=1e-4)
+    # ... and byte for byte what the reference's `file << double` loop writes from its f64 planes
+    ocfg0 = oracle.make_config(W, H, PW, G, N)
+    text, npts = oracle.result_text(ocfg0, want["x"], want["y"], want["z"])
+    assert (d / "cloud.txt").read_bytes() == text and npts == cloud.shape[0]
+    ply = (d / "cloud.ply").read_bytes()
+    head, body = ply.split(b"end_header\n", 1)
+    assert f"element vertex {npts}".encode() in head
+    pts = np.frombuffer(body, np.float32).reshape(-1, 3)
+    assert pts.shape[0] == npts and np.array_equal(pts, xyzw[vv, uu, :3])
     # CalculateOther(): dynamic frames through the class API
     ocfg = oracle.make_config(W, H, PW, G, N)
     seq = oracle.dyna_sequence(ocfg, oracle.make_calib(cal.cam, cal.pro, cal.R, cal.T), want["proj_u"], want["z"], frames)
@@ -87,3 +96,5 @@ def test_cpp_host_api_matches_oracle(tmp_path, built_library, oracle, base_calib
         assert np.abs(dxyzw[f, ..., 2] - r["z"]).max() <= tol
         assert np.abs(ddz[f] - r["delta_z"]).max() <= 2 * tol
     assert np.loadtxt(d / "cloud_dyn1.txt").reshape(-1, 3).shape[0] == int(seq[0]["mask"].sum())
+    text1, _ = oracle.result_text(ocfg, seq[0]["x"], seq[0]["y"], seq[0]["z"])
+    assert (d / "cloud_dyn1.txt").read_bytes() == text1

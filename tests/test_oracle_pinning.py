@@ -208,3 +208,28 @@ def test_dynamic_frame_golden_bit_exact(oracle):
     # U accumulates exactly: every addend is a multiple of 2^-27 far inside a double
     total = g["U0"] + g["delta_p"].astype(np.float64).sum(axis=0)
     assert bits_equal(seq[-1]["proj_u"], total)
+
+
+def test_result_text_restatement_is_printf(oracle):
+    """CCalculation::Result (CCalculation.cpp:323-357): the oracle's loop against an independent
+    Python rendering (u outer / v inner, z filter, '%g' == ostream << double)."""
+    rng = np.random.default_rng(5)
+    W, H = 37, 23
+    x = rng.uniform(-30, 30, (H, W))
+    y = rng.uniform(-30, 30, (H, W))
+    z = rng.uniform(0, 120, (H, W))
+    z[rng.random((H, W)) < 0.2] = 0.0
+    x[3, 4] = 1.25e-7
+    y[3, 4] = -123456.5
+    z[3, 4] = 10.0
+    cfg = oracle.make_config(W, H, 1280, 6, 4)
+    text, n = oracle.result_text(cfg, x, y, z)
+    lines = []
+    for u in range(W):
+        for v in range(H):
+            if z[v, u] < 10 or z[v, u] > 100:
+                continue
+            lines.append("%g %g %g\n" % (x[v, u], y[v, u], z[v, u]))
+    assert text == "".join(lines).encode() and n == len(lines)
+    crlf3, _ = oracle.result_text(cfg, x, y, z, oracle.TEXT_CRLF | oracle.TEXT_EXP3)
+    assert crlf3 == "".join(lines).replace("e-07", "e-007").replace("\n", "\r\n").encode()
