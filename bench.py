@@ -313,6 +313,105 @@ def run_dynamic(args):
     return 0
 
 
+def run_pointcloud(args):
+    """--path pointcloud: CCalculation::Result (SURVEY 8f rank 2) -- the text cloud of one
+    1920x1200 frame (BASELINE configs[1] geometry) formatted on the device from the f64
+    ProjectorU plane.  A step is `--pc-frames` frames, three kernel launches each."""
+    import torch
+    from structured_light_calculation_b200 import capi
+    from oracle import sl_oracle as O   # CPU baseline + byte check only
+
+    rank, local_rank, world = D.env_rank_world()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        D.init_process_group("nccl")
+    cfg = CONFIGS[args.config]
+    cal, scene, stacks = build_inputs(cfg, 1)
+    rec = capi.Reconstructor(cfg, device=local_rank, max_batch=1, num_slots=1)
+    rec.set_calibration(cal)
+    first = rec.reconstruct(stacks[0], parity=True)
+    u_host = first["proj_u"][0]
+    npx = cfg.pixels
+    F = args.pc_frames
+    d_u = torch.from_numpy(u_host).to(dev)
+    cap = 43 * npx + 16
+    d_text = torch.empty((cap,), dtype=torch.uint8, device=dev)
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    nbytes = npts = 0
+
+    def step():
+        nonlocal nbytes, npts
+        for _ in range(F):
+            nbytes, npts = rec.pointcloud_text_device(d_u.data_ptr(), d_text.data_ptr(), cap, 0, stream.cuda_stream)
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    launches0 = rec.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    D.barrier()
+    torch.cuda.synchronize()
+    e0.record(stream)
+    for _ in range(args.steps):
+        step()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    D.barrier()
+    ms = D.max_over_ranks(e0.elapsed_time(e1), dev)
+    launches = int(D.sum_over_ranks(rec.launch_count() - launches0, dev))
+    value = world * F * args.steps / (ms * 1e-3)
+
+    # end to end: host f64 plane in, host text out
+    e2e_reps = 10
+    h_u = capi.PinnedArray((cfg.height, cfg.width), np.float64)
+    h_u.array[...] = u_host
+    h_text = capi.PinnedArray((cap,), np.uint8)
+    rec.pointcloud_text_into(h_u, h_text)
+    t0 = time.perf_counter()
+    for _ in range(e2e_reps):
+        nb, _n = rec.pointcloud_text_into(h_u, h_text)
+    e2e_s = D.max_over_ranks(time.perf_counter() - t0, dev)
+    e2e_value = world * e2e_reps / e2e_s
+    text = h_text.array[:nb].tobytes()
+
+    if rank == 0:
+        ocfg = O.make_config(cfg.width, cfg.height, cfg.projector_width, cfg.gray_digits, cfg.phase_steps,
+                             cfg.fov_min, cfg.fov_max, cfg.modulation_min)
+        want = O.reconstruct(ocfg, O.make_calib(cal.cam, cal.pro, cal.R, cal.T), stacks[0])
+        t0 = time.perf_counter()
+        wtext, wn = O.result_text(ocfg, want["x"], want["y"], want["z"])
+        cpu_s = time.perf_counter() - t0
+        peak, peak_kind = hbm_peak()
+        alg = (8 * npx + nbytes) * F            # f64 ProjectorU read once + the text written once
+        achieved = alg / (ms * 1e-3 / args.steps) / 1e9
+        line = {
+            "metric": "pointcloud_text_frames_per_sec", "value": value, "unit": "frames/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"Result() text cloud of a {cfg.width}x{cfg.height} frame ({npts} points, "
+                                   f"{nbytes} bytes), {F} frame(s) per step"},
+            "points_per_s": value * npts, "text_gb_per_s": value * nbytes / 1e9,
+            "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": 8 * npx, "d2h_bytes_per_step": nbytes,
+                    "api": "capi.Reconstructor.pointcloud_text_into -> slc_pointcloud_text_host, pinned host buffers"},
+            "gpu_launches": launches,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_kind": f"of {peak_kind}",
+                         "kernel": "pc_emit_kernel<0,false> + pc_scan_kernel + pc_emit_kernel<0,true> (per frame)",
+                         "algorithmic_bytes_per_step": alg,
+                         "note": "formatting is FP64/integer-issue bound, not HBM bound; every number is formatted twice"},
+            "cpu_baseline": {"value": 1.0 / cpu_s, "unit": "frames/s", "cores": 1, "kind": "port",
+                             "sample": "one frame, oracle Result() restatement (snprintf %g), 1 thread, no file I/O"},
+            "checked_against_oracle": bool(text == wtext and wn == npts),
+        }
+        print(json.dumps(line), flush=True)
+    rec.close()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -328,8 +427,10 @@ def main():
     ap.add_argument("--pxt", type=int, default=0, help="tuning: pixels per thread (4/8/16)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-numa-bind", action="store_true")
-    ap.add_argument("--path", default="first", choices=["first", "dynamic"],
-                    help="first = the headline first-frame path; dynamic = CalculateOther sequences")
+    ap.add_argument("--path", default="first", choices=["first", "dynamic", "pointcloud"],
+                    help="first = the headline first-frame path; dynamic = CalculateOther sequences; "
+                         "pointcloud = Result() text formatting")
+    ap.add_argument("--pc-frames", type=int, default=4)
     ap.add_argument("--dyna-frames", type=int, default=100)
     ap.add_argument("--dyna-e2e-frames", type=int, default=24)
     ap.add_argument("--ref-stacks-per-step", type=int, default=2)
@@ -341,6 +442,8 @@ def main():
         return run_reference(args, cfg)
     if args.path == "dynamic":
         return run_dynamic(args)
+    if args.path == "pointcloud":
+        return run_pointcloud(args)
 
     import torch
     from structured_light_calculation_b200 import capi

@@ -88,13 +88,18 @@ struct StaticParameters {
 int ErrorHandling(std::string message);
 const std::string& LastErrorMessage();
 
-// In-memory replacement of the file-backed sensor (CSensorV.h:15-61).
-// group 0 = vGray images, 1 = vPhase images, 2 = dyna images.
+// The sensor (CSensorV.h:15-61): group 0 = vGray images, 1 = vPhase images, 2 = dyna images.
+// Either fed from memory (StoreDatas) or file-backed like the reference: after AttachFiles,
+// LoadDatas(group) reads <groupDataPath>/iFrame/vGrayCam{i}.bmp, .../iFrame/vPhaseCam{i}.bmp or
+// .../cFrame/dynaCam{i}.bmp (CSensorV.cpp:35-41,74-121); the BMP pixel work (row flip, padding,
+// palette / BGR -> gray as imread(..., CV_LOAD_IMAGE_GRAYSCALE)) runs on the device.
 class CSensor {
 public:
     bool InitSensor();
     bool CloseSensor();
     bool StoreDatas(int groupNum, int idx, const Mat& picture);   // feeds what LoadDatas would read from disk
+    void AttachFiles(slc_context* ctx, const StaticParameters& sp, const std::string& groupDataPath);
+    std::string FileName(int groupNum, int idx) const;
     bool LoadDatas(int groupNum);
     bool UnloadDatas();
     bool SetProPicture(int nowNum);
@@ -104,6 +109,12 @@ private:
     std::vector<Mat> groups_[3];
     int group_ = -1;
     int now_ = 0;
+    // file-backed mode
+    slc_context* ctx_ = nullptr;
+    int counts_[3] = {0, 0, 0};
+    int rows_ = 0, cols_ = 0;
+    std::string m_groupDataPath, m_iFramePath = "iFrame/", m_cFramePath = "cFrame/";
+    std::string m_vGrayName = "vGrayCam", m_vPhaseName = "vPhaseCam", m_dynaName = "dynaCam", m_dataFileSuffix = ".bmp";
 };
 
 // CDecodeGray.h:18-53
@@ -172,6 +183,8 @@ public:
     void SetParameterFile(const std::string& ymlPath) { m_paraFile = ymlPath; }
     void SetGrayCodeFile(const std::string& path, const std::string& name) { m_codePath = path; m_codeName = name; }
     void SetPointCloudFile(const std::string& file) { m_pcFile = file; }
+    // file-backed sensor: the directory that holds iFrame/ and cFrame/ (CSensorV.cpp:35); empty = in-memory sensor
+    void SetGroupDataPath(const std::string& path) { m_groupDataPath = path; }
     CSensor* Sensor() { return m_sensor; }                  // valid after Init()
 
     bool Init();
@@ -206,6 +219,7 @@ private:
     std::string m_paraFile = "parameters.yml";
     std::string m_codePath = "Patterns/", m_codeName = "vGrayCode.txt";
     std::string m_pcFile = "iFrame.txt";
+    std::string m_groupDataPath;
     uint8_t* pinned_stack_ = nullptr;
     Mat m_xyzw, m_mask, m_projU;
     std::vector<Mat> m_dynXyzw, m_dynMask, m_dynDeltaZ, m_dynProjU;

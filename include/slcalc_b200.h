@@ -205,6 +205,37 @@ int slc_dyna_track_host(slc_context *ctx, const uint8_t *h_frames, int32_t n_fra
                         const double *h_u0, float *h_xyzw, uint8_t *h_mask, float *h_delta_z,
                         const slc_dyna_parity *h_parity);
 
+/* ---- input ingest ("next" row: CSensor::LoadDatas) ------------------------- */
+/* What the reference's imread(file, CV_LOAD_IMAGE_GRAYSCALE) (CSensorV.cpp:111-114) yields for a
+ * .bmp: uncompressed 8-bit paletted, 24-bit BGR or 32-bit BGRA, bottom-up or top-down. */
+typedef struct {
+    int32_t width, height;        /* pixels */
+    int32_t bits_per_pixel;       /* 8, 24 or 32 */
+    int32_t top_down;             /* 1: first stored row is the top row (biHeight < 0) */
+    int32_t row_stride;           /* bytes per stored row (padded to 4) */
+    int32_t palette_is_identity;  /* 8 bpp: gray[i] == i for every i */
+    int64_t pixel_offset;         /* bfOffBits: start of the pixel array inside the file */
+    uint8_t gray[256];            /* 8 bpp: palette index -> gray level, OpenCV's fixed-point BGR weights */
+} slc_bmp_info;
+
+/* Header + palette only (host, no context, no pixel work).  SLC_ERR_INVALID_ARG for anything that
+ * is not one of the flavours above (RLE, 1/4/16 bpp, truncated file). */
+int slc_bmp_parse(const void *file_bytes, int64_t n_bytes, slc_bmp_info *info);
+/* Pixel array (device pointer to file_bytes + pixel_offset) -> one [height][width] u8 plane on the
+ * device: row flip, padding removal, palette / BGR -> gray.  Asynchronous. */
+int slc_bmp_unpack_device(slc_context *ctx, const uint8_t *d_pixels, const slc_bmp_info *info,
+                          uint8_t *d_plane, void *cuda_stream);
+/* The whole file from host memory to a host plane (upload, unpack, download; synchronous): what
+ * the file-backed CSensor hands to SetMat. */
+int slc_bmp_decode_host(slc_context *ctx, const void *h_file_bytes, int64_t n_bytes, uint8_t *h_plane,
+                        int32_t expect_width, int32_t expect_height);
+/* replaces: CSensor::LoadDatas + the SetProPicture/GetCamPicture/SetMat loop of
+ * CCalculation::FillFirstProjectorU (CCalculation.cpp:536-557).  Reads n_files .bmp files (each must
+ * be width x height of the context) through pinned double-buffered staging and unpacks file i
+ * into plane i of d_stack (u8 [n_files][H][W], e.g. a whole 2G+N stack or a dynaCam sequence).
+ * Synchronous; on failure the message names the file. */
+int slc_load_bmp_planes(slc_context *ctx, const char *const *paths, int32_t n_files, uint8_t *d_stack);
+
 /* ---- point-cloud output ("next" row: CCalculation::Result) ----------------- */
 #define SLC_ORDER_ROW_MAJOR 0   /* v outer, u inner: the memory order of the maps */
 #define SLC_ORDER_REFERENCE 1   /* u outer, v inner: the order Result() walks (CCalculation.cpp:336-338) */

@@ -60,6 +60,12 @@ class SlcInfo(C.Structure):
     ]
 
 
+class SlcBmpInfo(C.Structure):
+    _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("bits_per_pixel", C.c_int32), ("top_down", C.c_int32),
+                ("row_stride", C.c_int32), ("palette_is_identity", C.c_int32), ("pixel_offset", C.c_int64),
+                ("gray", C.c_uint8 * 256)]
+
+
 class SlcDynaParity(C.Structure):
     _fields_ = [("strips", C.c_void_p), ("delta_p", C.c_void_p), ("proj_u", C.c_void_p)]
 
@@ -124,6 +130,10 @@ def load_library():
     L.slc_dyna_track_host.argtypes = [vp, vp, i32, i32, vp, vp, vp, vp, C.POINTER(SlcDynaParity)]
     L.slc_eval_phase_host.argtypes = [vp, vp, vp, C.c_int64, vp, vp]
     i64p = C.POINTER(C.c_int64)
+    L.slc_bmp_parse.argtypes = [vp, C.c_int64, C.POINTER(SlcBmpInfo)]
+    L.slc_bmp_unpack_device.argtypes = [vp, vp, C.POINTER(SlcBmpInfo), vp, vp]
+    L.slc_bmp_decode_host.argtypes = [vp, vp, C.c_int64, vp, i32, i32]
+    L.slc_load_bmp_planes.argtypes = [vp, C.POINTER(C.c_char_p), i32, vp]
     L.slc_pointcloud_text_device.argtypes = [vp, vp, C.c_uint32, vp, C.c_int64, i64p, i64p, vp]
     L.slc_pointcloud_text_host.argtypes = [vp, vp, C.c_uint32, vp, C.c_int64, i64p, i64p]
     L.slc_pointcloud_compact_device.argtypes = [vp, vp, vp, i32, vp, C.c_int64, i64p, vp]
@@ -136,6 +146,15 @@ def load_library():
     L.slc_tune_pixels_per_thread.restype = None
     _lib = L
     return L
+
+
+def bmp_parse(file_bytes: bytes) -> SlcBmpInfo:
+    """Header + palette of a BMP (host only; raises SlcError for unsupported flavours)."""
+    info = SlcBmpInfo()
+    st = load_library().slc_bmp_parse(file_bytes, len(file_bytes), C.byref(info))
+    if st != SLC_OK:
+        raise SlcError(st, "not an uncompressed 8/24/32-bit BMP (or truncated)")
+    return info
 
 
 class PinnedArray:
@@ -163,6 +182,12 @@ class PinnedArray:
             self.free()
         except Exception:
             pass
+
+
+def _nbytes(a) -> int:
+    if isinstance(a, PinnedArray):
+        return int(np.prod(a.shape)) * a.dtype.itemsize
+    return int(a.nbytes)
 
 
 def _ptr(a):
@@ -345,6 +370,19 @@ class Reconstructor:
         self._check(self.lib.slc_dyna_track_device(self.h, d_frames, n_frames, window, d_u0, d_xyzw, d_mask,
                                                    d_delta_z, None, stream))
 
+    # -- input ingest -----------------------------------------------------------
+    def bmp_decode(self, file_bytes: bytes, expect_shape=None) -> np.ndarray:
+        """imread(..., GRAYSCALE) of a BMP file image, pixel work on the device."""
+        info = bmp_parse(file_bytes)
+        out = np.empty((info.height, info.width), np.uint8)
+        eh, ew = expect_shape if expect_shape else (0, 0)
+        self._check(self.lib.slc_bmp_decode_host(self.h, file_bytes, len(file_bytes), out.ctypes.data, ew, eh))
+        return out
+
+    def load_bmp_planes(self, paths, d_stack: int):
+        arr = (C.c_char_p * len(paths))(*[os.fsencode(p) for p in paths])
+        self._check(self.lib.slc_load_bmp_planes(self.h, arr, len(paths), d_stack))
+
     # -- point-cloud output ----------------------------------------------------
     def pointcloud_text(self, proj_u: np.ndarray, flags: int = 0, capacity: int | None = None):
         """CCalculation::Result's text for one f64 ProjectorU plane -> (bytes, n_points)."""
@@ -353,10 +391,16 @@ class Reconstructor:
         assert proj_u.shape == (cfg.height, cfg.width)
         cap = 43 * proj_u.size + 16 if capacity is None else capacity
         buf = np.empty(max(cap, 1), np.uint8)
+        nb, npts = self.pointcloud_text_into(proj_u, buf, flags, cap)
+        return buf[:nb].tobytes(), npts
+
+    def pointcloud_text_into(self, proj_u, text_buf, flags: int = 0, capacity: int | None = None):
+        """Same, into a caller-owned (ideally pinned) byte buffer -> (n_bytes, n_points)."""
+        cap = int(_nbytes(text_buf)) if capacity is None else capacity
         nb, npts = C.c_int64(0), C.c_int64(0)
-        self._check(self.lib.slc_pointcloud_text_host(self.h, proj_u.ctypes.data, flags, buf.ctypes.data, cap,
+        self._check(self.lib.slc_pointcloud_text_host(self.h, _ptr(proj_u), flags, _ptr(text_buf), cap,
                                                       C.byref(nb), C.byref(npts)))
-        return buf[: nb.value].tobytes(), int(npts.value)
+        return int(nb.value), int(npts.value)
 
     def pointcloud_text_device(self, d_proj_u: int, d_text: int, capacity: int, flags: int = 0,
                                stream: int | None = None):

@@ -8,6 +8,7 @@
 #include "../../include/slcalc_b200.h"
 #include "slc_kernels.h"
 
+#include <climits>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -55,6 +56,9 @@ struct slc_context {
     void* d_pc_scratch = nullptr;  size_t pc_scratch_bytes = 0;  // point cloud: block sums
     void* d_pc_in = nullptr;       size_t pc_in_bytes = 0;       // point cloud: staging for the host entry points
     void* d_pc_out = nullptr;      size_t pc_out_bytes = 0;
+    void* d_bmp[2] = {nullptr, nullptr}; size_t bmp_bytes[2] = {0, 0};   // ingest: raw file staging (device)
+    void* h_bmp[2] = {nullptr, nullptr}; size_t h_bmp_bytes[2] = {0, 0}; // ingest: raw file staging (pinned)
+    cudaEvent_t bmp_done[2] = {nullptr, nullptr};
     void* d_dyna = nullptr;        size_t dyna_bytes = 0;        // dynamic frames: staging for the host entry point
     long long launches = 0;
     std::string err;
@@ -319,6 +323,11 @@ void slc_destroy(slc_context* ctx)
     cudaFree(ctx->d_scratch_in); cudaFree(ctx->d_scratch_out); cudaFree(ctx->d_scratch_aux);
     cudaFree(ctx->d_strips); cudaFree(ctx->d_dsums); cudaFree(ctx->d_dyna);
     cudaFree(ctx->d_pc_scratch); cudaFree(ctx->d_pc_in); cudaFree(ctx->d_pc_out);
+    for (int k = 0; k < 2; k++) {
+        cudaFree(ctx->d_bmp[k]);
+        if (ctx->h_bmp[k]) cudaFreeHost(ctx->h_bmp[k]);
+        if (ctx->bmp_done[k]) cudaEventDestroy(ctx->bmp_done[k]);
+    }
     delete ctx;
 }
 
@@ -723,6 +732,148 @@ int slc_dyna_track_host(slc_context* ctx, const uint8_t* h_frames, int32_t n_fra
     if (h_parity && h_parity->strips)
         SLC_CUDA(ctx, cudaMemcpyAsync(h_parity->strips, dpar.strips, nf * npx * 2, cudaMemcpyDeviceToHost, st));
     SLC_CUDA(ctx, cudaStreamSynchronize(st));
+    return SLC_OK;
+}
+
+/* ---- input ingest ------------------------------------------------------ */
+namespace {
+
+uint32_t rd_u32(const uint8_t* p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24); }
+uint32_t rd_u16(const uint8_t* p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8); }
+
+int ensure_pinned(slc_context* ctx, void** p, size_t* have, size_t want)
+{
+    if (*have >= want) return SLC_OK;
+    if (*p) cudaFreeHost(*p);
+    *p = nullptr; *have = 0;
+    SLC_CUDA(ctx, cudaHostAlloc(p, want, cudaHostAllocDefault));
+    *have = want;
+    return SLC_OK;
+}
+
+int bmp_unpack(slc_context* ctx, const uint8_t* d_pixels, const slc_bmp_info* info, uint8_t* d_plane, cudaStream_t st)
+{
+    SLC_CUDA(ctx, slc::launch_bmp_unpack(d_pixels, info->width, info->height, info->bits_per_pixel, info->top_down,
+                                         info->row_stride, info->palette_is_identity, info->gray, d_plane, st));
+    ctx->launches++;
+    return SLC_OK;
+}
+
+}  // namespace
+
+int slc_bmp_parse(const void* file_bytes, int64_t n_bytes, slc_bmp_info* info)
+{
+    if (!file_bytes || !info || n_bytes < 54) return SLC_ERR_INVALID_ARG;
+    const uint8_t* f = static_cast<const uint8_t*>(file_bytes);
+    if (f[0] != 'B' || f[1] != 'M') return SLC_ERR_INVALID_ARG;
+    const uint32_t off = rd_u32(f + 10), hdr = rd_u32(f + 14);
+    if (hdr < 40) return SLC_ERR_INVALID_ARG;                      /* BITMAPCOREHEADER files are not camera output */
+    const int32_t w = (int32_t)rd_u32(f + 18), hs = (int32_t)rd_u32(f + 22);
+    const uint32_t bpp = rd_u16(f + 28), comp = rd_u32(f + 30);
+    uint32_t used = rd_u32(f + 46);
+    if (w <= 0 || hs == 0 || hs == INT32_MIN) return SLC_ERR_INVALID_ARG;
+    if (comp != 0 || (bpp != 8 && bpp != 24 && bpp != 32)) return SLC_ERR_INVALID_ARG;
+    std::memset(info, 0, sizeof(*info));
+    info->width = w;
+    info->height = hs < 0 ? -hs : hs;
+    info->bits_per_pixel = (int32_t)bpp;
+    info->top_down = hs < 0;
+    const int64_t stride = (((int64_t)w * (bpp / 8)) + 3) & ~(int64_t)3;
+    if (stride > INT32_MAX) return SLC_ERR_INVALID_ARG;
+    info->row_stride = (int32_t)stride;
+    info->pixel_offset = off;
+    if ((int64_t)off + stride * info->height > n_bytes) return SLC_ERR_INVALID_ARG;   /* truncated */
+    info->palette_is_identity = 1;
+    if (bpp == 8) {
+        if (used == 0 || used > 256) used = 256;
+        if (14 + (int64_t)hdr + 4 * (int64_t)used > n_bytes) return SLC_ERR_INVALID_ARG;
+        const uint8_t* pal = f + 14 + hdr;                          /* B G R 0 */
+        for (uint32_t i = 0; i < used; i++) {
+            const uint32_t g = (pal[4 * i] * 1868u + pal[4 * i + 1] * 9617u + pal[4 * i + 2] * 4899u + 8192u) >> 14;
+            info->gray[i] = (uint8_t)g;
+        }
+        for (int i = 0; i < 256; i++)
+            if (info->gray[i] != i) info->palette_is_identity = 0;
+    }
+    return SLC_OK;
+}
+
+int slc_bmp_unpack_device(slc_context* ctx, const uint8_t* d_pixels, const slc_bmp_info* info, uint8_t* d_plane,
+                          void* cuda_stream)
+{
+    if (!ctx) return SLC_ERR_INVALID_ARG;
+    if (!d_pixels || !info || !d_plane) return fail(ctx, SLC_ERR_INVALID_ARG, "NULL argument");
+    SLC_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+    cudaStream_t st = cuda_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : ctx->stream;
+    return bmp_unpack(ctx, d_pixels, info, d_plane, st);
+}
+
+int slc_bmp_decode_host(slc_context* ctx, const void* h_file_bytes, int64_t n_bytes, uint8_t* h_plane,
+                        int32_t expect_width, int32_t expect_height)
+{
+    if (!ctx) return SLC_ERR_INVALID_ARG;
+    if (!h_file_bytes || !h_plane) return fail(ctx, SLC_ERR_INVALID_ARG, "NULL buffer");
+    slc_bmp_info info;
+    if (slc_bmp_parse(h_file_bytes, n_bytes, &info) != SLC_OK)
+        return fail(ctx, SLC_ERR_INVALID_ARG, "not an uncompressed 8/24/32-bit BMP (or truncated)");
+    if ((expect_width > 0 && info.width != expect_width) || (expect_height > 0 && info.height != expect_height))
+        return fail(ctx, SLC_ERR_INVALID_ARG, "BMP is %dx%d, expected %dx%d", info.width, info.height, expect_width,
+                    expect_height);
+    SLC_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+    const size_t raw = (size_t)info.row_stride * info.height, plane = (size_t)info.width * info.height;
+    int rc = ensure_scratch(ctx, &ctx->d_bmp[0], &ctx->bmp_bytes[0], raw + plane);
+    if (rc != SLC_OK) return rc;
+    uint8_t* d_raw = static_cast<uint8_t*>(ctx->d_bmp[0]);
+    uint8_t* d_plane = d_raw + raw;
+    SLC_CUDA(ctx, cudaMemcpyAsync(d_raw, static_cast<const uint8_t*>(h_file_bytes) + info.pixel_offset, raw,
+                                  cudaMemcpyHostToDevice, ctx->stream));
+    rc = bmp_unpack(ctx, d_raw, &info, d_plane, ctx->stream);
+    if (rc != SLC_OK) return rc;
+    SLC_CUDA(ctx, cudaMemcpyAsync(h_plane, d_plane, plane, cudaMemcpyDeviceToHost, ctx->stream));
+    SLC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SLC_OK;
+}
+
+int slc_load_bmp_planes(slc_context* ctx, const char* const* paths, int32_t n_files, uint8_t* d_stack)
+{
+    if (!ctx) return SLC_ERR_INVALID_ARG;
+    if (!paths || !d_stack || n_files < 0) return fail(ctx, SLC_ERR_INVALID_ARG, "NULL argument or n_files < 0");
+    SLC_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+    const size_t npx = (size_t)ctx->kp.npx;
+    for (int k = 0; k < 2; k++)
+        if (!ctx->bmp_done[k]) SLC_CUDA(ctx, cudaEventCreateWithFlags(&ctx->bmp_done[k], cudaEventDisableTiming));
+    int used[2] = {0, 0};
+    for (int i = 0; i < n_files; i++) {
+        const int k = i & 1;
+        if (!paths[i]) return fail(ctx, SLC_ERR_INVALID_ARG, "NULL path for file %d", i);
+        FILE* f = std::fopen(paths[i], "rb");
+        if (!f) return fail(ctx, SLC_ERR_INVALID_ARG, "imread error: %s", paths[i]);     /* CSensorV.cpp:122-129 */
+        std::fseek(f, 0, SEEK_END);
+        const long sz = std::ftell(f);
+        std::fseek(f, 0, SEEK_SET);
+        if (sz < 54) { std::fclose(f); return fail(ctx, SLC_ERR_INVALID_ARG, "imread error: %s", paths[i]); }
+        // the staging pair is reused every other file: wait until its previous upload + unpack are done
+        if (used[k]) SLC_CUDA(ctx, cudaEventSynchronize(ctx->bmp_done[k]));
+        int rc = ensure_pinned(ctx, &ctx->h_bmp[k], &ctx->h_bmp_bytes[k], (size_t)sz);
+        if (rc == SLC_OK) rc = ensure_scratch(ctx, &ctx->d_bmp[k], &ctx->bmp_bytes[k], (size_t)sz + npx);
+        if (rc != SLC_OK) { std::fclose(f); return rc; }
+        const size_t got = std::fread(ctx->h_bmp[k], 1, (size_t)sz, f);
+        std::fclose(f);
+        slc_bmp_info info;
+        if (got != (size_t)sz || slc_bmp_parse(ctx->h_bmp[k], sz, &info) != SLC_OK)
+            return fail(ctx, SLC_ERR_INVALID_ARG, "imread error (not an uncompressed 8/24/32-bit BMP): %s", paths[i]);
+        if (info.width != ctx->kp.W || info.height != ctx->kp.H)
+            return fail(ctx, SLC_ERR_INVALID_ARG, "%s is %dx%d, the context is %dx%d", paths[i], info.width, info.height,
+                        ctx->kp.W, ctx->kp.H);
+        const size_t raw = (size_t)info.row_stride * info.height;
+        SLC_CUDA(ctx, cudaMemcpyAsync(ctx->d_bmp[k], static_cast<uint8_t*>(ctx->h_bmp[k]) + info.pixel_offset, raw,
+                                      cudaMemcpyHostToDevice, ctx->stream));
+        rc = bmp_unpack(ctx, static_cast<const uint8_t*>(ctx->d_bmp[k]), &info, d_stack + (size_t)i * npx, ctx->stream);
+        if (rc != SLC_OK) return rc;
+        SLC_CUDA(ctx, cudaEventRecord(ctx->bmp_done[k], ctx->stream));
+        used[k] = 1;
+    }
+    SLC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return SLC_OK;
 }
 

@@ -46,6 +46,10 @@ cudaError_t launch_pointcloud(const KParams& p, int mode, int order, unsigned fl
 cudaError_t launch_format_g6(const double* d_values, long long n, unsigned flags, char* d_text, uint8_t* d_len,
                              cudaStream_t stream);
 
+// input ingest (slc_ingest.cu)
+cudaError_t launch_bmp_unpack(const uint8_t* d_pixels, int width, int height, int bpp, int top_down, int row_stride,
+                              int identity, const uint8_t* gray256, uint8_t* d_plane, cudaStream_t stream);
+
 // tuning hook (bench / tests): pixels per thread of the vector kernel, 4 / 8 / 16
 void set_default_pixels_per_thread(int pxt);
 

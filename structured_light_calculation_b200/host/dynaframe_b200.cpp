@@ -167,12 +167,57 @@ bool CSensor::StoreDatas(int groupNum, int idx, const Mat& picture)
     return true;
 }
 
+void CSensor::AttachFiles(slc_context* ctx, const StaticParameters& sp, const std::string& groupDataPath)
+{
+    ctx_ = ctx;
+    m_groupDataPath = groupDataPath;
+    if (!m_groupDataPath.empty() && m_groupDataPath.back() != '/' && m_groupDataPath.back() != '\\') m_groupDataPath += '/';
+    counts_[0] = sp.GRAY_V_NUMDIGIT * 2;       // CSensorV.cpp:74
+    counts_[1] = sp.PHASE_NUMDIGIT;            // :82
+    counts_[2] = sp.DYNAFRAME_MAXNUM;          // :90
+    rows_ = sp.CAMERA_RESROW;
+    cols_ = sp.CAMERA_RESLINE;
+}
+
+std::string CSensor::FileName(int groupNum, int idx) const
+{
+    // CSensorV.cpp:111-114: m_filePath + m_fileName + idx + m_fileSuffix
+    std::ostringstream ss;
+    ss << m_groupDataPath << (groupNum == 2 ? m_cFramePath : m_iFramePath)
+       << (groupNum == 0 ? m_vGrayName : groupNum == 1 ? m_vPhaseName : m_dynaName) << idx << m_dataFileSuffix;
+    return ss.str();
+}
+
 bool CSensor::LoadDatas(int groupNum)
 {
-    // CSensorV.cpp:60-133 chooses the file group; here the group is already in memory
+    // CSensorV.cpp:60-133
     if (groupNum < 0 || groupNum > 2) { ErrorHandling("CSensor::LoadDatas->invalid groupNum."); return false; }
     group_ = groupNum;
     now_ = 0;
+    if (ctx_ == nullptr || m_groupDataPath.empty() || !groups_[groupNum].empty()) return true;   // fed from memory
+    std::vector<Mat>& g = groups_[groupNum];
+    for (int i = 0; i < counts_[groupNum]; i++) {
+        const std::string path = FileName(groupNum, i);
+        std::ifstream f(path.c_str(), std::ios::binary | std::ios::ate);
+        Mat pic;
+        bool ok = (bool)f;
+        if (ok) {
+            const std::streamsize n = f.tellg();
+            std::vector<char> bytes((size_t)(n > 0 ? n : 0));
+            f.seekg(0);
+            ok = n > 0 && (bool)f.read(bytes.data(), n);
+            if (ok) {
+                pic.create(rows_, cols_, CV_8UC1);
+                ok = slc_bmp_decode_host(ctx_, bytes.data(), (int64_t)n, pic.ptr(), cols_, rows_) == SLC_OK;
+            }
+        }
+        if (!ok) {
+            if (groupNum == 2 && i >= 2) break;          // a shorter dynamic sequence than DYNAFRAME_MAXNUM
+            ErrorHandling("CSensor::LoadPatterns::<Read>, imread error: " + path);   // :122-129 (reports, continues)
+            pic = Mat();
+        }
+        g.push_back(pic);
+    }
     return true;
 }
 
@@ -372,6 +417,7 @@ bool CCalculation::Init()
         ReleaseSpace();
         return false;
     }
+    if (!m_groupDataPath.empty()) m_sensor->AttachFiles(ctx_, sp_, m_groupDataPath);
     const size_t npx = (size_t)sp_.CAMERA_RESROW * sp_.CAMERA_RESLINE;
     const size_t planes = (size_t)2 * sp_.GRAY_V_NUMDIGIT + sp_.PHASE_NUMDIGIT;
     pinned_stack_ = static_cast<uint8_t*>(slc_host_alloc(planes * npx));

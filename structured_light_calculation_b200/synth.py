@@ -125,3 +125,51 @@ def render_dyna_frames(cfg: StackConfig, cal: Calibration, n_frames: int, stripe
         img = np.where(sc.lit, img, 6.0) + rng.standard_normal(img.shape) * noise_sigma
         frames[f] = np.clip(np.rint(img), 0, 255).astype(np.uint8)
     return frames
+
+
+def encode_bmp(pixels: np.ndarray, bpp: int = 8, top_down: bool = False) -> bytes:
+    """A BITMAPINFOHEADER .bmp of a [H][W] u8 image: 8 bpp with the gray palette a camera SDK
+    writes, or 24 bpp (B = G = R).  Test / bench input for the ingest path (the reference reads
+    vGrayCam{i}.bmp etc., CSensorV.cpp:111-114)."""
+    import struct
+    pixels = np.ascontiguousarray(pixels, dtype=np.uint8)
+    H, W = pixels.shape
+    if bpp == 24:
+        pixels = np.repeat(pixels[:, :, None], 3, axis=2)
+    elif bpp != 8:
+        raise ValueError("bpp must be 8 or 24")
+    row = W * (bpp // 8)
+    stride = (row + 3) & ~3
+    rows = pixels if top_down else pixels[::-1]
+    body = np.zeros((H, stride), np.uint8)
+    body[:, :row] = rows.reshape(H, row)
+    pal = b""
+    if bpp == 8:
+        g = np.arange(256, dtype=np.uint8)
+        pal = np.stack([g, g, g, np.zeros(256, np.uint8)], axis=1).tobytes()
+    off = 14 + 40 + len(pal)
+    head = struct.pack("<2sIHHI", b"BM", off + body.size, 0, 0, off)
+    info = struct.pack("<IiiHHIIiiII", 40, W, -H if top_down else H, 1, bpp, 0, body.size, 2835, 2835, 0, 0)
+    return head + info + pal + body.tobytes()
+
+
+def write_reference_layout(group_dir: str, cfg: StackConfig, planes: np.ndarray, dyna_frames=None, bpp: int = 8):
+    """Write a stack (and optionally a dynamic sequence) as the reference's file layout
+    (CSensorV.cpp:35-41): iFrame/vGrayCam{i}.bmp, iFrame/vPhaseCam{i}.bmp, cFrame/dynaCam{i}.bmp.
+    Returns the list of first-frame paths in stack-plane order."""
+    import os
+    G2 = 2 * cfg.gray_digits
+    os.makedirs(os.path.join(group_dir, "iFrame"), exist_ok=True)
+    paths = []
+    for i in range(planes.shape[0]):
+        name = f"vGrayCam{i}.bmp" if i < G2 else f"vPhaseCam{i - G2}.bmp"
+        path = os.path.join(group_dir, "iFrame", name)
+        with open(path, "wb") as f:
+            f.write(encode_bmp(planes[i], bpp))
+        paths.append(path)
+    if dyna_frames is not None:
+        os.makedirs(os.path.join(group_dir, "cFrame"), exist_ok=True)
+        for i in range(dyna_frames.shape[0]):
+            with open(os.path.join(group_dir, "cFrame", f"dynaCam{i}.bmp"), "wb") as f:
+                f.write(encode_bmp(dyna_frames[i], bpp))
+    return paths

@@ -10,6 +10,7 @@
 // reads  <dir>/planes.u8 (2G+N planes), <dir>/parameters.yml, <dir>/vGrayCode.txt
 // writes <dir>/gray.f64 <dir>/phase.f64 <dir>/xyzw.f32 <dir>/mask.u8 <dir>/projU.f64 <dir>/cloud.txt
 #include <cstdio>
+#include <cstring>
 #include <cstdlib>
 #include <fstream>
 #include <string>
@@ -134,6 +135,28 @@ int main(int argc, char** argv)
     CHECK(!calc.Result(dir + "/no/such/dir/cloud.txt", 0));   // open failure (CCalculation.cpp:327-331)
     Mat z = calc.GetZ();
     CHECK(z.type() == CV_64FC1 && z.at<double>(H / 2, W / 2) == (double)calc.PointMap().at<float>(H / 2, 4 * (W / 2) + 2));
+    {   // file-backed sensor (CSensorV.cpp:31-133): <dir>/group/iFrame/vGrayCam{i}.bmp ... through a second CCalculation
+        std::ifstream probe(dir + "/group/iFrame/vGrayCam0.bmp", std::ios::binary);
+        if (probe) {
+            CCalculation fcalc(sp);
+            fcalc.SetParameterFile("parameters.yml");
+            fcalc.SetGrayCodeFile(dir + "/", "vGrayCode.txt");
+            fcalc.SetPointCloudFile("");
+            fcalc.SetGroupDataPath(dir + "/group");
+            CHECK(fcalc.Init());
+            CHECK(fcalc.Sensor()->FileName(0, 3) == dir + "/group/iFrame/vGrayCam3.bmp");
+            CHECK(fcalc.Sensor()->FileName(1, 0) == dir + "/group/iFrame/vPhaseCam0.bmp");
+            CHECK(fcalc.Sensor()->FileName(2, 7) == dir + "/group/cFrame/dynaCam7.bmp");
+            CHECK(fcalc.CalculateFirst());
+            CHECK(std::memcmp(fcalc.PointMap().ptr(), calc.PointMap().ptr(), npx * 16) == 0);
+            CHECK(std::memcmp(fcalc.ValidMask().ptr(), calc.ValidMask().ptr(), npx) == 0);
+            CHECK(fcalc.CalculateOther());
+            CHECK(fcalc.FrameCount() == calc.FrameCount());
+            for (int i = 1; i < fcalc.FrameCount(); i++)
+                CHECK(std::memcmp(fcalc.PointMap(i).ptr(), calc.PointMap(i).ptr(), npx * 16) == 0);
+            std::printf("file-backed sensor ok\n");
+        }
+    }
     std::printf("host_api_test ok\n");
     return 0;
 }

@@ -18,7 +18,10 @@ The reference ships no tests or golden vectors and cannot be compiled here
                           with every intermediate plane stored;
   4. dyna_g6.npz       -- the dynamic-frame path (StripRegression, FillOtherDeltaProU) restated
                           with numpy cumsum/argmin and cv2.blur;
-  5. kat.npz           -- the hand-derived known-answer tables of SURVEY.md 8(c).
+  5. kat.npz           -- the hand-derived known-answer tables of SURVEY.md 8(c);
+  6. bmp_cases.npz     -- BMP files (8-bit gray / colour palette, 24- and 32-bit, bottom-up and top-down,
+                          padded rows) with what cv2.imread(path, IMREAD_GRAYSCALE) -- the call of
+                          CSensorV.cpp:111-114 -- returns for each.
 Nothing here imports the oracle: the fixtures are independent of it.
 """
 import hashlib
@@ -199,6 +202,58 @@ def golden_dyna():
     print("dyna: nonzero deltaP", [(d != 0).mean() for d in out["delta_p"]])
 
 
+def make_bmp(pixels: np.ndarray, bpp: int, palette: np.ndarray | None = None, top_down: bool = False,
+             clr_used: int = 0) -> bytes:
+    """A BITMAPINFOHEADER BMP.  pixels: [H][W] indices (8 bpp) or [H][W][3|4] BGR(A)."""
+    import struct
+    H, W = pixels.shape[:2]
+    bytes_pp = bpp // 8
+    stride = (W * bytes_pp + 3) & ~3
+    rows = pixels if top_down else pixels[::-1]
+    body = bytearray()
+    for r in rows:
+        raw = np.ascontiguousarray(r, dtype=np.uint8).tobytes()
+        body += raw + b"\0" * (stride - len(raw))
+    pal = b""
+    if bpp == 8:
+        n = clr_used if clr_used else 256
+        pal = np.concatenate([palette[:n].astype(np.uint8), np.zeros((n, 1), np.uint8)], axis=1).tobytes()   # B G R 0
+    off = 14 + 40 + len(pal)
+    head = struct.pack("<2sIHHI", b"BM", off + len(body), 0, 0, off)
+    info = struct.pack("<IiiHHIIiiII", 40, W, -H if top_down else H, 1, bpp, 0, len(body), 2835, 2835, clr_used, 0)
+    return head + info + pal + bytes(body)
+
+
+def golden_bmp():
+    import tempfile
+    rng = np.random.Generator(np.random.PCG64(99))
+    ident = np.repeat(np.arange(256, dtype=np.uint8)[:, None], 3, axis=1)
+    colour = rng.integers(0, 256, (256, 3)).astype(np.uint8)
+    cases = {
+        "gray8_37x11": make_bmp(rng.integers(0, 256, (11, 37)), 8, ident),
+        "gray8_64x16_topdown": make_bmp(rng.integers(0, 256, (16, 64)), 8, ident, top_down=True),
+        "pal8_colour_50x9": make_bmp(rng.integers(0, 256, (9, 50)), 8, colour),
+        "pal8_used100_21x7": make_bmp(rng.integers(0, 100, (7, 21)), 8, colour, clr_used=100),
+        "bgr24_33x10": make_bmp(rng.integers(0, 256, (10, 33, 3)), 24),
+        "bgr24_40x6_topdown": make_bmp(rng.integers(0, 256, (6, 40, 3)), 24, top_down=True),
+        "bgra32_19x5": make_bmp(rng.integers(0, 256, (5, 19, 4)), 32),
+        "bgr24_extremes_16x4": make_bmp(np.array([[[255, 255, 255], [0, 0, 0], [255, 0, 0], [0, 255, 0], [0, 0, 255],
+                                                   [1, 1, 1], [254, 255, 253], [128, 127, 129]] * 2] * 4), 24),
+    }
+    out = {}
+    with tempfile.TemporaryDirectory() as d:
+        for name, data in cases.items():
+            path = os.path.join(d, name + ".bmp")
+            with open(path, "wb") as f:
+                f.write(data)
+            img = cv2.imread(path, cv2.IMREAD_GRAYSCALE)      # CSensorV.cpp:111-114
+            assert img is not None and img.dtype == np.uint8, name
+            out[name + "__file"] = np.frombuffer(data, np.uint8)
+            out[name + "__gray"] = img
+    np.savez_compressed(os.path.join(HERE, "bmp_cases.npz"), **out)
+    print("bmp cases", list(cases))
+
+
 def golden_kat():
     # SURVEY.md 8(c) KAT-E (G=6, PW=1280, T=40, gp=20) and KAT-T (Result.yml)
     kat_e = np.array([
@@ -223,6 +278,7 @@ def golden_kat():
 
 
 if __name__ == "__main__":
+    golden_bmp()
     golden_fast_atan2()
     if os.path.isdir(REF):
         golden_gray_code()

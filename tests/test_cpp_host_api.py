@@ -54,10 +54,11 @@ def test_cpp_host_api_matches_oracle(tmp_path, built_library, oracle, base_calib
     from structured_light_calculation_b200 import synth
     frames = synth.render_dyna_frames(cfg, cal, 4, stripe_period=14.0, z_step=0.4, noise_sigma=1.5)
     frames.tofile(d / "dyna.u8")
+    synth.write_reference_layout(str(d / "group"), cfg, planes, dyna_frames=frames, bpp=8 if G == 6 else 24)
     res = subprocess.run([exe, str(d), str(W), str(H), str(PW), str(G), str(N)], stdout=subprocess.PIPE,
                          stderr=subprocess.STDOUT, text=True)
     assert res.returncode == 0, res.stdout
-    assert "host_api_test ok" in res.stdout
+    assert "host_api_test ok" in res.stdout and "file-backed sensor ok" in res.stdout
     want = oracle_run(oracle, cfg, cal, planes)
     gray = np.fromfile(d / "gray.f64", np.float64).reshape(H, W)
     phase = np.fromfile(d / "phase.f64", np.float64).reshape(H, W)
