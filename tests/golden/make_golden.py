@@ -19,6 +19,10 @@ The reference ships no tests or golden vectors and cannot be compiled here
   4. dyna_g6.npz       -- the dynamic-frame path (StripRegression, FillOtherDeltaProU) restated
                           with numpy cumsum/argmin and cv2.blur;
   5. kat.npz           -- the hand-derived known-answer tables of SURVEY.md 8(c);
+  7. reference_run_g6n4.npz -- inputs and outputs of the REFERENCE ITSELF: oracle/_ref/dynaframe_ref
+                          (the reference's own path sources compiled in place, oracle/Makefile) run on a
+                          small synthetic stack + dynamic sequence laid out as the reference reads it;
+                          every plane it computes and the text clouds it writes.
   6. bmp_cases.npz     -- BMP files (8-bit gray / colour palette, 24- and 32-bit, bottom-up and top-down,
                           padded rows) with what cv2.imread(path, IMREAD_GRAYSCALE) -- the call of
                           CSensorV.cpp:111-114 -- returns for each.
@@ -254,6 +258,34 @@ def golden_bmp():
     print("bmp cases", list(cases))
 
 
+def golden_reference_run():
+    """Run the reference's own compiled sources and keep what they produce."""
+    from oracle import ref_runner as R          # builds / runs the reference binary only (not the oracle port)
+    if not R.build():
+        print("reference binary unavailable; keeping the committed reference_run fixture")
+        return
+    base = load_calibration(os.path.join(HERE, "Result.yml"))
+    cfg = StackConfig(72, 56, 1280, 6, 4)       # the reference's own digit counts and projector width
+    cal = synth.synthetic_calibration(cfg, base)
+    scene = synth.make_scene(cfg, cal)
+    planes = synth.render_stack(cfg, scene, noise_sigma=1.0, seed=17)
+    frames = synth.render_dyna_frames(cfg, cal, 4, stripe_period=14.0, z_step=0.4, noise_sigma=1.5)
+    ws = R.Workspace(cfg, cal, planes, frames)
+    full = ws.run_full()
+    first = ws.run_first()
+    ws.close()
+    out = {"planes": planes, "dyna_frames": frames, "cam": cal.cam, "pro": cal.pro, "R": cal.R, "T": cal.T,
+           "gray": first["gray"], "phase": first["phase"], "A": first["A"], "B": first["B"], "P": first["P"],
+           "cC": first["cC"], "cD": first["cD"]}
+    for f, fr in enumerate(full["frames"]):
+        for k, v in fr.items():
+            out[f"f{f}_{k}"] = v
+        out[f"cloud{f}"] = np.frombuffer(full["clouds"][f], np.uint8)
+    assert np.array_equal(first["projU"], full["frames"][0]["projU"]) and np.array_equal(first["z"], full["frames"][0]["z"])
+    np.savez_compressed(os.path.join(HERE, "reference_run_g6n4.npz"), **out)
+    print("reference run:", {k: (v.shape if hasattr(v, "shape") else v) for k, v in list(out.items())[:6]}, "...")
+
+
 def golden_kat():
     # SURVEY.md 8(c) KAT-E (G=6, PW=1280, T=40, gp=20) and KAT-T (Result.yml)
     kat_e = np.array([
@@ -278,6 +310,7 @@ def golden_kat():
 
 
 if __name__ == "__main__":
+    golden_reference_run()
     golden_bmp()
     golden_fast_atan2()
     if os.path.isdir(REF):
