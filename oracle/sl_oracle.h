@@ -6,12 +6,16 @@
  * cpu_baseline / --impl reference legs may load this; the product library
  * (libslcalc_b200.so) never links or calls it.
  *
- * PARITY PINNING: the reference ships no tests or golden vectors
- *  and cannot be compiled here (needs OpenCV 2.4.9 C++
- * headers + Windows; neither present).  The oracle is pinned instead against
+ * PARITY PINNING: the reference ships no tests or golden vectors (SURVEY.md
+ * section 4).  This restatement is pinned against
+ *   - the reference ITSELF: oracle/_ref/dynaframe_ref, the reference's own path
+ *     sources compiled in place (oracle/Makefile) against a minimal OpenCV
+ *     stand-in (oracle/ref_shim/); bit for bit on every f64 plane and byte for
+ *     byte on the text clouds (tests/test_reference_pinning.py, and the
+ *     committed run tests/golden/reference_run_g6n4.npz);
  *   - the container's cv2 4.13 scalar primitives (cv2.fastAtan2,
- *     cv2.subtract) through committed fixtures tests/golden/ (.npz files) made by
- *     tests/golden/make_golden.py, and
+ *     cv2.subtract, cv2.gemm, cv2.blur) through committed fixtures
+ *     tests/golden/ (.npz files) made by tests/golden/make_golden.py, and
  *   - the hand-derived known-answer tables of SURVEY.md section 8(c)
  *     (KAT-E, KAT-T) which follow the cited reference formulas.
  * The third-party arithmetic on the path (cvFastArctan, OpenCV 2.4.9

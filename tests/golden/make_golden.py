@@ -4,8 +4,9 @@
 Run in the build container (needs cv2 4.13 and, for the Gray-code table check,
 /root/reference):  python tests/golden/make_golden.py
 
-The reference ships no tests or golden vectors and cannot be compiled here
-(OpenCV 2.4.9 C++ + Windows), so the pins are:
+The reference ships no tests or golden vectors, so the pins are made here (the
+reference's own sources are compiled in place against a minimal OpenCV stand-in,
+oracle/Makefile -> oracle/_ref, for item 7; cv2 4.13 pins the OpenCV primitives):
   1. fast_atan2.npz    -- the container's *scalar* cv2.fastAtan2 on all 511^2
                           (s, c) pairs reachable from 4-step u8 input: sha256 of
                           the full f32 table + an explicit 8k-sample subset;
