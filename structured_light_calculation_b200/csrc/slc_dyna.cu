@@ -408,10 +408,18 @@ struct DynaOut {
 
 // The frame-to-frame recurrence U[f] = U[f-1] + deltaP[f] (CCalculation.cpp:656-658) is per
 // pixel: one thread walks all frames of its pixel, then FillCoordinate (:672-775) per frame.
+constexpr int kLutN = 2 * 9 * 19 + 1;               // 3x3 sums of deltas in [-19, 19]: [-171, 171]
+
 __global__ void __launch_bounds__(256)
 dyna_track_kernel(const __grid_constant__ KParams p, const unsigned short* __restrict__ sums, int n_frames,
                   const double* __restrict__ u0, const DynaOut o)
 {
+    // deltaP for every possible 3x3 sum: cv::blur on CV_32F is a double sum * (1./9) narrowed to
+    // float (:650); kept as the double it is added to U as (:656-658)
+    __shared__ double s_dp[kLutN];
+    for (int i = threadIdx.x; i < kLutN; i += blockDim.x)
+        s_dp[i] = (double)(float)__dmul_rn((double)(i - kLutN / 2), 1.0 / 9.0);
+    __syncthreads();
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= p.npx) return;
     int v, u;
@@ -428,35 +436,46 @@ dyna_track_kernel(const __grid_constant__ KParams p, const unsigned short* __res
         if (U != 0.0) r0 = resolve_f64_u(p, U, u, v, &ok);
         z_prev = r0.z;
     }
+    // the 3x3 sums of the next group of frames are in flight while this group is processed
     constexpr int kAhead = 4;
+    const unsigned short* sp = sums + idx;
+    unsigned short cur[kAhead], nxt[kAhead];
+#pragma unroll
+    for (int k = 0; k < kAhead; k++)
+        cur[k] = (1 + k < n_frames) ? __ldcs(sp + (long long)k * p.npx) : (unsigned short)kDsBias9;
     for (int f0 = 1; f0 < n_frames; f0 += kAhead) {
-        unsigned short sv[kAhead];
 #pragma unroll
         for (int k = 0; k < kAhead; k++)
-            sv[k] = (f0 + k < n_frames) ? __ldcs(sums + (long long)(f0 + k - 1) * p.npx + idx) : (unsigned short)kDsBias9;
+            nxt[k] = (f0 + kAhead + k < n_frames) ? __ldcs(sp + (long long)(f0 + kAhead + k - 1) * p.npx)
+                                                  : (unsigned short)kDsBias9;
 #pragma unroll
         for (int k = 0; k < kAhead; k++) {
             const int f = f0 + k;
             if (f >= n_frames) break;
-            // cv::blur on CV_32F: double sum, * (1./9), narrowed to float (:650)
-            const float dP = (float)__dmul_rn((double)((int)sv[k] - kDsBias9), 1.0 / 9.0);
-            U = __dadd_rn(U, (double)dP);                        // :656-658
+            const double dP = s_dp[(int)cur[k] - (kDsBias9 - kLutN / 2)];
+            U = __dadd_rn(U, dP);                                // :656-658
             // FillCoordinate (:672-771): f32 solve on U split exactly into two floats
             const float a = (float)U;
             const float b = (float)(U - (double)a);
             PixelResult r;
             triangulate_split<false>(p, rc, a, b, U != 0.0, uf, r);
             float4 outv = make_float4(r.x, r.y, r.z, r.w);
-            int ok = r.valid ? 1 : 0;
-            if (r.need64) outv = resolve_f64_u(p, U, u, v, &ok);
+            bool ok = r.valid;
+            if (r.need64) {
+                int ok64;                                        // address-taken only inside the rare branch
+                outv = resolve_f64_u(p, U, u, v, &ok64);
+                ok = ok64 != 0;
+            }
             const long long q = (long long)(f - 1) * p.npx + idx;
             st_stream_f4(o.xyzw + q, outv);
-            o.mask[q] = (uint8_t)ok;
+            o.mask[q] = ok ? (uint8_t)1 : (uint8_t)0;
             if (o.delta_z) o.delta_z[q] = outv.z - z_prev;       // :772-775
-            if (o.delta_p) o.delta_p[q] = dP;
+            if (o.delta_p) o.delta_p[q] = (float)dP;
             if (o.proj_u) o.proj_u[q] = U;
             z_prev = outv.z;
         }
+#pragma unroll
+        for (int k = 0; k < kAhead; k++) cur[k] = nxt[k];
     }
     if (o.u_final) o.u_final[idx] = U;
 }

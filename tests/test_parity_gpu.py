@@ -481,3 +481,68 @@ def test_dynamic_frames_match_oracle(built_library, oracle, base_calibration, W,
 def test_smoke_entry_point(built_library):
     import __graft_entry__
     __graft_entry__.smoke()
+
+
+def test_device_entry_points_stay_inside_their_buffers(built_library, oracle, base_calibration, tmp_path):
+    """compute-sanitizer is not available on the GPU pool, so every device entry point that writes a
+    caller-owned buffer is run with canary bytes after (and before) the region it may touch."""
+    import torch
+    from structured_light_calculation_b200 import capi, synth
+    from structured_light_calculation_b200.capi import SlcDynaParity
+    from structured_light_calculation_b200.configs import StackConfig
+    W, H, n_frames = 200, 75, 5
+    cfg = StackConfig(W, H, 1280, 7, 4)
+    cal, scene, planes = make_case(cfg, base_calibration, noise=1.0, seed=3)
+    frames = synth.render_dyna_frames(cfg, cal, n_frames, stripe_period=14.0, z_step=0.4, noise_sigma=1.5)
+    npx, PAD, CAN = W * H, 4096, 0xA5
+    dev = torch.device("cuda", 0)
+
+    def guarded(nbytes):
+        t = torch.full((nbytes + 2 * PAD,), CAN, dtype=torch.uint8, device=dev)
+        return t, t.data_ptr() + PAD
+
+    def intact(t, nbytes):
+        return bool((t[:PAD] == CAN).all()) and bool((t[PAD + nbytes:] == CAN).all())
+
+    rec = _reconstructor(cfg, cal)
+    d_stack = torch.from_numpy(planes).to(dev)
+    bufs = {"xyzw": 16 * npx, "mask": npx, "kbin": 2 * npx, "corr": npx, "pix": 4 * npx, "u": 8 * npx}
+    g = {k: guarded(n) for k, n in bufs.items()}
+    par = capi.SlcParityPlanes(g["kbin"][1], g["corr"][1], g["pix"][1], g["u"][1])
+    rec.reconstruct_device(d_stack.data_ptr(), 1, g["xyzw"][1], g["mask"][1], par)
+    rec.synchronize()
+    assert all(intact(g[k][0], n) for k, n in bufs.items())
+    d_u0 = g["u"][0][PAD:PAD + 8 * npx].clone()
+
+    d_frames = torch.from_numpy(frames).to(dev)
+    no = n_frames - 1
+    dbufs = {"xyzw": 16 * npx * no, "mask": npx * no, "dz": 4 * npx * no, "strips": 2 * npx * n_frames,
+             "dp": 4 * npx * no, "pu": 8 * npx * no}
+    dg = {k: guarded(n) for k, n in dbufs.items()}
+    dpar = SlcDynaParity(dg["strips"][1], dg["dp"][1], dg["pu"][1])
+    rec._check(rec.lib.slc_dyna_track_device(rec.h, d_frames.data_ptr(), n_frames, 21, d_u0.data_ptr(), dg["xyzw"][1],
+                                             dg["mask"][1], dg["dz"][1], dpar, None))
+    rec.synchronize()
+    assert all(intact(dg[k][0], n) for k, n in dbufs.items())
+
+    # text cloud: exactly `bytes` bytes written, nothing after them
+    cap = 43 * npx + 16
+    tt, tptr = guarded(cap)
+    nb, npts = rec.pointcloud_text_device(g["u"][1], tptr, cap)
+    assert npts > 0 and intact(tt, cap) and bool((tt[PAD + nb:PAD + cap] == CAN).all())
+    ct, cptr = guarded(12 * npx)
+    n = rec.pointcloud_compact_device(g["xyzw"][1], g["mask"][1], cptr, npx, capi.SLC_ORDER_REFERENCE)
+    assert n == npts and intact(ct, 12 * npx) and bool((ct[PAD + 12 * n:PAD + 12 * npx] == CAN).all())
+
+    # BMP unpack: odd width, padded rows
+    img = np.random.default_rng(1).integers(0, 256, (37, 53)).astype(np.uint8)
+    for bpp in (8, 24):
+        data = synth.encode_bmp(img, bpp)
+        info = capi.bmp_parse(data)
+        raw = torch.frombuffer(bytearray(data[info.pixel_offset:]), dtype=torch.uint8).to(dev)
+        pt, pptr = guarded(img.size)
+        rec._check(rec.lib.slc_bmp_unpack_device(rec.h, raw.data_ptr(), info, pptr, None))
+        rec.synchronize()
+        assert intact(pt, img.size)
+        assert np.array_equal(pt[PAD:PAD + img.size].cpu().numpy().reshape(img.shape), img)
+    rec.close()
