@@ -411,8 +411,22 @@ struct DynaOut {
 
 // The frame-to-frame recurrence U[f] = U[f-1] + deltaP[f] (CCalculation.cpp:656-658) is per
 // pixel: one thread walks all frames of its pixel, then FillCoordinate (:672-775) per frame.
+//
+// The kernel is instruction-issue bound (with every store removed it ran only 14 % faster), so the
+// frame loop is written for a short instruction stream: everything that depends on the pixel only
+// (C, D, the x / y factors, the output pointers) is computed once, pointers advance by a constant
+// stride per frame, deltaP comes from a shared-memory table addressed with one 32-bit add, the
+// optional planes are template parameters, and the rare f64 re-solve is out of line.
 constexpr int kLutN = 2 * 9 * 19 + 1;               // 3x3 sums of deltas in [-19, 19]: [-171, 171]
 
+__device__ __forceinline__ double lds_f64(uint32_t addr)
+{
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+    return v;
+}
+
+template <bool kDz, bool kParity>
 __global__ void __launch_bounds__(256)
 dyna_track_kernel(const __grid_constant__ KParams p, const unsigned short* __restrict__ sums, int n_frames,
                   const double* __restrict__ u0, const DynaOut o)
@@ -429,53 +443,79 @@ dyna_track_kernel(const __grid_constant__ KParams p, const unsigned short* __res
     split_row_col(p, (unsigned)idx, v, u);
     const RowConst rc = make_row_const(p, v);
     const float uf = (float)u;
+    // per-pixel constants of the f32 solve (triangulate_split evaluates the same expressions)
+    const float C = fmaf(p.cu1, uf, rc.rowC), nD = -fmaf(p.du1, uf, rc.rowD);
+    const float xr = fmaf(p.rx1, uf, p.rx0), yr = rc.ry;
+    const float B32 = p.B32, nA32 = -p.A32, mid = p.fov_mid32, half = p.fov_half32, guard = p.guard_band,
+                ng = p.num_guard, dg = p.den_guard;
+    // table address of sum value s:  lut0 + 8*s  (s is stored with a bias of 576)
+    const uint32_t lut0 = (uint32_t)__cvta_generic_to_shared(s_dp) - 8u * (uint32_t)(kDsBias9 - kLutN / 2);
 
     double U = u0[idx];
     // z of the frame before the first dynamic one: FillCoordinate(0) on U0 (CCalculation.cpp:189)
-    float z_prev;
-    {
-        int ok = 0;
-        float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (U != 0.0) r0 = resolve_f64_u(p, U, u, v, &ok);
-        z_prev = r0.z;
+    float z_prev = 0.f;
+    if (kDz && U != 0.0) {
+        int ok;
+        z_prev = resolve_f64_u(p, U, u, v, &ok).z;
     }
+    const long long npx = p.npx;
+    float4* px = o.xyzw + idx;
+    uint8_t* pm = o.mask + idx;
+    float* pz = kDz ? o.delta_z + idx : nullptr;
+    float* pdp = (kParity && o.delta_p) ? o.delta_p + idx : nullptr;
+    double* ppu = (kParity && o.proj_u) ? o.proj_u + idx : nullptr;
+    const unsigned short* ps = sums + idx;
+
     // the 3x3 sums of the next group of frames are in flight while this group is processed
     constexpr int kAhead = 4;
-    const unsigned short* sp = sums + idx;
-    unsigned short cur[kAhead], nxt[kAhead];
+    const int n_dyn = n_frames - 1;
+    unsigned cur[kAhead], nxt[kAhead];
 #pragma unroll
-    for (int k = 0; k < kAhead; k++)
-        cur[k] = (1 + k < n_frames) ? __ldcs(sp + (long long)k * p.npx) : (unsigned short)kDsBias9;
-    for (int f0 = 1; f0 < n_frames; f0 += kAhead) {
+    for (int k = 0; k < kAhead; k++) cur[k] = (k < n_dyn) ? (unsigned)__ldcs(ps + (long long)k * npx) : (unsigned)kDsBias9;
+    ps += (long long)kAhead * npx;
+    for (int g = 0; g < n_dyn; g += kAhead) {
 #pragma unroll
         for (int k = 0; k < kAhead; k++)
-            nxt[k] = (f0 + kAhead + k < n_frames) ? __ldcs(sp + (long long)(f0 + kAhead + k - 1) * p.npx)
-                                                  : (unsigned short)kDsBias9;
+            nxt[k] = (g + kAhead + k < n_dyn) ? (unsigned)__ldcs(ps + (long long)k * npx) : (unsigned)kDsBias9;
+        ps += (long long)kAhead * npx;
 #pragma unroll
         for (int k = 0; k < kAhead; k++) {
-            const int f = f0 + k;
-            if (f >= n_frames) break;
-            const double dP = s_dp[(int)cur[k] - (kDsBias9 - kLutN / 2)];
+            if (g + k >= n_dyn) break;
+            const double dP = lds_f64(lut0 + 8u * cur[k]);
             U = __dadd_rn(U, dP);                                // :656-658
             // FillCoordinate (:672-771): f32 solve on U split exactly into two floats
             const float a = (float)U;
             const float b = (float)(U - (double)a);
-            PixelResult r;
-            triangulate_split<false>(p, rc, a, b, U != 0.0, uf, r);
-            float4 outv = make_float4(r.x, r.y, r.z, r.w);
-            bool ok = r.valid;
-            if (r.need64) {
-                int ok64;                                        // address-taken only inside the rare branch
+            const float num = fmaf(B32, b, fmaf(B32, a, nA32));  // B*U - A
+            const float den = fmaf(nD, b, fmaf(nD, a, C));       // C - D*U
+            float rden;
+            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rden) : "f"(den));
+            float z = num * rden;
+            const float dist = fabsf(z - mid) - half;            // <= 0 <=> inside the FOV
+            const bool has_u = (U != 0.0);
+            const bool need64 = (!(fabsf(dist) >= guard) || (fabsf(num) < ng) || (fabsf(den) < dg)) && has_u;
+            bool ok = (dist <= 0.f) && has_u;
+            z = ok ? z : 0.f;
+            float4 outv = make_float4(z * xr, z * yr, z, a + b);
+            if (need64) {                                        // undecidable in f32: the reference's f64 solve
+                int ok64;
                 outv = resolve_f64_u(p, U, u, v, &ok64);
                 ok = ok64 != 0;
             }
-            const long long q = (long long)(f - 1) * p.npx + idx;
-            st_stream_f4(o.xyzw + q, outv);
-            o.mask[q] = ok ? (uint8_t)1 : (uint8_t)0;
-            if (o.delta_z) o.delta_z[q] = outv.z - z_prev;       // :772-775
-            if (o.delta_p) o.delta_p[q] = (float)dP;
-            if (o.proj_u) o.proj_u[q] = U;
-            z_prev = outv.z;
+            // write-once maps: streaming (evict-first) stores
+            st_stream_f4(px, outv);
+            asm volatile("st.global.cs.u8 [%0], %1;" :: "l"(pm), "r"(ok ? 1u : 0u) : "memory");
+            px += npx;
+            pm += npx;
+            if (kDz) {                                           // :772-775
+                asm volatile("st.global.cs.f32 [%0], %1;" :: "l"(pz), "f"(outv.z - z_prev) : "memory");
+                pz += npx;
+                z_prev = outv.z;
+            }
+            if (kParity) {
+                if (pdp) { *pdp = (float)dP; pdp += npx; }
+                if (ppu) { *ppu = U; ppu += npx; }
+            }
         }
 #pragma unroll
         for (int k = 0; k < kAhead; k++) cur[k] = nxt[k];
@@ -528,8 +568,16 @@ cudaError_t launch_dyna_track(KParams p, const unsigned short* d_sums, int n_fra
     p.row_magic = ((unsigned long long)p.npx * (unsigned long long)p.W < (1ull << 40))
                       ? ((1ull << 40) / (unsigned long long)p.W + 1ull) : 0ull;
     DynaOut o{reinterpret_cast<float4*>(d_xyzw), d_mask, d_delta_z, d_delta_p, d_proj_u, d_u_final};
-    const long long blocks = (p.npx + 255) / 256;
-    dyna_track_kernel<<<(unsigned)blocks, 256, 0, stream>>>(p, d_sums, n_frames, d_u0, o);
+    // one pixel per thread (2 and 4 per thread measured slower)
+    const unsigned blocks = (unsigned)((p.npx + 255) / 256);
+    const bool parity = d_delta_p || d_proj_u;
+    if (parity) {
+        if (d_delta_z) dyna_track_kernel<true, true><<<blocks, 256, 0, stream>>>(p, d_sums, n_frames, d_u0, o);
+        else dyna_track_kernel<false, true><<<blocks, 256, 0, stream>>>(p, d_sums, n_frames, d_u0, o);
+    } else {
+        if (d_delta_z) dyna_track_kernel<true, false><<<blocks, 256, 0, stream>>>(p, d_sums, n_frames, d_u0, o);
+        else dyna_track_kernel<false, false><<<blocks, 256, 0, stream>>>(p, d_sums, n_frames, d_u0, o);
+    }
     return cudaGetLastError();
 }
 
