@@ -268,7 +268,7 @@ def run_dynamic(args):
     """--path dynamic: the reference's CalculateOther mode -- a sequence of
     single stripe images tracked frame to frame (StripRegression + FillOtherDeltaProU +
     FillCoordinate), at the reference's own geometry (1280x1024, 100 frames, window 21).
-    A step is `--batch` sequences; every sequence is two kernel launches."""
+    A step is `--batch // 64` sequences; every sequence is three kernel launches."""
     import torch
     from structured_light_calculation_b200 import capi
     from oracle import sl_oracle as O   # U0 for the synthetic sequence + CPU baseline only
@@ -326,14 +326,24 @@ def run_dynamic(args):
     launches = int(D.sum_over_ranks(rec.launch_count() - launches0, dev))
     value = world * S * (F - 1) * args.steps / (ms * 1e-3)
 
-    # end to end: host frames in, host maps out (one blocking call per sequence)
+    # end to end: host frames in, host maps out (one blocking call per sequence), pinned host buffers
+    E = args.dyna_e2e_frames
+    h_frames = capi.PinnedArray((E, cfg.height, cfg.width), np.uint8)
+    h_frames.array[...] = frames[:E]
+    h_u0 = capi.PinnedArray((cfg.height, cfg.width), np.float64)
+    h_u0.array[...] = u0
+    h_xyzw = capi.PinnedArray((E - 1, cfg.height, cfg.width, 4), np.float32)
+    h_mask = capi.PinnedArray((E - 1, cfg.height, cfg.width), np.uint8)
+    h_dz = capi.PinnedArray((E - 1, cfg.height, cfg.width), np.float32)
+    rec.dyna_track_into(h_frames, E, h_u0, h_xyzw, h_mask, h_dz, window)
+    D.barrier()
     t0 = time.perf_counter()
-    e2e_reps = 3
-    out = None
+    e2e_reps = 5
     for _ in range(e2e_reps):
-        out = rec.dyna_track(frames[: args.dyna_e2e_frames], u0, window=window)
+        rec.dyna_track_into(h_frames, E, h_u0, h_xyzw, h_mask, h_dz, window)
     e2e_s = D.max_over_ranks(time.perf_counter() - t0, dev)
-    e2e_value = world * e2e_reps * (args.dyna_e2e_frames - 1) / e2e_s
+    e2e_value = world * e2e_reps * (E - 1) / e2e_s
+    out = {"xyzw": h_xyzw.array, "mask": h_mask.array}
 
     if rank == 0:
         ocfg = O.make_config(cfg.width, cfg.height, cfg.projector_width, cfg.gray_digits, cfg.phase_steps)
@@ -357,7 +367,8 @@ def run_dynamic(args):
                                    f"(reference CalculateOther), {S} sequence(s) per step"},
             "mpix_per_s": value * npx / 1e6,
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": args.dyna_e2e_frames * npx,
-                    "d2h_bytes_per_step": (args.dyna_e2e_frames - 1) * npx * 21},
+                    "d2h_bytes_per_step": (args.dyna_e2e_frames - 1) * npx * 21,
+                    "api": "capi.Reconstructor.dyna_track_into -> slc_dyna_track_host, pinned host buffers"},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "peak_kind": f"of {peak_kind}",
@@ -375,7 +386,7 @@ def run_dynamic(args):
 def run_pointcloud(args):
     """--path pointcloud: CCalculation::Result (SURVEY 8f rank 2) -- the text cloud of one
     1920x1200 frame (BASELINE configs[1] geometry) formatted on the device from the f64
-    ProjectorU plane.  A step is `--pc-frames` frames, three kernel launches each."""
+    ProjectorU plane.  A step is `--pc-frames` frames, two kernel launches each."""
     import torch
     from structured_light_calculation_b200 import capi
     from oracle import sl_oracle as O   # CPU baseline + byte check only
@@ -459,7 +470,7 @@ def run_pointcloud(args):
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "peak_kind": f"of {peak_kind}",
-                         "kernel": "pc_emit_kernel<0,false> + pc_scan_kernel + pc_emit_kernel<0,true> (per frame)",
+                         "kernel": "pc_emit_kernel<0,false> + pc_emit_kernel<0,true> (per frame)",
                          "algorithmic_bytes_per_step": alg,
                          "note": "formatting is FP64/integer-issue bound, not HBM bound; every number is formatted twice"},
             "cpu_baseline": {"value": 1.0 / cpu_s, "unit": "frames/s", "cores": 1, "kind": "port",

@@ -365,6 +365,12 @@ class Reconstructor:
                                                  out["delta_z"].ctypes.data, C.byref(par) if par else None))
         return out
 
+    def dyna_track_into(self, h_frames, n_frames: int, h_u0, h_xyzw, h_mask, h_delta_z=None, window: int = 21):
+        """CalculateOther with caller-owned (ideally pinned) host buffers: frames u8 [n][H][W], u0 f64 [H][W] in;
+        xyzw f32 [n-1][H][W][4], mask u8 [n-1][H][W], delta_z f32 [n-1][H][W] out."""
+        self._check(self.lib.slc_dyna_track_host(self.h, _ptr(h_frames), n_frames, window, _ptr(h_u0), _ptr(h_xyzw),
+                                                 _ptr(h_mask), _ptr(h_delta_z), None))
+
     def dyna_track_device(self, d_frames: int, n_frames: int, d_u0: int, d_xyzw: int, d_mask: int,
                           d_delta_z: int | None = None, window: int = 21, stream: int | None = None):
         self._check(self.lib.slc_dyna_track_device(self.h, d_frames, n_frames, window, d_u0, d_xyzw, d_mask,

@@ -894,7 +894,7 @@ int pointcloud_run(slc_context* ctx, int mode, int order, uint32_t flags, const 
     const unsigned long long* d_totals = nullptr;
     SLC_CUDA(ctx, slc::launch_pointcloud(ctx->kp, mode, order, flags, d_proj_u, d_xyzw, d_mask, d_out,
                                          (unsigned long long)capacity_bytes, ctx->d_pc_scratch, &d_totals, st));
-    ctx->launches += 3;
+    ctx->launches += 2;
     unsigned long long totals[2] = {0, 0};
     SLC_CUDA(ctx, cudaMemcpyAsync(totals, d_totals, sizeof(totals), cudaMemcpyDeviceToHost, st));
     SLC_CUDA(ctx, cudaStreamSynchronize(st));

@@ -5,8 +5,8 @@
 // [FOV_MIN_DISTANCE, FOV_MAX_DISTANCE] and writes "x y z\n" with ostream << double, i.e.
 // printf("%g") with precision 6.  Here that is a variable-length record emission:
 //   pass 1  pc_emit_kernel<MODE, false>  length of every record, summed per block
-//   scan    pc_scan_kernel               exclusive scan of the block sums (one block)
-//   pass 2  pc_emit_kernel<MODE, true>   records again, block-local scan, staged in shared memory
+//   pass 2  pc_emit_kernel<MODE, true>   each block sums the counts of the blocks before it, then the
+//                                        records again, block-local scan, staged in shared memory
 //                                        at the output's own 16-byte phase, written as uint4
 // MODE 0 records are text lines formatted from f64 x, y, z -- recomputed from the f64
 // ProjectorU plane in the reference's operation order (:686-687, :761-767), so the text is
@@ -127,7 +127,7 @@ struct PcArgs {
     const float4* xyzw;              // MODE 1
     const uint8_t* mask;             // MODE 1
     unsigned flags;
-    unsigned long long* block_sums;  // [2 * n_blocks + 2]: (bytes, records) per block; after the scan exclusive offsets, totals last
+    unsigned long long* block_sums;  // [2 * n_blocks + 2]: (bytes, records) per block, totals last
     unsigned char* out;
     unsigned long long capacity;     // bytes
 };
@@ -165,8 +165,37 @@ pc_emit_kernel(const __grid_constant__ KParams p, const PcArgs a)
     __shared__ int s_warp[kPcThreads / 32];
     const int t = threadIdx.x;
     const long long base = (long long)blockIdx.x * kPcChunk;
-    unsigned long long gofs = WRITE ? a.block_sums[2 * blockIdx.x] : 0ull;
     unsigned long long nbytes = 0ull, nrec = 0ull;
+    unsigned long long gofs = 0ull;
+    if (WRITE) {
+        // this block's offset = sum of the byte counts of all earlier blocks (a few thousand values
+        // sitting in L2; cheaper than a separate scan launch); the last block also publishes the totals
+        __shared__ unsigned long long s_part[3][kPcThreads / 32];
+        const int nb = (int)gridDim.x, me = (int)blockIdx.x;
+        const bool last = (me == nb - 1);
+        unsigned long long before = 0ull, all_b = 0ull, all_r = 0ull;
+        for (int i = t; i < (last ? nb : me); i += kPcThreads) {
+            const unsigned long long vb = a.block_sums[2 * i];
+            if (i < me) before += vb;
+            all_b += vb;
+            all_r += a.block_sums[2 * i + 1];
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            before += __shfl_down_sync(0xFFFFFFFFu, before, d);
+            all_b += __shfl_down_sync(0xFFFFFFFFu, all_b, d);
+            all_r += __shfl_down_sync(0xFFFFFFFFu, all_r, d);
+        }
+        if ((t & 31) == 0) { s_part[0][t >> 5] = before; s_part[1][t >> 5] = all_b; s_part[2][t >> 5] = all_r; }
+        __syncthreads();
+        unsigned long long tb = 0ull, ta = 0ull, tr = 0ull;
+        for (int w = 0; w < kPcThreads / 32; w++) { tb += s_part[0][w]; ta += s_part[1][w]; tr += s_part[2][w]; }
+        gofs = tb;
+        if (last && t == 0) {
+            a.block_sums[2 * nb] = ta;
+            a.block_sums[2 * nb + 1] = tr;
+        }
+    }
     const bool crlf = (a.flags & 1u) != 0u, exp3 = (a.flags & 2u) != 0u;
 
     for (int it = 0; it < kPcIters; it++) {
@@ -252,37 +281,6 @@ pc_emit_kernel(const __grid_constant__ KParams p, const PcArgs a)
     }
 }
 
-// exclusive scan of (bytes, records) pairs over the blocks; totals land at index n
-__global__ void __launch_bounds__(1024)
-pc_scan_kernel(unsigned long long* sums, int n)
-{
-    __shared__ unsigned long long s_b[1024], s_r[1024];
-    const int t = threadIdx.x;
-    const int per = (n + 1023) / 1024;
-    const int i0 = t * per, i1 = min(n, i0 + per);
-    unsigned long long b = 0, r = 0;
-    for (int i = i0; i < i1; i++) { b += sums[2 * i]; r += sums[2 * i + 1]; }
-    s_b[t] = b; s_r[t] = r;
-    __syncthreads();
-    if (t == 0) {
-        unsigned long long ab = 0, ar = 0;
-        for (int k = 0; k < 1024; k++) {
-            const unsigned long long vb = s_b[k], vr = s_r[k];
-            s_b[k] = ab; s_r[k] = ar;
-            ab += vb; ar += vr;
-        }
-        sums[2 * n] = ab;
-        sums[2 * n + 1] = ar;
-    }
-    __syncthreads();
-    b = s_b[t]; r = s_r[t];
-    for (int i = i0; i < i1; i++) {
-        const unsigned long long vb = sums[2 * i], vr = sums[2 * i + 1];
-        sums[2 * i] = b; sums[2 * i + 1] = r;
-        b += vb; r += vr;
-    }
-}
-
 __global__ void format_g6_kernel(const double* __restrict__ v, long long n, unsigned flags, char* __restrict__ text,
                                  uint8_t* __restrict__ len)
 {
@@ -321,7 +319,6 @@ cudaError_t launch_pointcloud(const KParams& p, int mode, int order, unsigned fl
     a.capacity = capacity;
     if (mode == 0) pc_emit_kernel<0, false><<<blocks, kPcThreads, 0, stream>>>(p, a);
     else pc_emit_kernel<1, false><<<blocks, kPcThreads, 0, stream>>>(p, a);
-    pc_scan_kernel<<<1, 1024, 0, stream>>>(a.block_sums, blocks);
     if (mode == 0) pc_emit_kernel<0, true><<<blocks, kPcThreads, 0, stream>>>(p, a);
     else pc_emit_kernel<1, true><<<blocks, kPcThreads, 0, stream>>>(p, a);
     *d_totals = a.block_sums + 2 * blocks;
