@@ -268,7 +268,7 @@ def run_dynamic(args):
     """--path dynamic: the reference's CalculateOther mode -- a sequence of
     single stripe images tracked frame to frame (StripRegression + FillOtherDeltaProU +
     FillCoordinate), at the reference's own geometry (1280x1024, 100 frames, window 21).
-    A step is `--batch // 64` sequences; every sequence is three kernel launches."""
+    A step is `--batch // 64` sequences; every sequence is two kernel launches."""
     import torch
     from structured_light_calculation_b200 import capi
     from oracle import sl_oracle as O   # U0 for the synthetic sequence + CPU baseline only
@@ -372,7 +372,7 @@ def run_dynamic(args):
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "peak_kind": f"of {peak_kind}",
-                         "kernel": "strip_regression21_kernel + delta_sum_kernel + dyna_track_kernel (per sequence)",
+                         "kernel": "strip_regression21_kernel + dyna_fused_kernel (per sequence)",
                          "algorithmic_bytes_per_step": alg},
             "cpu_baseline": {"value": 1.0 / cpu_s, "unit": "frames/s", "cores": 1, "kind": "port",
                              "sample": "3 dynamic frames, oracle port, 1 thread"},

@@ -673,7 +673,12 @@ int slc_dyna_track_device(slc_context* ctx, const uint8_t* d_frames, int32_t n_f
     }
     SLC_CUDA(ctx, slc::launch_strip_regression(d_frames, n_frames, ctx->kp.W, ctx->kp.H, window, strips, st));
     ctx->launches++;
-    if (n_frames > 1) {
+    if (n_frames > 1 && slc::dyna_fused_supported(ctx->kp.W, strips)) {
+        SLC_CUDA(ctx, slc::launch_dyna_fused(ctx->kp, strips, n_frames, d_u0, d_xyzw, d_mask, d_delta_z,
+                                             d_parity ? d_parity->delta_p : nullptr,
+                                             d_parity ? d_parity->proj_u : nullptr, nullptr, ctx->sm_count, st));
+        ctx->launches++;
+    } else if (n_frames > 1) {
         rc = ensure_scratch(ctx, &ctx->d_dsums, &ctx->dsums_bytes, 2 * npx * (size_t)(n_frames - 1));
         if (rc != SLC_OK) return rc;
         unsigned short* sums = static_cast<unsigned short*>(ctx->d_dsums);

@@ -1,16 +1,19 @@
 // slc_dyna.cu -- dynamic frames: the reference's CalculateOther path
-// (CCalculation.cpp:208-320) as two kernels.
+// (CCalculation.cpp:208-320).
 //
-//   strip_regression_kernel  StripRegression (CCalculation.cpp:789-892): 21-row box sum per
-//                            column, then the offset of the minimum / maximum of that sum
-//                            over the 20 columns [w-10, w+9] -> (stripB, stripW) per pixel.
-//                            Independent per frame: one launch covers every frame (grid.z).
-//   dyna_track_kernel        FillOtherDeltaProU (CCalculation.cpp:595-663) + FillCoordinate(i>0)
+//   strip_regression21_kernel  StripRegression (CCalculation.cpp:789-892) for the reference's window
+//                            of 21: 21-row box sum per column, then the offset of the minimum /
+//                            maximum of that sum over the 20 columns [w-10, w+9] -> (stripB, stripW)
+//                            per pixel.  Independent per frame: one launch covers every frame
+//                            (grid.z).  strip_regression_kernel: any other odd window / alignment.
+//   dyna_fused_kernel        FillOtherDeltaProU (CCalculation.cpp:595-663) + FillCoordinate(i>0)
 //                            (CCalculation.cpp:666-775): nearer-of-two delta, 3x3 cv::blur
 //                            (BORDER_REFLECT_101, double sum * (1./9) narrowed to f32),
 //                            U[f] = U[f-1] + deltaP, triangulation, deltaZ.  The frame-to-frame
-//                            recurrence is per pixel, so one thread walks all frames of its
-//                            pixel: a single launch for the whole sequence.
+//                            recurrence is per pixel, so a block walks all frames of its tile:
+//                            a single launch for the whole sequence, no intermediate plane.
+//   delta_sum_generic_kernel + dyna_track_kernel   the same in two kernels through a u16 plane of
+//                            3x3 sums, for widths that are not a multiple of 8.
 //
 // Everything up to U is integer / exactly-representable arithmetic (sums of <= 21 u8 values,
 // index differences, multiples of 2^-27 well inside a double), so strips, deltaP and U are
@@ -307,16 +310,10 @@ delta_sum_generic_kernel(const char2* __restrict__ strips, unsigned short* __res
     }
 }
 
-// fast path (W % 8 == 0): byte / 16-bit-lane SIMD throughout.
-//  producer: 4 pixels per item; per 32-bit word (2 pixels x (B, W)):  D = a - b + 64 per byte,
-//    |d| by VABSDIFF4, the nearer of (dB, dW) picked per 16-bit lane -> biased delta in [45, 83];
-//  consumer: 8 pixels per thread; vertical 3-sum = one 3-input add per word, horizontal 3-sum =
-//    two funnel shifts + one 3-input add per word (16-bit lanes, <= 747, no carries).
-constexpr int kDsW = 128, kDsH = 16;
-constexpr int kDsLead = 4;                          // smem index of image column x is x - x0 + 4
-constexpr int kDsCols = kDsW + 8;                   // x0-4 .. x0+131
-constexpr int kDsQuads = kDsCols / 4;               // 34
-constexpr int kDsRows = kDsH + 2;
+// byte / 16-bit-lane SIMD pieces of the fused kernel below (W % 8 == 0):
+//  per 32-bit word (2 pixels x (B, W)):  D = a - b + 64 per byte, |d| by VABSDIFF4, the nearer of
+//  (dB, dW) picked per 16-bit lane -> biased delta in [45, 83]; the 3x3 sum then works on those
+//  lanes (<= 747, no carries).
 
 __device__ __forceinline__ uint32_t nearer_delta_lanes(uint32_t a, uint32_t b)
 {
@@ -329,70 +326,6 @@ __device__ __forceinline__ uint32_t nearer_delta_lanes(uint32_t a, uint32_t b)
     asm("prmt.b32 %0, %1, %2, 0x4a48;" : "=r"(sel) : "r"(Z), "r"(0u));   // 0x00FF per lane whose bit 7 is set
     const uint32_t DB = D & 0x00FF00FFu, DW = __byte_perm(D, 0u, 0x4341);
     return DB ^ ((DB ^ DW) & sel);                       // (abs(dB) < abs(dW)) ? dB : dW   (CCalculation.cpp:603-617)
-}
-
-__global__ void __launch_bounds__(256)
-delta_sum_kernel(const char2* __restrict__ strips, unsigned short* __restrict__ sums, int W, int H)
-{
-    __shared__ __align__(16) unsigned short s_d[kDsRows][kDsCols];
-    const long long npx = (long long)W * H;
-    const char2* s0 = strips + (long long)blockIdx.z * npx;
-    const char2* s1 = s0 + npx;
-    const int x0 = blockIdx.x * kDsW, y0 = blockIdx.y * kDsH;
-    const int t = threadIdx.x;
-
-    // producer: four-pixel items over the tile + halo (every cell is written: the consumer adds whole
-    // 32-bit words, so even lanes it does not use must hold values that cannot carry)
-    for (int e = t; e < kDsRows * kDsQuads; e += 256) {
-        const int ry = e / kDsQuads, qx = e - ry * kDsQuads;
-        const int y = y0 + ry - 1, x = x0 - kDsLead + 4 * qx;
-        uint2 res = make_uint2(0x00400040u, 0x00400040u);
-        if (y >= 0 && y < H && x >= 0 && x < W) {
-            const uint2 a = __ldg(reinterpret_cast<const uint2*>(s0 + (long long)y * W + x));
-            const uint2 b = __ldg(reinterpret_cast<const uint2*>(s1 + (long long)y * W + x));
-            res.x = nearer_delta_lanes(a.x, b.x);
-            res.y = nearer_delta_lanes(a.y, b.y);
-        }
-        *reinterpret_cast<uint2*>(&s_d[ry][4 * qx]) = res;
-    }
-    __syncthreads();
-    // cv::blur's default border (BORDER_REFLECT_101): column -1 = column 1, column W = column W-2,
-    // then the same for rows (so the corners mirror on both axes)
-    const bool left = (x0 == 0), right = (W - x0 <= kDsW);
-    const bool top = (y0 == 0), bottom = (H - y0 <= kDsH);
-    if (left || right || top || bottom) {
-        if (t < kDsRows) {
-            if (left) s_d[t][kDsLead - 1] = s_d[t][kDsLead + 1];
-            if (right) s_d[t][W - x0 + kDsLead] = s_d[t][W - 2 - x0 + kDsLead];
-        }
-        __syncthreads();
-        if (t < kDsCols) {
-            if (top) s_d[0][t] = s_d[2][t];
-            if (bottom) s_d[H - y0 + 1][t] = s_d[H - y0 - 1][t];
-        }
-        __syncthreads();
-    }
-    const int k = t & 15, ry = t >> 4;
-    const int y = y0 + ry, c = x0 + 8 * k;
-    if (y >= H || c >= W) return;
-    uint32_t V[8];
-#pragma unroll
-    for (int rr = 0; rr < 3; rr++) {
-        const uint4 lo = *reinterpret_cast<const uint4*>(&s_d[ry + rr][8 * k]);        // columns c-4 .. c+3
-        const uint4 hi = *reinterpret_cast<const uint4*>(&s_d[ry + rr][8 * k + 8]);    // columns c+4 .. c+11
-        const uint32_t w[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
-#pragma unroll
-        for (int i = 1; i < 7; i++) V[i] = (rr == 0) ? w[i] : V[i] + w[i];
-    }
-    uint32_t S[4];
-#pragma unroll
-    for (int m = 0; m < 4; m++) {
-        const uint32_t L = __funnelshift_l(V[m + 1], V[m + 2], 16);     // columns (c+2m-1, c+2m)
-        const uint32_t R = __funnelshift_l(V[m + 2], V[m + 3], 16);     // columns (c+2m+1, c+2m+2)
-        S[m] = L + V[m + 2] + R;
-    }
-    unsigned short* dst = sums + (long long)blockIdx.z * npx + (long long)y * W + c;
-    *reinterpret_cast<uint4*>(dst) = make_uint4(S[0], S[1], S[2], S[3]);
 }
 
 // z_exact + FOV test for a projector column held in f64
@@ -528,6 +461,196 @@ dyna_track_kernel(const __grid_constant__ KParams p, const unsigned short* __res
     if (o.u_final) o.u_final[idx] = U;
 }
 
+
+// ---- FillOtherDeltaProU + FillCoordinate fused (W % 8 == 0) --------------------------------
+// One block owns a 128-column x (2*kPxT)-row tile and walks every frame of the sequence, so the
+// 3x3 sums never leave the SM and the strips are read once per frame:
+//   P  each thread keeps the strips of "its" four-pixel items of the tile + 1-pixel halo in
+//      registers, has the next frame's in flight (one 8-byte load per item, issued a frame ahead)
+//      and writes the nearer-of-two delta (+64, 16-bit lanes) to shared memory.  cv::blur's
+//      BORDER_REFLECT_101 is folded into the item's source address (column -1 <- 1, W <- W-2, rows
+//      alike).  Every cell of the region is written (dead ones once, with the bias): S adds whole
+//      32-bit words, so even lanes it does not use must not be able to carry;
+//   S  3x3 sums on 16-bit lanes: a thread owns 8 adjacent pixels; vertical = 3-input adds,
+//      horizontal = two funnel shifts + one 3-input add per pixel pair;
+//   T  the lean per-pixel loop of dyna_track_kernel; a thread owns kPxT pixels of one column, two
+//      rows apart, so every store instruction of a warp covers 32 adjacent pixels.
+// The tile height is picked on the host so that the grid fills whole waves of resident blocks
+// (every block runs for the whole sequence, so a partly filled last wave costs a full one).
+constexpr int kTfW = 128;
+constexpr int kTfCols = kTfW + 8;                   // image columns x0-4 .. x0+131; smem index = x - x0 + 4
+constexpr int kTfQuads = kTfCols / 4;               // 34
+
+template <int kPxT, bool kDz, bool kParity>
+__global__ void __launch_bounds__(256)
+dyna_fused_kernel(const __grid_constant__ KParams p, const char2* __restrict__ strips, int n_frames,
+                  const double* __restrict__ u0, const DynaOut o)
+{
+    constexpr int kTH = 2 * kPxT;                   // tile rows
+    constexpr int kRows = kTH + 2;                  // + halo rows y0-1, y0+kTH
+    constexpr int kItems = (kRows * kTfQuads + 255) / 256;
+    __shared__ __align__(16) unsigned short s_d[kRows][kTfCols];
+    __shared__ __align__(16) unsigned short s_sum[kTH][kTfW];
+    __shared__ double s_dp[kLutN];
+    const int W = p.W, H = p.H;
+    const long long npx = p.npx;
+    const int t = threadIdx.x;
+    const int x0 = blockIdx.x * kTfW, y0 = blockIdx.y * kTH;
+
+    for (int i = t; i < kLutN; i += 256)
+        s_dp[i] = (double)(float)__dmul_rn((double)(i - kLutN / 2), 1.0 / 9.0);
+
+    // ---- P items
+    int src[kItems];              // pixel offset of the item's source quad inside a frame; -1 = dead
+    int mode[kItems];             // 0 normal, 1 left mirror, 2 right mirror
+    uint32_t dsts[kItems];        // shared-memory address of the item's four cells
+    uint2 prev[kItems], cur[kItems];
+#pragma unroll
+    for (int it = 0; it < kItems; it++) {
+        const int e = t + 256 * it;
+        const bool cell = (e < kRows * kTfQuads);
+        const int ry = cell ? e / kTfQuads : 0, qx = cell ? e - ry * kTfQuads : 0;
+        int y = y0 + ry - 1, x = x0 - 4 + 4 * qx;
+        bool live = cell;
+        mode[it] = 0;
+        if (y == -1) y = 1; else if (y == H) y = H - 2; else if (y > H) live = false;
+        if (x == -4) { x = 0; mode[it] = 1; } else if (x == W) { x = W - 4; mode[it] = 2; } else if (x > W) live = false;
+        src[it] = live ? y * W + x : -1;
+        dsts[it] = (uint32_t)__cvta_generic_to_shared(&s_d[ry][4 * qx]);
+        prev[it] = cur[it] = make_uint2(0u, 0u);
+        if (live) {
+            prev[it] = __ldg(reinterpret_cast<const uint2*>(strips + src[it]));
+            if (n_frames > 1) cur[it] = __ldg(reinterpret_cast<const uint2*>(strips + npx + src[it]));
+        } else if (cell) {
+            *reinterpret_cast<uint2*>(&s_d[ry][4 * qx]) = make_uint2(0x00400040u, 0x00400040u);
+        }
+    }
+
+    // ---- T pixels: column t & 127, rows (t >> 7) + 2j
+    const int col = t & 127, row0 = t >> 7;
+    const int u = x0 + col;
+    const float uf = (float)u;
+    const float xr = fmaf(p.rx1, uf, p.rx0);
+    const float B32 = p.B32, nA32 = -p.A32, mid = p.fov_mid32, half = p.fov_half32, guard = p.guard_band,
+                ng = p.num_guard, dg = p.den_guard;
+    double U[kPxT];
+    float zprev[kPxT], Cc[kPxT], nD[kPxT], yr[kPxT];
+    bool in[kPxT];
+#pragma unroll
+    for (int j = 0; j < kPxT; j++) {
+        const int v = y0 + row0 + 2 * j;
+        in[j] = (v < H) && (u < W);
+        const RowConst rc = make_row_const(p, v);
+        Cc[j] = fmaf(p.cu1, uf, rc.rowC);
+        nD[j] = -fmaf(p.du1, uf, rc.rowD);
+        yr[j] = rc.ry;
+        U[j] = in[j] ? u0[(long long)v * W + u] : 0.0;
+        // z of the frame before the first dynamic one: FillCoordinate(0) on U0 (CCalculation.cpp:189)
+        zprev[j] = 0.f;
+        if (kDz && in[j] && U[j] != 0.0) {
+            int ok;
+            zprev[j] = resolve_f64_u(p, U[j], u, v, &ok).z;
+        }
+    }
+    const long long pbase = (long long)(y0 + row0) * W + u;          // pixel j sits 2*j*W further
+    float4* px = o.xyzw + pbase;
+    uint8_t* pm = o.mask + pbase;
+    float* pz = kDz ? o.delta_z + pbase : nullptr;
+    float* pdp = (kParity && o.delta_p) ? o.delta_p + pbase : nullptr;
+    double* ppu = (kParity && o.proj_u) ? o.proj_u + pbase : nullptr;
+    const uint32_t lut0 = (uint32_t)__cvta_generic_to_shared(s_dp) - 8u * (uint32_t)(kDsBias9 - kLutN / 2);
+    const uint32_t sum0 = (uint32_t)__cvta_generic_to_shared(&s_sum[row0][col]);
+    const int sk = t & 15, sry = t >> 4;   // S role: 8 pixels from column 8*sk of tile row sry
+    const char2* sp = strips + 2 * npx;    // frame f + 1 for the loop below
+
+    for (int f = 1; f < n_frames; f++) {
+        // ---- P
+#pragma unroll
+        for (int it = 0; it < kItems; it++) {
+            if (src[it] >= 0) {
+                const uint32_t rx = nearer_delta_lanes(prev[it].x, cur[it].x);
+                const uint32_t ry = nearer_delta_lanes(prev[it].y, cur[it].y);
+                const uint32_t w0 = (mode[it] == 2) ? ry : rx, w1 = (mode[it] == 1) ? rx : ry;
+                asm volatile("st.shared.v2.u32 [%0], {%1, %2};" :: "r"(dsts[it]), "r"(w0), "r"(w1) : "memory");
+                prev[it] = cur[it];
+                if (f + 1 < n_frames) cur[it] = __ldg(reinterpret_cast<const uint2*>(sp + src[it]));
+            }
+        }
+        sp += npx;
+        __syncthreads();
+        // ---- S
+        if (sry < kTH) {
+            uint32_t V[8];
+#pragma unroll
+            for (int rr = 0; rr < 3; rr++) {
+                const uint4 lo = *reinterpret_cast<const uint4*>(&s_d[sry + rr][8 * sk]);        // columns c-4 .. c+3
+                const uint4 hi = *reinterpret_cast<const uint4*>(&s_d[sry + rr][8 * sk + 8]);    // columns c+4 .. c+11
+                const uint32_t w[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+#pragma unroll
+                for (int i = 1; i < 7; i++) V[i] = (rr == 0) ? w[i] : V[i] + w[i];
+            }
+            uint32_t S[4];
+#pragma unroll
+            for (int m = 0; m < 4; m++) {
+                const uint32_t L = __funnelshift_l(V[m + 1], V[m + 2], 16);     // columns (c+2m-1, c+2m)
+                const uint32_t R = __funnelshift_l(V[m + 2], V[m + 3], 16);     // columns (c+2m+1, c+2m+2)
+                S[m] = L + V[m + 2] + R;
+            }
+            *reinterpret_cast<uint4*>(&s_sum[sry][8 * sk]) = make_uint4(S[0], S[1], S[2], S[3]);
+        }
+        __syncthreads();
+        // ---- T
+#pragma unroll
+        for (int j = 0; j < kPxT; j++) {
+            if (!in[j]) continue;
+            uint32_t sb;                                                  // 576 + 3x3 sum
+            asm volatile("ld.shared.u16 %0, [%1];" : "=r"(sb) : "r"(sum0 + (uint32_t)(2 * j * kTfW * 2)));
+            const double dP = lds_f64(lut0 + 8u * sb);
+            U[j] = __dadd_rn(U[j], dP);                                   // :656-658
+            const float a = (float)U[j];
+            const float b = (float)(U[j] - (double)a);
+            const float num = fmaf(B32, b, fmaf(B32, a, nA32));           // B*U - A
+            const float den = fmaf(nD[j], b, fmaf(nD[j], a, Cc[j]));      // C - D*U
+            float rden;
+            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rden) : "f"(den));
+            float z = num * rden;
+            const float dist = fabsf(z - mid) - half;                     // <= 0 <=> inside the FOV
+            const bool has_u = (U[j] != 0.0);
+            const bool need64 = (!(fabsf(dist) >= guard) || (fabsf(num) < ng) || (fabsf(den) < dg)) && has_u;
+            bool ok = (dist <= 0.f) && has_u;
+            z = ok ? z : 0.f;
+            float4 outv = make_float4(z * xr, z * yr[j], z, a + b);
+            if (need64) {                                                 // undecidable in f32: the reference's f64 solve
+                int ok64;
+                outv = resolve_f64_u(p, U[j], u, y0 + row0 + 2 * j, &ok64);
+                ok = ok64 != 0;
+            }
+            const long long oj = (long long)(2 * j) * W;
+            st_stream_f4(px + oj, outv);
+            asm volatile("st.global.cs.u8 [%0], %1;" :: "l"(pm + oj), "r"(ok ? 1u : 0u) : "memory");
+            if (kDz) {                                                    // :772-775
+                asm volatile("st.global.cs.f32 [%0], %1;" :: "l"(pz + oj), "f"(outv.z - zprev[j]) : "memory");
+                zprev[j] = outv.z;
+            }
+            if (kParity) {
+                if (pdp) pdp[oj] = (float)dP;
+                if (ppu) ppu[oj] = U[j];
+            }
+        }
+        px += npx;
+        pm += npx;
+        if (kDz) pz += npx;
+        if (kParity) { if (pdp) pdp += npx; if (ppu) ppu += npx; }
+        // the next P writes s_d only after every thread has passed the second barrier (S is done),
+        // the next S writes s_sum only after the next first barrier (T is done)
+    }
+    if (o.u_final) {
+#pragma unroll
+        for (int j = 0; j < kPxT; j++)
+            if (in[j]) o.u_final[(long long)(y0 + row0 + 2 * j) * W + u] = U[j];
+    }
+}
+
 }  // namespace
 
 cudaError_t launch_strip_regression(const uint8_t* d_frames, int n_frames, int W, int H, int window,
@@ -554,15 +677,8 @@ cudaError_t launch_delta_sum(const signed char* d_strips, int n_frames, int W, i
                              cudaStream_t stream)
 {
     if (n_frames < 2) return cudaSuccess;
-    const bool aligned = (W % 8 == 0) && ((reinterpret_cast<uintptr_t>(d_strips) & 7) == 0) &&
-                         ((reinterpret_cast<uintptr_t>(d_sums) & 15) == 0);
-    if (aligned) {
-        dim3 grid((W + kDsW - 1) / kDsW, (H + kDsH - 1) / kDsH, n_frames - 1);
-        delta_sum_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const char2*>(d_strips), d_sums, W, H);
-    } else {
-        dim3 grid((W + kDgW - 1) / kDgW, (H + kDgH - 1) / kDgH, n_frames - 1);
-        delta_sum_generic_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const char2*>(d_strips), d_sums, W, H);
-    }
+    dim3 grid((W + kDgW - 1) / kDgW, (H + kDgH - 1) / kDgH, n_frames - 1);
+    delta_sum_generic_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const char2*>(d_strips), d_sums, W, H);
     return cudaGetLastError();
 }
 
@@ -584,6 +700,57 @@ cudaError_t launch_dyna_track(KParams p, const unsigned short* d_sums, int n_fra
         else dyna_track_kernel<false, false><<<blocks, 256, 0, stream>>>(p, d_sums, n_frames, d_u0, o);
     }
     return cudaGetLastError();
+}
+
+bool dyna_fused_supported(int W, const signed char* d_strips)
+{
+    return (W % 8 == 0) && ((reinterpret_cast<uintptr_t>(d_strips) & 7) == 0);
+}
+
+namespace {
+template <int kPxT>
+cudaError_t launch_fused_rows(const KParams& p, const char2* st, int n_frames, const double* d_u0, const DynaOut& o,
+                              bool dz, bool parity, cudaStream_t stream)
+{
+    dim3 grid((p.W + kTfW - 1) / kTfW, (p.H + 2 * kPxT - 1) / (2 * kPxT), 1);
+    if (parity) {
+        if (dz) dyna_fused_kernel<kPxT, true, true><<<grid, 256, 0, stream>>>(p, st, n_frames, d_u0, o);
+        else dyna_fused_kernel<kPxT, false, true><<<grid, 256, 0, stream>>>(p, st, n_frames, d_u0, o);
+    } else {
+        if (dz) dyna_fused_kernel<kPxT, true, false><<<grid, 256, 0, stream>>>(p, st, n_frames, d_u0, o);
+        else dyna_fused_kernel<kPxT, false, false><<<grid, 256, 0, stream>>>(p, st, n_frames, d_u0, o);
+    }
+    return cudaGetLastError();
+}
+
+// how full the last wave of resident blocks is for a grid of long-running blocks
+template <int kPxT>
+double fused_wave_fill(const KParams& p, int sm_count)
+{
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dyna_fused_kernel<kPxT, true, false>, 256, 0) != cudaSuccess ||
+        per_sm < 1)
+        return 0.0;
+    const long long blocks = (long long)((p.W + kTfW - 1) / kTfW) * ((p.H + 2 * kPxT - 1) / (2 * kPxT));
+    const long long slots = (long long)per_sm * sm_count;
+    const long long waves = (blocks + slots - 1) / slots;
+    return (double)blocks / (double)(waves * slots);
+}
+}  // namespace
+
+cudaError_t launch_dyna_fused(KParams p, const signed char* d_strips, int n_frames, const double* d_u0,
+                              float* d_xyzw, uint8_t* d_mask, float* d_delta_z, float* d_delta_p,
+                              double* d_proj_u, double* d_u_final, int sm_count, cudaStream_t stream)
+{
+    DynaOut o{reinterpret_cast<float4*>(d_xyzw), d_mask, d_delta_z, d_delta_p, d_proj_u, d_u_final};
+    const char2* st = reinterpret_cast<const char2*>(d_strips);
+    const bool dz = d_delta_z != nullptr, parity = d_delta_p || d_proj_u;
+    // 8-row tiles (4 pixels per thread) unless 4-row tiles fill the waves of resident blocks clearly
+    // better.  Measured at 1280x1024 x 100 frames: 8 rows 570 us, 4 rows 660 us, 16 rows 1090 us
+    // (2 blocks / SM at 118 registers and a last wave that is 16 % full).
+    const bool small = fused_wave_fill<4>(p, sm_count) < 0.8 && fused_wave_fill<2>(p, sm_count) > fused_wave_fill<4>(p, sm_count) + 0.1;
+    return small ? launch_fused_rows<2>(p, st, n_frames, d_u0, o, dz, parity, stream)
+                 : launch_fused_rows<4>(p, st, n_frames, d_u0, o, dz, parity, stream);
 }
 
 }  // namespace slc

@@ -38,6 +38,12 @@ cudaError_t launch_dyna_track(KParams p, const unsigned short* d_sums, int n_fra
                               float* d_xyzw, uint8_t* d_mask, float* d_delta_z, float* d_delta_p,
                               double* d_proj_u, double* d_u_final, cudaStream_t stream);
 
+// W % 8 == 0: delta + 3x3 sum + track in one kernel straight from the strips (no sums plane)
+bool dyna_fused_supported(int W, const signed char* d_strips);
+cudaError_t launch_dyna_fused(KParams p, const signed char* d_strips, int n_frames, const double* d_u0,
+                              float* d_xyzw, uint8_t* d_mask, float* d_delta_z, float* d_delta_p,
+                              double* d_proj_u, double* d_u_final, int sm_count, cudaStream_t stream);
+
 // point-cloud output (slc_pointcloud.cu)
 size_t pointcloud_scratch_bytes(long long npx);
 cudaError_t launch_pointcloud(const KParams& p, int mode, int order, unsigned flags, const double* d_proj_u,
