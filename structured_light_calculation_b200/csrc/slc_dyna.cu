@@ -481,8 +481,9 @@ constexpr int kTfW = 128;
 constexpr int kTfCols = kTfW + 8;                   // image columns x0-4 .. x0+131; smem index = x - x0 + 4
 constexpr int kTfQuads = kTfCols / 4;               // 34
 
+// (a single barrier per frame with both staging arrays double buffered was measured 16 % slower)
 template <int kPxT, bool kDz, bool kParity>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, kPxT <= 4 ? 3 : 2)
 dyna_fused_kernel(const __grid_constant__ KParams p, const char2* __restrict__ strips, int n_frames,
                   const double* __restrict__ u0, const DynaOut o)
 {
@@ -600,12 +601,18 @@ dyna_fused_kernel(const __grid_constant__ KParams p, const char2* __restrict__ s
         }
         __syncthreads();
         // ---- T
+        // the shared-memory reads of all kPxT pixels first: independent chains for the scheduler
+        uint32_t sb[kPxT];                                                // 576 + 3x3 sum
+        double dPs[kPxT];
+#pragma unroll
+        for (int j = 0; j < kPxT; j++)
+            asm volatile("ld.shared.u16 %0, [%1];" : "=r"(sb[j]) : "r"(sum0 + (uint32_t)(2 * j * kTfW * 2)));
+#pragma unroll
+        for (int j = 0; j < kPxT; j++) dPs[j] = lds_f64(lut0 + 8u * sb[j]);
 #pragma unroll
         for (int j = 0; j < kPxT; j++) {
             if (!in[j]) continue;
-            uint32_t sb;                                                  // 576 + 3x3 sum
-            asm volatile("ld.shared.u16 %0, [%1];" : "=r"(sb) : "r"(sum0 + (uint32_t)(2 * j * kTfW * 2)));
-            const double dP = lds_f64(lut0 + 8u * sb);
+            const double dP = dPs[j];
             U[j] = __dadd_rn(U[j], dP);                                   // :656-658
             const float a = (float)U[j];
             const float b = (float)(U[j] - (double)a);
