@@ -8,6 +8,10 @@
 #include "../../include/slcalc_b200.h"
 #include "slc_kernels.h"
 
+#include <algorithm>
+#include <condition_variable>
+#include <mutex>
+#include <thread>
 #include <climits>
 #include <cmath>
 #include <cstdarg>
@@ -38,6 +42,8 @@ struct Slot {
 
 }  // namespace
 
+constexpr int kBmpSlots = 8;   // staging slots of slc_load_bmp_planes
+
 struct slc_context {
     slc_config cfg{};
     int gp = 0, T = 0;
@@ -56,9 +62,9 @@ struct slc_context {
     void* d_pc_scratch = nullptr;  size_t pc_scratch_bytes = 0;  // point cloud: block sums
     void* d_pc_in = nullptr;       size_t pc_in_bytes = 0;       // point cloud: staging for the host entry points
     void* d_pc_out = nullptr;      size_t pc_out_bytes = 0;
-    void* d_bmp[2] = {nullptr, nullptr}; size_t bmp_bytes[2] = {0, 0};   // ingest: raw file staging (device)
-    void* h_bmp[2] = {nullptr, nullptr}; size_t h_bmp_bytes[2] = {0, 0}; // ingest: raw file staging (pinned)
-    cudaEvent_t bmp_done[2] = {nullptr, nullptr};
+    void* d_bmp[kBmpSlots] = {};   size_t bmp_bytes[kBmpSlots] = {};     // ingest: raw file staging (device)
+    void* h_bmp[kBmpSlots] = {};   size_t h_bmp_bytes[kBmpSlots] = {};   // ingest: raw file staging (pinned)
+    cudaEvent_t bmp_done[kBmpSlots] = {};
     void* d_dyna = nullptr;        size_t dyna_bytes = 0;        // dynamic frames: staging for the host entry point
     long long launches = 0;
     std::string err;
@@ -323,7 +329,7 @@ void slc_destroy(slc_context* ctx)
     cudaFree(ctx->d_scratch_in); cudaFree(ctx->d_scratch_out); cudaFree(ctx->d_scratch_aux);
     cudaFree(ctx->d_strips); cudaFree(ctx->d_dsums); cudaFree(ctx->d_dyna);
     cudaFree(ctx->d_pc_scratch); cudaFree(ctx->d_pc_in); cudaFree(ctx->d_pc_out);
-    for (int k = 0; k < 2; k++) {
+    for (int k = 0; k < kBmpSlots; k++) {
         cudaFree(ctx->d_bmp[k]);
         if (ctx->h_bmp[k]) cudaFreeHost(ctx->h_bmp[k]);
         if (ctx->bmp_done[k]) cudaEventDestroy(ctx->bmp_done[k]);
@@ -843,41 +849,104 @@ int slc_load_bmp_planes(slc_context* ctx, const char* const* paths, int32_t n_fi
 {
     if (!ctx) return SLC_ERR_INVALID_ARG;
     if (!paths || !d_stack || n_files < 0) return fail(ctx, SLC_ERR_INVALID_ARG, "NULL argument or n_files < 0");
+    if (n_files == 0) return SLC_OK;
     SLC_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
     const size_t npx = (size_t)ctx->kp.npx;
-    for (int k = 0; k < 2; k++)
-        if (!ctx->bmp_done[k]) SLC_CUDA(ctx, cudaEventCreateWithFlags(&ctx->bmp_done[k], cudaEventDisableTiming));
-    int used[2] = {0, 0};
+    // file sizes first: one staging size for every slot
+    std::vector<size_t> sizes((size_t)n_files);
+    size_t max_size = 0;
     for (int i = 0; i < n_files; i++) {
-        const int k = i & 1;
         if (!paths[i]) return fail(ctx, SLC_ERR_INVALID_ARG, "NULL path for file %d", i);
         FILE* f = std::fopen(paths[i], "rb");
         if (!f) return fail(ctx, SLC_ERR_INVALID_ARG, "imread error: %s", paths[i]);     /* CSensorV.cpp:122-129 */
         std::fseek(f, 0, SEEK_END);
         const long sz = std::ftell(f);
-        std::fseek(f, 0, SEEK_SET);
-        if (sz < 54) { std::fclose(f); return fail(ctx, SLC_ERR_INVALID_ARG, "imread error: %s", paths[i]); }
-        // the staging pair is reused every other file: wait until its previous upload + unpack are done
-        if (used[k]) SLC_CUDA(ctx, cudaEventSynchronize(ctx->bmp_done[k]));
-        int rc = ensure_pinned(ctx, &ctx->h_bmp[k], &ctx->h_bmp_bytes[k], (size_t)sz);
-        if (rc == SLC_OK) rc = ensure_scratch(ctx, &ctx->d_bmp[k], &ctx->bmp_bytes[k], (size_t)sz + npx);
-        if (rc != SLC_OK) { std::fclose(f); return rc; }
-        const size_t got = std::fread(ctx->h_bmp[k], 1, (size_t)sz, f);
         std::fclose(f);
-        slc_bmp_info info;
-        if (got != (size_t)sz || slc_bmp_parse(ctx->h_bmp[k], sz, &info) != SLC_OK)
-            return fail(ctx, SLC_ERR_INVALID_ARG, "imread error (not an uncompressed 8/24/32-bit BMP): %s", paths[i]);
-        if (info.width != ctx->kp.W || info.height != ctx->kp.H)
-            return fail(ctx, SLC_ERR_INVALID_ARG, "%s is %dx%d, the context is %dx%d", paths[i], info.width, info.height,
-                        ctx->kp.W, ctx->kp.H);
-        const size_t raw = (size_t)info.row_stride * info.height;
-        SLC_CUDA(ctx, cudaMemcpyAsync(ctx->d_bmp[k], static_cast<uint8_t*>(ctx->h_bmp[k]) + info.pixel_offset, raw,
-                                      cudaMemcpyHostToDevice, ctx->stream));
-        rc = bmp_unpack(ctx, static_cast<const uint8_t*>(ctx->d_bmp[k]), &info, d_stack + (size_t)i * npx, ctx->stream);
-        if (rc != SLC_OK) return rc;
-        SLC_CUDA(ctx, cudaEventRecord(ctx->bmp_done[k], ctx->stream));
-        used[k] = 1;
+        if (sz < 54) return fail(ctx, SLC_ERR_INVALID_ARG, "imread error: %s", paths[i]);
+        sizes[(size_t)i] = (size_t)sz;
+        if ((size_t)sz > max_size) max_size = (size_t)sz;
     }
+    // kBmpSlots staging slots (pinned host + device + event); file i uses slot i % kBmpSlots.  Reader
+    // threads fill slots ahead of the uploads; this thread issues upload + unpack in file order.
+    const int K = kBmpSlots;
+    for (int k = 0; k < K; k++) {
+        int rc = ensure_pinned(ctx, &ctx->h_bmp[k], &ctx->h_bmp_bytes[k], max_size);
+        if (rc == SLC_OK) rc = ensure_scratch(ctx, &ctx->d_bmp[k], &ctx->bmp_bytes[k], max_size + npx);
+        if (rc != SLC_OK) return rc;
+        if (!ctx->bmp_done[k]) SLC_CUDA(ctx, cudaEventCreateWithFlags(&ctx->bmp_done[k], cudaEventDisableTiming));
+    }
+    const int R = std::max(1, std::min({4, n_files, (int)std::thread::hardware_concurrency()}));
+    std::mutex mu;
+    std::condition_variable cv;
+    std::vector<int> state((size_t)n_files, 0);      // 0 pending, 1 read ok, -1 read failed
+    std::vector<int> slot_free_for((size_t)K);       // index of the file allowed to use slot k next
+    for (int k = 0; k < K; k++) slot_free_for[(size_t)k] = k;
+    bool abort_all = false;
+    auto reader = [&](int r) {
+        for (int i = r; i < n_files; i += R) {
+            const int k = i % K;
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&] { return abort_all || slot_free_for[(size_t)k] == i; });
+                if (abort_all) return;
+            }
+            bool ok = false;
+            if (FILE* f = std::fopen(paths[i], "rb")) {
+                ok = std::fread(ctx->h_bmp[k], 1, sizes[(size_t)i], f) == sizes[(size_t)i];
+                std::fclose(f);
+            }
+            {
+                std::lock_guard<std::mutex> lk(mu);
+                state[(size_t)i] = ok ? 1 : -1;
+            }
+            cv.notify_all();
+        }
+    };
+    std::vector<std::thread> threads;
+    for (int r = 0; r < R; r++) threads.emplace_back(reader, r);
+    auto stop = [&] {
+        { std::lock_guard<std::mutex> lk(mu); abort_all = true; }
+        cv.notify_all();
+        for (auto& th : threads) th.join();
+    };
+    int rc = SLC_OK;
+    for (int i = 0; i < n_files && rc == SLC_OK; i++) {
+        const int k = i % K;
+        {
+            std::unique_lock<std::mutex> lk(mu);
+            cv.wait(lk, [&] { return state[(size_t)i] != 0; });
+        }
+        slc_bmp_info info;
+        if (state[(size_t)i] < 0 || slc_bmp_parse(ctx->h_bmp[k], (int64_t)sizes[(size_t)i], &info) != SLC_OK) {
+            rc = fail(ctx, SLC_ERR_INVALID_ARG, "imread error (not an uncompressed 8/24/32-bit BMP): %s", paths[i]);
+            break;
+        }
+        if (info.width != ctx->kp.W || info.height != ctx->kp.H) {
+            rc = fail(ctx, SLC_ERR_INVALID_ARG, "%s is %dx%d, the context is %dx%d", paths[i], info.width, info.height,
+                      ctx->kp.W, ctx->kp.H);
+            break;
+        }
+        const size_t raw = (size_t)info.row_stride * info.height;
+        cudaError_t e = cudaMemcpyAsync(ctx->d_bmp[k], static_cast<uint8_t*>(ctx->h_bmp[k]) + info.pixel_offset, raw,
+                                        cudaMemcpyHostToDevice, ctx->stream);
+        if (e == cudaSuccess)
+            e = slc::launch_bmp_unpack(static_cast<const uint8_t*>(ctx->d_bmp[k]), info.width, info.height, info.bits_per_pixel,
+                                       info.top_down, info.row_stride, info.palette_is_identity, info.gray,
+                                       d_stack + (size_t)i * npx, ctx->stream);
+        if (e == cudaSuccess) e = cudaEventRecord(ctx->bmp_done[k], ctx->stream);
+        if (e != cudaSuccess) { rc = fail(ctx, SLC_ERR_CUDA, "BMP upload / unpack failed: %s", cudaGetErrorString(e)); break; }
+        ctx->launches++;
+        // hand the slot of an older file back to the readers once its upload + unpack are done
+        const int j = i - K / 2;
+        if (j >= 0 && j + K < n_files) {
+            e = cudaEventSynchronize(ctx->bmp_done[j % K]);
+            if (e != cudaSuccess) { rc = fail(ctx, SLC_ERR_CUDA, "cudaEventSynchronize failed: %s", cudaGetErrorString(e)); break; }
+            { std::lock_guard<std::mutex> lk(mu); slot_free_for[(size_t)(j % K)] = j + K; }
+            cv.notify_all();
+        }
+    }
+    stop();
+    if (rc != SLC_OK) { cudaStreamSynchronize(ctx->stream); return rc; }
     SLC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return SLC_OK;
 }
