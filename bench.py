@@ -579,6 +579,76 @@ def run_ingest(args):
     return 0
 
 
+def run_app(args):
+    """--path app: the whole reference program (main.cpp:42-45: Init, CalculateFirst, CalculateOther with
+    its file reads and text clouds) against the same program on this library
+    (examples/dynaframe_main.cpp -> include/dynaframe_b200.hpp), on the same input files, at the
+    reference's own geometry.  The two sets of text clouds are compared byte for byte."""
+    from oracle import ref_runner as R          # runs the reference binary: the baseline of this mode
+    rank, _, world = D.env_rank_world()
+    if rank != 0:
+        return 0
+    exe = os.path.join(ROOT, "structured_light_calculation_b200", "bin", "dynaframe_main")
+    if not os.path.exists(exe):
+        raise SystemExit("bench.py: build the library first (python -c 'import __graft_entry__ as g; g.build()')")
+    if not R.available():
+        print(json.dumps({"metric": "app_frames_per_sec", "unavailable": "oracle/_ref/dynaframe_ref not built"}))
+        return 0
+    cfg = CONFIGS["reference_default"]
+    n = args.app_frames
+    base = load_calibration(os.path.join(ROOT, "tests", "golden", "Result.yml"))
+    cal = synth.synthetic_calibration(cfg, base)
+    scene = synth.make_scene(cfg, cal)
+    stack = synth.render_stack(cfg, scene, noise_sigma=1.0, seed=77)
+    pool = synth.render_dyna_frames(cfg, cal, min(n, 8), stripe_period=20.0, z_step=0.3, noise_sigma=1.5)
+    frames = np.stack([pool[k if k < len(pool) else 2 * len(pool) - 2 - k]
+                       for k in (f % max(1, 2 * len(pool) - 2) for f in range(n))])
+    tmp = tempfile.mkdtemp(prefix="slc_app_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+    try:
+        ws = R.Workspace(cfg, cal, stack, frames, root=tmp)
+        out = os.path.join(tmp, "ours")
+        os.makedirs(out)
+        cmd = [exe, ws.data, str(cfg.width), str(cfg.height), str(cfg.projector_width), str(cfg.gray_digits),
+               str(cfg.phase_steps), str(n), out]
+        subprocess.run(cmd, cwd=ws.cwd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)      # warm-up (driver, page cache)
+        t0 = time.perf_counter()
+        res = subprocess.run(cmd, cwd=ws.cwd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+        ours_s = time.perf_counter() - t0
+        if res.returncode != 0:
+            raise SystemExit(f"dynaframe_main failed ({res.returncode}): {res.stdout[-500:]} {res.stderr[-500:]}")
+        phases = json.loads([ln for ln in res.stdout.splitlines() if ln.startswith("{")][-1])
+        ref = ws.run_app()
+        ref_s = ref["seconds"]
+        same, nbytes = True, 0
+        for f in range(n):
+            name = "iFrame.txt" if f == 0 else f"cFrame{f}.txt"
+            with open(os.path.join(out, name), "rb") as fh:
+                mine = fh.read()
+            same = same and (mine == ref["clouds"][f])
+            nbytes += len(mine)
+        line = {
+            "metric": "app_frames_per_sec", "value": n / ours_s, "unit": "frames/s", "n_gpus": 1, "steps": 1, "warmup": 1,
+            "ms_per_step": 1e3 * ours_s, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": f"whole program: {cfg.planes} pattern .bmp + {n} dynaCam .bmp of {cfg.width}x{cfg.height} in, "
+                                   f"{n} text clouds ({nbytes} bytes) out; process start to exit, files on tmpfs"},
+            "phases_s": phases,
+            "e2e": {"value": n / ours_s, "unit": "frames/s", "h2d_bytes_per_step": (cfg.planes + n) * cfg.pixels,
+                    "d2h_bytes_per_step": nbytes, "api": "examples/dynaframe_main.cpp (CCalculation::Init / CalculateFirst / "
+                                                         "CalculateOther / Result)"},
+            "cpu_baseline": {"value": n / ref_s, "unit": "frames/s", "cores": 1, "kind": "reference",
+                             "sample": f"oracle/_ref/dynaframe_ref full: the reference's own Init + CalculateFirst + CalculateOther "
+                                       f"on the same files ({ref_s:.2f} s, process start to exit)"},
+            "speedup_vs_reference": ref_s / ours_s,
+            "clouds_byte_identical": bool(same),
+        }
+        print(json.dumps(line), flush=True)
+    finally:
+        import shutil
+        shutil.rmtree(tmp, ignore_errors=True)
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -594,10 +664,11 @@ def main():
     ap.add_argument("--pxt", type=int, default=0, help="tuning: pixels per thread (4/8/16)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-numa-bind", action="store_true")
-    ap.add_argument("--path", default="first", choices=["first", "dynamic", "pointcloud", "ingest"],
+    ap.add_argument("--path", default="first", choices=["first", "dynamic", "pointcloud", "ingest", "app"],
                     help="first = the headline first-frame path; dynamic = CalculateOther sequences; "
                          "pointcloud = Result() text formatting; ingest = .bmp files -> device stack")
     ap.add_argument("--ingest-reps", type=int, default=8)
+    ap.add_argument("--app-frames", type=int, default=16, help="--path app: first frame + this many - 1 dynamic frames")
     ap.add_argument("--pc-frames", type=int, default=4)
     ap.add_argument("--dyna-frames", type=int, default=100)
     ap.add_argument("--dyna-e2e-frames", type=int, default=24)
@@ -614,6 +685,8 @@ def main():
         return run_pointcloud(args)
     if args.path == "ingest":
         return run_ingest(args)
+    if args.path == "app":
+        return run_app(args)
 
     import torch
     from structured_light_calculation_b200 import capi

@@ -222,7 +222,9 @@ private:
     std::string m_groupDataPath;
     uint8_t* pinned_stack_ = nullptr;
     Mat m_xyzw, m_mask, m_projU;
-    std::vector<Mat> m_dynXyzw, m_dynMask, m_dynDeltaZ, m_dynProjU;
+    std::vector<Mat> m_dynXyzw, m_dynMask, m_dynDeltaZ, m_dynProjU;   // headers onto m_dynBlock
+    uint8_t* m_dynBlock = nullptr;      // pinned: every map of the dynamic sequence
+    char* m_textBuf = nullptr;          // pinned: Result()'s text of one frame
     uint32_t m_textFlags = 0;
     std::string m_pcDynaPrefix;
     bool calibrated_ = false;

@@ -108,6 +108,10 @@ class Workspace:
                 d["deltaP"] = self._load(f"deltaP{f}.f32", np.float32)
                 d["deltaZ"] = self._load(f"deltaZ{f}.f64", np.float64)
             frames.append(d)
+        clouds = self._clouds(n)
+        return {"frames": frames, "clouds": clouds}
+
+    def _clouds(self, n: int) -> list[bytes]:
         # CCalculation.cpp:192-197,310-315: DATA_PATH + "Res1103\\MoveBoard1103\\" + "PointCloud\\" + name + ".txt";
         # on this platform the backslashes are ordinary file-name characters
         clouds = []
@@ -115,7 +119,19 @@ class Workspace:
             name = "Res1103\\MoveBoard1103\\PointCloud\\" + ("iFrame" if f == 0 else f"cFrame{f}") + ".txt"
             with open(os.path.join(self.data, name), "rb") as fh:
                 clouds.append(fh.read())
-        return {"frames": frames, "clouds": clouds}
+        return clouds
+
+    def run_app(self) -> dict:
+        """The reference program as main.cpp:42-45 runs it (no plane dumps): wall seconds + its clouds."""
+        import time
+        n = self.n_dyna
+        t0 = time.perf_counter()
+        res = subprocess.run([BINARY, "app", self.out], env=self.env(n), stdout=subprocess.PIPE,
+                             stderr=subprocess.STDOUT, text=True)
+        secs = time.perf_counter() - t0
+        if res.returncode != 0 or "dynaframe_ref ok" not in res.stdout:
+            raise RuntimeError(f"dynaframe_ref app failed ({res.returncode}):\n{res.stdout[-2000:]}")
+        return {"seconds": secs, "clouds": self._clouds(n)}
 
     def time_first(self, reps: int) -> list[float]:
         res = subprocess.run([BINARY, "time", str(reps)], env=self.env(1), stdout=subprocess.PIPE,

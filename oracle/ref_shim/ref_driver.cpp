@@ -9,6 +9,8 @@
 //   dynaframe_ref full <outdir>      Init, CalculateFirst, CalculateOther (the reference writes its own
 //                                    text clouds under DATA_PATH); dumps per-frame stripB/W, deltaP,
 //                                    ProjectorU, x, y, z, deltaZ
+//   dynaframe_ref app <outdir>       Init, CalculateFirst, CalculateOther and nothing else: the reference program
+//                                    as main.cpp:42-45 runs it (its text clouds land under DATA_PATH)
 //   dynaframe_ref time <reps>        Init once, then reps x (FillFirstProjectorU + FillCoordinate(0)),
 //                                    prints seconds per repetition (hot loops; images come from the
 //                                    stand-in imread's in-memory cache after the first repetition)
@@ -68,6 +70,12 @@ int main(int argc, char** argv)
             std::printf("%s%.6f", r ? ", " : "", std::chrono::duration<double>(t1 - t0).count());
         }
         std::printf("], \"z_centre\": %.17g}\n", calc.m_zMat[0].at<double>(CAMERA_RESROW / 2, CAMERA_RESLINE / 2));
+        return 0;
+    }
+
+    if (mode == "app") {
+        if (!calc.CalculateFirst() || !calc.CalculateOther()) { std::fprintf(stderr, "Calculate* failed\n"); return 6; }
+        std::printf("dynaframe_ref ok\n");
         return 0;
     }
 

@@ -399,6 +399,9 @@ bool CCalculation::ReleaseSpace()
 {
     if (m_sensor) { delete m_sensor; m_sensor = nullptr; }
     if (pinned_stack_) { slc_host_free(pinned_stack_); pinned_stack_ = nullptr; }
+    m_dynXyzw.clear(); m_dynMask.clear(); m_dynDeltaZ.clear(); m_dynProjU.clear();
+    if (m_dynBlock) { slc_host_free(m_dynBlock); m_dynBlock = nullptr; }
+    if (m_textBuf) { slc_host_free(m_textBuf); m_textBuf = nullptr; }
     if (ctx_) { slc_destroy(ctx_); ctx_ = nullptr; }
     calibrated_ = false;
     return true;
@@ -517,30 +520,36 @@ bool CCalculation::CalculateOther()
         if (!copy_plane(img, sp_, frames + (size_t)i * npx, "CCalculation::StripRegression")) { slc_host_free(frames); return false; }
     }
     const size_t no = (size_t)n - 1;
-    std::vector<float> xyzw(no * npx * 4), dz(no * npx);
-    std::vector<uint8_t> mask(no * npx);
+    // one pinned block holds every map of the sequence (xyzw | deltaZ | ProjectorU | mask per frame);
+    // the per-frame Mats are headers onto it, so the download is the only copy
+    const size_t per = npx * (16 + 4 + 8 + 1);
+    if (m_dynBlock) { slc_host_free(m_dynBlock); m_dynBlock = nullptr; }
+    m_dynXyzw.clear(); m_dynMask.clear(); m_dynDeltaZ.clear(); m_dynProjU.clear();
+    m_dynBlock = static_cast<uint8_t*>(slc_host_alloc(no * per));
+    if (!m_dynBlock) { slc_host_free(frames); ErrorHandling("CCalculation::CalculateOther()->pinned allocation failed."); return false; }
+    float* xyzw = reinterpret_cast<float*>(m_dynBlock);
+    float* dz = reinterpret_cast<float*>(m_dynBlock + no * npx * 16);
+    double* pu = reinterpret_cast<double*>(m_dynBlock + no * npx * 20);
+    uint8_t* mask = m_dynBlock + no * npx * 28;
     // StripRegression + FillOtherDeltaProU + FillCoordinate for every frame: two launches
-    std::vector<double> pu(no * npx);               // m_ProjectorU[f]: Result(f) prints from the f64 plane
     slc_dyna_parity par;
     std::memset(&par, 0, sizeof(par));
-    par.proj_u = pu.data();
+    par.proj_u = pu;                                // m_ProjectorU[f]: Result(f) prints from the f64 plane
     const int rc = slc_dyna_track_host(ctx_, frames, n, sp_.RECO_WINDOW_SIZE, reinterpret_cast<const double*>(m_projU.ptr()),
-                                       xyzw.data(), mask.data(), dz.data(), &par);
+                                       xyzw, mask, dz, &par);
     slc_host_free(frames);
     if (rc != SLC_OK) {
         ErrorHandling(std::string("CCalculation::CalculateOther()->") + slc_last_error(ctx_));
         return false;
     }
-    m_dynXyzw.assign(no, Mat());
-    m_dynMask.assign(no, Mat());
-    m_dynDeltaZ.assign(no, Mat());
-    m_dynProjU.assign(no, Mat());
     for (size_t f = 0; f < no; f++) {
         std::cout << "Frame: " << (f + 1) << " begin." << std::endl;       // :228
-        Mat(sp_.CAMERA_RESROW, sp_.CAMERA_RESLINE, CV_32FC4, xyzw.data() + f * npx * 4).copyTo(m_dynXyzw[f]);
-        Mat(sp_.CAMERA_RESROW, sp_.CAMERA_RESLINE, CV_8UC1, mask.data() + f * npx).copyTo(m_dynMask[f]);
-        Mat(sp_.CAMERA_RESROW, sp_.CAMERA_RESLINE, CV_32FC1, dz.data() + f * npx).copyTo(m_dynDeltaZ[f]);
-        Mat(sp_.CAMERA_RESROW, sp_.CAMERA_RESLINE, CV_64FC1, pu.data() + f * npx).copyTo(m_dynProjU[f]);
+        m_dynXyzw.emplace_back(sp_.CAMERA_RESROW, sp_.CAMERA_RESLINE, CV_32FC4, xyzw + f * npx * 4);
+        m_dynMask.emplace_back(sp_.CAMERA_RESROW, sp_.CAMERA_RESLINE, CV_8UC1, mask + f * npx);
+        m_dynDeltaZ.emplace_back(sp_.CAMERA_RESROW, sp_.CAMERA_RESLINE, CV_32FC1, dz + f * npx);
+        m_dynProjU.emplace_back(sp_.CAMERA_RESROW, sp_.CAMERA_RESLINE, CV_64FC1, pu + f * npx);
+    }
+    for (size_t f = 0; f < no; f++) {
         if (!m_pcDynaPrefix.empty()) {                                      // :309-315
             std::ostringstream name;
             name << sp_.DATA_PATH << m_pcDynaPrefix << (f + 1) << ".txt";
@@ -565,7 +574,8 @@ bool CCalculation::Result(std::string fileName, int i)
     }
     const size_t npx = (size_t)sp_.CAMERA_RESROW * sp_.CAMERA_RESLINE;
     const int64_t cap = (int64_t)(npx * 43 + 16);
-    char* text = static_cast<char*>(slc_host_alloc((size_t)cap));
+    if (!m_textBuf) m_textBuf = static_cast<char*>(slc_host_alloc((size_t)cap));      // pinned, kept for the next frame
+    char* text = m_textBuf;
     bool ok = (text != nullptr);
     int64_t bytes = 0, points = 0;
     if (ok && slc_pointcloud_text_host(ctx_, reinterpret_cast<const double*>(U.ptr()), m_textFlags, text, cap, &bytes,
@@ -574,7 +584,6 @@ bool CCalculation::Result(std::string fileName, int i)
         ok = false;
     }
     if (ok && bytes > 0) ok = (std::fwrite(text, 1, (size_t)bytes, file) == (size_t)bytes);
-    if (text) slc_host_free(text);
     std::fclose(file);
     return ok;
 }
