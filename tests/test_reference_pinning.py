@@ -159,3 +159,33 @@ def test_cuda_dynamic_frames_and_clouds_match_reference_binary(ref, built_librar
         assert np.abs(dyn["delta_z"][f - 1] - fr["deltaZ"]).max() <= 2 * tol
         assert rec.pointcloud_text(dyn["proj_u"][f - 1])[0] == want["clouds"][f]
     rec.close()
+
+
+@pytest.mark.gpu
+def test_whole_program_writes_the_reference_programs_bytes(ref, built_library, base_calibration, tmp_path):
+    """examples/dynaframe_main.cpp (the reference main() on the library, file-backed sensor) and the
+    reference's own program on the same files: every text cloud byte for byte."""
+    import subprocess
+    from structured_light_calculation_b200 import synth
+    from structured_light_calculation_b200.configs import StackConfig
+    from conftest import ROOT
+    exe = os.path.join(ROOT, "structured_light_calculation_b200", "bin", "dynaframe_main")
+    if not os.path.exists(exe):
+        import __graft_entry__
+        __graft_entry__.build()
+    cfg = StackConfig(200, 96, 1280, 6, 4)
+    cal, scene, planes = make_case(cfg, base_calibration, noise=1.0, seed=71)
+    n = 5
+    frames = synth.render_dyna_frames(cfg, cal, n, stripe_period=14.0, z_step=0.4, noise_sigma=1.5)
+    ws = ref.Workspace(cfg, cal, planes, frames, root=str(tmp_path))
+    want = ws.run_app()
+    out = tmp_path / "ours"
+    out.mkdir()
+    res = subprocess.run([exe, ws.data, str(cfg.width), str(cfg.height), str(cfg.projector_width), str(cfg.gray_digits),
+                          str(cfg.phase_steps), str(n), str(out)], cwd=ws.cwd, stdout=subprocess.PIPE,
+                         stderr=subprocess.STDOUT, text=True)
+    assert res.returncode == 0, res.stdout
+    for f in range(n):
+        name = "iFrame.txt" if f == 0 else f"cFrame{f}.txt"
+        assert (out / name).read_bytes() == want["clouds"][f], name
+    assert len(want["clouds"][0]) > 1000
