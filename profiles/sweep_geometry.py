@@ -1,0 +1,42 @@
+"""Device-resident throughput of the fused first-frame kernel over (W, H, G, N): frame sets/s and the
+fraction of the measured HBM copy peak (algorithmic bytes 2G+N+17 per pixel).  Run on a B200:
+    python profiles/sweep_geometry.py"""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from structured_light_calculation_b200 import capi, synth  # noqa: E402
+from structured_light_calculation_b200.calibration import load_calibration  # noqa: E402
+from structured_light_calculation_b200.configs import StackConfig  # noqa: E402
+
+peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(
+    os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
+base = load_calibration(os.path.join(ROOT, "tests", "golden", "Result.yml"))
+dev = torch.device("cuda", 0)
+cases = [(1280, 1024, 1280, 6, 4), (1280, 1024, 1280, 7, 4), (1280, 1024, 1280, 8, 4), (1280, 1024, 2560, 9, 4),
+         (1920, 1200, 2560, 6, 4), (1920, 1200, 2560, 7, 4), (1920, 1200, 2560, 8, 4), (1920, 1200, 2560, 9, 4),
+         (1280, 1040, 1280, 7, 4), (1296, 1024, 1280, 7, 4)]
+if os.environ.get("SWEEP_QUICK"):          # one small batch per Gray depth, for an ncu capture
+    cases = cases[:4]
+for W, H, PW, G, N in cases:
+    cfg = StackConfig(W, H, PW, G, N)
+    cal = synth.synthetic_calibration(cfg, base)
+    rec = capi.Reconstructor(cfg, device=0, max_batch=1, num_slots=1)
+    rec.set_calibration(cal)
+    F = 16 if os.environ.get("SWEEP_QUICK") else max(8, int(6e9 // (cfg.planes * cfg.pixels)))
+    d_in = torch.randint(0, 256, (F, cfg.planes, H, W), dtype=torch.uint8, device=dev)
+    d_xyzw = torch.empty((F, H, W, 4), dtype=torch.float32, device=dev)
+    d_mask = torch.empty((F, H, W), dtype=torch.uint8, device=dev)
+    rec.time_device(d_in.data_ptr(), F, d_xyzw.data_ptr(), d_mask.data_ptr(), 1 if os.environ.get("SWEEP_QUICK") else 3)
+    ms = rec.time_device(d_in.data_ptr(), F, d_xyzw.data_ptr(), d_mask.data_ptr(), 1 if os.environ.get("SWEEP_QUICK") else 10)
+    gbs = (cfg.planes + 17) * cfg.pixels * F / (ms * 1e-3) / 1e9
+    print(f"{W}x{H} G={G} N={N} P={cfg.planes}: {F / (ms * 1e-3):9.0f} frame sets/s  {gbs:7.0f} GB/s  {gbs / peak:.3f} of peak  "
+          f"(batch {F}, {ms:.3f} ms)")
+    rec.close()
+    del d_in, d_xyzw, d_mask
+    torch.cuda.empty_cache()
