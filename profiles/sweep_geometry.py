@@ -20,7 +20,8 @@ base = load_calibration(os.path.join(ROOT, "tests", "golden", "Result.yml"))
 dev = torch.device("cuda", 0)
 cases = [(1280, 1024, 1280, 6, 4), (1280, 1024, 1280, 7, 4), (1280, 1024, 1280, 8, 4), (1280, 1024, 2560, 9, 4),
          (1920, 1200, 2560, 6, 4), (1920, 1200, 2560, 7, 4), (1920, 1200, 2560, 8, 4), (1920, 1200, 2560, 9, 4),
-         (1280, 1040, 1280, 7, 4), (1296, 1024, 1280, 7, 4)]
+         (1280, 1040, 1280, 7, 4), (1296, 1024, 1280, 7, 4),
+         (1280, 1024, 1280, 8, 3), (1280, 1024, 1280, 7, 6), (1280, 1024, 1280, 8, 5)]     # generic instance
 if os.environ.get("SWEEP_QUICK"):          # one small batch per Gray depth, for an ncu capture
     cases = cases[:4]
 for W, H, PW, G, N in cases:
@@ -29,7 +30,9 @@ for W, H, PW, G, N in cases:
     rec = capi.Reconstructor(cfg, device=0, max_batch=1, num_slots=1)
     rec.set_calibration(cal)
     F = 16 if os.environ.get("SWEEP_QUICK") else max(8, int(6e9 // (cfg.planes * cfg.pixels)))
-    d_in = torch.randint(0, 256, (F, cfg.planes, H, W), dtype=torch.uint8, device=dev)
+    scene = synth.make_scene(cfg, cal)                   # rendered stack (random bytes would make most pixels invalid)
+    stack = torch.from_numpy(synth.render_stack(cfg, scene, noise_sigma=1.0, seed=5)).to(dev)
+    d_in = stack.unsqueeze(0).expand(F, -1, -1, -1).contiguous()
     d_xyzw = torch.empty((F, H, W, 4), dtype=torch.float32, device=dev)
     d_mask = torch.empty((F, H, W), dtype=torch.uint8, device=dev)
     rec.time_device(d_in.data_ptr(), F, d_xyzw.data_ptr(), d_mask.data_ptr(), 1 if os.environ.get("SWEEP_QUICK") else 3)

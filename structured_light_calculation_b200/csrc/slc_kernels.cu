@@ -116,8 +116,8 @@ reconstruct_vec_kernel(const __grid_constant__ KParams p)
 #pragma unroll
             for (int b = 0; b < G_T; b++) gray_bit(b);
         } else {
-#pragma unroll 1
-            for (int b = 0; b < G; b++) gray_bit(b);
+#pragma unroll 4
+            for (int b = 0; b < G; b++) gray_bit(b);     // generic depth: four pairs of loads in flight
         }
         // gray2bin (CDecodeGray.cpp:120-125,200): arithmetic for the reflected code
         const bool use_lut = (MODE == 2) && (p.lut != nullptr);
@@ -170,14 +170,14 @@ reconstruct_vec_kernel(const __grid_constant__ KParams p)
 #pragma unroll
                 for (int k = 0; k < N_T / 2; k++) phase_pair(k);
             } else {
-#pragma unroll 1
+#pragma unroll 2
                 for (int k = 0; k < half; k++) phase_pair(k);
             }
         } else {
             // [EXT] odd N: plain sums
 #pragma unroll
             for (int i = 0; i < PXT; i++) { sv[i] = 0.f; cv[i] = 0.f; }
-#pragma unroll 1
+#pragma unroll 3
             for (int k = 0; k < N; k++) {
                 uint32_t qa[NW];
                 VecLoad<PXT>::load(plane(2 * G + k), qa);
@@ -446,10 +446,13 @@ struct VecEntry { int G, N, pxt, mode; VecKernel fn; };
     { G, N, PXT, 1, reconstruct_vec_kernel<PXT, G, N, 1> }, \
     { G, N, PXT, 2, reconstruct_vec_kernel<PXT, G, N, 2> }
 
-// Specialised <G, N> instances: the reference default and BASELINE.json's
-// configurations; anything else runs the generic (0, 0) instance.
+// Specialised <G, N> instances: the reference default, BASELINE.json's configurations and the
+// other 4-step Gray depths (every plane loop unrolled, loads issued ahead of their use); anything
+// else runs the generic (0, 0) instance, which is latency bound (0.58-0.65 of the HBM peak measured
+// at G = 8, N = 4 before that pair got its own instance, profiles/r01_sweep_geometry.txt).
 const VecEntry kVecTable[] = {
     SLC_VEC(8, 6, 4),   SLC_VEC(8, 7, 4),   SLC_VEC(8, 9, 4),
+    SLC_VEC(8, 5, 4),   SLC_VEC(8, 8, 4),   SLC_VEC(8, 10, 4),
     SLC_VEC(8, 8, 8),   SLC_VEC(8, 10, 12), SLC_VEC(8, 0, 0),
     SLC_VEC(16, 9, 4),  SLC_VEC(16, 0, 0),
     SLC_VEC(4, 9, 4),   SLC_VEC(4, 0, 0),
