@@ -453,21 +453,25 @@ struct VecEntry { int G, N, pxt, mode; VecKernel fn; };
 const VecEntry kVecTable[] = {
     SLC_VEC(8, 6, 4),   SLC_VEC(8, 7, 4),   SLC_VEC(8, 9, 4),
     SLC_VEC(8, 5, 4),   SLC_VEC(8, 8, 4),   SLC_VEC(8, 10, 4),
-    SLC_VEC(8, 8, 8),   SLC_VEC(8, 10, 12), SLC_VEC(8, 0, 0),
+    SLC_VEC(8, 8, 8),   SLC_VEC(8, 10, 12),
+    // Gray depth fixed, any number of phase steps (the Gray planes are most of the loads)
+    SLC_VEC(8, 5, 0),   SLC_VEC(8, 6, 0),   SLC_VEC(8, 7, 0),   SLC_VEC(8, 8, 0),   SLC_VEC(8, 9, 0),   SLC_VEC(8, 10, 0),
+    SLC_VEC(8, 0, 0),
     SLC_VEC(16, 9, 4),  SLC_VEC(16, 0, 0),
     SLC_VEC(4, 9, 4),   SLC_VEC(4, 0, 0),
 };
 
 const VecEntry* find_vec(int G, int N, int pxt, int mode, bool* specialised)
 {
-    const VecEntry* generic = nullptr;
+    const VecEntry *generic = nullptr, *gray_only = nullptr;
     for (const VecEntry& e : kVecTable) {
         if (e.pxt != pxt || e.mode != mode) continue;
         if (e.G == G && e.N == N) { *specialised = true; return &e; }
+        if (e.G == G && e.N == 0) gray_only = &e;
         if (e.G == 0 && e.N == 0) generic = &e;
     }
     *specialised = false;
-    return generic;
+    return gray_only ? gray_only : generic;
 }
 
 int g_default_pxt = 8;

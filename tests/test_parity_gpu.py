@@ -77,6 +77,11 @@ CASES = [
     ("generic_g11n4", 11, 4, 4096, 128, 64, 0.0, 0.0),
     ("odd_n5", 8, 5, 2048, 128, 64, 1.0, 0.0),
     ("odd_n3", 7, 3, 1280, 128, 64, 1.0, 2.0),
+    ("g8n4", 8, 4, 2048, 256, 64, 1.0, 0.0),          # 4-step instances beside the BASELINE ones
+    ("g10n4", 10, 4, 4096, 256, 64, 1.0, 3.0),
+    ("g5n4", 5, 4, 640, 128, 64, 1.0, 0.0),
+    ("g9n8", 9, 8, 2560, 192, 64, 1.0, 0.0),          # fixed Gray depth, generic even / odd step count
+    ("g6n7", 6, 7, 1280, 192, 64, 1.0, 2.0),
     ("g1", 1, 4, 64, 64, 32, 1.0, 0.0),
     ("g16", 16, 4, 65536, 64, 32, 0.0, 0.0),
 ]
