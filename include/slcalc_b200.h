@@ -282,7 +282,7 @@ int slc_time_reconstruct_device(slc_context *ctx, const uint8_t *d_stack, int32_
 /* Number of kernels this library has launched on this context so far. */
 int64_t slc_launch_count(const slc_context *ctx);
 /* Tuning hook for bench/tests: pixels owned by one thread of the vector kernel
- * (4, 8 or 16; process-wide).  Results do not depend on it. */
+ * (4, 8 or 16; 0 = chosen per geometry, the default; process-wide).  Results do not depend on it. */
 void slc_tune_pixels_per_thread(int32_t pxt);
 
 #ifdef __cplusplus

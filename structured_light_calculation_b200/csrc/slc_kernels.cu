@@ -457,8 +457,10 @@ const VecEntry kVecTable[] = {
     // Gray depth fixed, any number of phase steps (the Gray planes are most of the loads)
     SLC_VEC(8, 5, 0),   SLC_VEC(8, 6, 0),   SLC_VEC(8, 7, 0),   SLC_VEC(8, 8, 0),   SLC_VEC(8, 9, 0),   SLC_VEC(8, 10, 0),
     SLC_VEC(8, 0, 0),
-    SLC_VEC(16, 9, 4),  SLC_VEC(16, 0, 0),
-    SLC_VEC(4, 9, 4),   SLC_VEC(4, 0, 0),
+    SLC_VEC(16, 9, 4),  SLC_VEC(16, 7, 4), SLC_VEC(16, 8, 4), SLC_VEC(16, 0, 0),
+    SLC_VEC(4, 9, 4),   SLC_VEC(4, 7, 4), SLC_VEC(4, 8, 4),  SLC_VEC(4, 6, 4), SLC_VEC(4, 8, 8), SLC_VEC(4, 10, 12),
+    SLC_VEC(4, 5, 0),   SLC_VEC(4, 6, 0),   SLC_VEC(4, 7, 0),   SLC_VEC(4, 8, 0),   SLC_VEC(4, 9, 0),   SLC_VEC(4, 10, 0),
+    SLC_VEC(4, 0, 0),
 };
 
 const VecEntry* find_vec(int G, int N, int pxt, int mode, bool* specialised)
@@ -474,13 +476,25 @@ const VecEntry* find_vec(int G, int N, int pxt, int mode, bool* specialised)
     return gray_only ? gray_only : generic;
 }
 
-int g_default_pxt = 8;
+int g_forced_pxt = 0;      // 0 = pick per geometry
+
+// Pixels per thread: 8 (one 8-byte load per plane, 64 registers, 4 blocks / SM) is the fastest shape
+// for most instances; the 4-step G = 7 and G = 8 instances run at 0.87 / 0.83 of the HBM peak with 8 and
+// at 0.94 / 0.98 with 4 (40-48 registers, 6 blocks / SM) -- profiles/r01_sweep_geometry.txt.
+// The instances without a compile-time step count are also faster with 4 (0.75-0.87 against 0.70-0.76).
+int preferred_pxt(int G, int N)
+{
+    if (N == 4 && (G == 7 || G == 8)) return 4;
+    bool exact = false;
+    find_vec(G, N, 8, 0, &exact);
+    return exact ? 8 : 4;
+}
 
 }  // namespace
 
 void set_default_pixels_per_thread(int pxt)
 {
-    if (pxt == 4 || pxt == 8 || pxt == 16) g_default_pxt = pxt;
+    if (pxt == 0 || pxt == 4 || pxt == 8 || pxt == 16) g_forced_pxt = pxt;
 }
 
 bool vector_kernel_applicable(const KParams& p, int pxt)
@@ -497,7 +511,7 @@ cudaError_t launch_reconstruct(KParams p, bool force_scalar, cudaStream_t stream
     // v = off / W by multiplication: exact while off * W < 2^40 (split_row_col)
     p.row_magic = ((unsigned long long)p.npx * (unsigned long long)p.W < (1ull << 40))
                       ? ((1ull << 40) / (unsigned long long)p.W + 1ull) : 0ull;
-    int pxt = g_default_pxt;
+    int pxt = g_forced_pxt ? g_forced_pxt : preferred_pxt(p.G, p.N);
     while (pxt >= 4 && p.W % pxt != 0) pxt >>= 1;   // groups must not straddle rows
     if (pxt < 4) pxt = 0;
     if (!force_scalar && pxt != 0 && vector_kernel_applicable(p, pxt)) {

@@ -104,7 +104,7 @@ def test_fused_kernel_matches_oracle(built_library, oracle, base_calibration, ca
         check_fast_modes(rec, planes, got)
         rec.close()
     finally:
-        built_library.slc_tune_pixels_per_thread(8)
+        built_library.slc_tune_pixels_per_thread(0)
     want = oracle_run(oracle, cfg, cal, planes)
     check_parity(got, want, cfg)
     del capi
