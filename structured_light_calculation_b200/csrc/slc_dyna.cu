@@ -97,9 +97,9 @@ strip_regression_kernel(const uint8_t* __restrict__ frames, char2* __restrict__ 
 // ---- StripRegression, window 21 (the reference's RECO_WINDOW_SIZE), fast path ----------
 // Tile: 160 output columns x 32 rows per block.
 //  Phase 1 (184 threads): a thread owns 4 adjacent columns (one 32-bit load per image row) and
-//    8 consecutive rows; the 21-row sums live as 16-bit lanes of two registers (<= 5355, no
-//    carries), built once from 21 rows and then slid down 7 times.  Each sum goes to shared
-//    memory as a key  sum << 9 | 0x100 | tile_column.
+//    16 consecutive rows; one running 21-row sum per column, built once from 21 rows and then
+//    slid down 15 times with byte dot products.  Each sum goes to shared memory as a key
+//    sum << 9 | 0x100 | tile_column.
 //  Phase 2 (256 threads): a thread owns 20 consecutive outputs of one row.  Their 20-column
 //    windows [w-10, w+9] all straddle one boundary between two 20-element blocks, so the window
 //    minimum is min(suffix-minimum of block 1, prefix-minimum of block 2) (van Herk / Gil-Werman):
@@ -116,6 +116,14 @@ constexpr int kVhStride = kVhCols + 2;            // 186 words: conflict-free 8-
 constexpr int kVhOut = 20;                        // outputs per phase-2 thread (= window - 1)
 constexpr unsigned kVhFlag = 0x100u;
 constexpr unsigned kVhInv = 8191u << 9;
+
+// d = c + sum_i (unsigned byte i of a) * (signed byte i of b)
+__device__ __forceinline__ int dp4a_us(uint32_t a, int b, int c)
+{
+    int d;
+    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
 
 // kRowIn / kColIn: every image row / column the tile touches exists and every sum row / column of
 // the tile lies inside the reference's [10, H-10) / [10, W-10) region, so nothing along that axis
@@ -137,12 +145,15 @@ __device__ __forceinline__ void strip21_tile(const uint8_t* __restrict__ img, ch
             if (kRowIn) return __ldg(reinterpret_cast<const uint32_t*>(colp + (long long)row * W));
             return (row >= 0 && row < H) ? __ldg(reinterpret_cast<const uint32_t*>(colp + (long long)row * W)) : 0u;
         };
-        uint32_t lo = 0, hi = 0;                          // 16-bit lanes: (col0, col2) and (col1, col3)
+        // one 32-bit running sum per column, maintained with byte dot products (IDP4A: selector byte 1
+        // adds a row's pixel, selector byte -1 removes one) -- they issue on the FMA pipe, beside the
+        // integer min / max work of phase 2 that saturates the ALU pipe
+        int sum[4] = {0, 0, 0, 0};
 #pragma unroll
         for (int k = -kVhHalf; k <= kVhHalf; k++) {
             const uint32_t w = ld(hb + k);
-            lo += w & 0x00FF00FFu;
-            hi += __byte_perm(w, 0u, 0x4341);
+#pragma unroll
+            for (int j = 0; j < 4; j++) sum[j] = dp4a_us(w, 1 << (8 * j), sum[j]);
         }
         // valSum is 0 outside [10, H-10) x [10, W-10) (the zero-initialised Mat, CCalculation.cpp:801-823)
         bool cok[4];
@@ -154,15 +165,14 @@ __device__ __forceinline__ void strip21_tile(const uint8_t* __restrict__ img, ch
             const int h = hb + r;
             if (r > 0) {
                 const uint32_t wa = ld(h + kVhHalf), ws = ld(h - kVhHalf - 1);
-                lo = lo + (wa & 0x00FF00FFu) - (ws & 0x00FF00FFu);
-                hi = hi + __byte_perm(wa, 0u, 0x4341) - __byte_perm(ws, 0u, 0x4341);
+#pragma unroll
+                for (int j = 0; j < 4; j++) sum[j] = dp4a_us(ws, 0xFF << (8 * j), dp4a_us(wa, 1 << (8 * j), sum[j]));
             }
             const bool row_ok = kRowIn || ((h >= kVhHalf) && (h < H - kVhHalf));
-            const uint32_t sv[4] = {lo & 0xFFFFu, hi & 0xFFFFu, lo >> 16, hi >> 16};
             uint32_t key[4];
 #pragma unroll
             for (int j = 0; j < 4; j++)
-                key[j] = ((row_ok && cok[j]) ? sv[j] : 0u) * 512u + (kbase + (unsigned)j);
+                key[j] = ((row_ok && cok[j]) ? (uint32_t)sum[j] : 0u) * 512u + (kbase + (unsigned)j);
             uint2* dst = reinterpret_cast<uint2*>(&s_key[seg * kVhSeg + r][4 * q]);
             dst[0] = make_uint2(key[0], key[1]);
             dst[1] = make_uint2(key[2], key[3]);
