@@ -95,7 +95,7 @@ strip_regression_kernel(const uint8_t* __restrict__ frames, char2* __restrict__ 
 }
 
 // ---- StripRegression, window 21 (the reference's RECO_WINDOW_SIZE), fast path ----------
-// Tile: 160 output columns x 32 rows per block.
+// Tile: 160 output columns x 64 rows per block.
 //  Phase 1 (184 threads): a thread owns 4 adjacent columns (one 32-bit load per image row) and
 //    16 consecutive rows; one running 21-row sum per column, built once from 21 rows and then
 //    slid down 15 times with byte dot products.  Each sum goes to shared memory as a key
