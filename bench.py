@@ -222,8 +222,8 @@ def run_reference(args, cfg):
 
 
 def workload_name(cfg):
-    which = {"config1": "configs[0]", "config2": "configs[1]", "config3": "configs[2]", "config5": "configs[4]",
-             "reference_default": "the reference's own constants"}.get(cfg.name, cfg.name)
+    which = {"config1": "configs[0]", "config2": "configs[1]", "config3": "configs[2]", "config4": "configs[3]", "config5": "configs[4]",
+             "reference_default": "none: the reference's own StaticParameters"}.get(cfg.name, cfg.name)
     extra = ", modulation mask" if cfg.modulation_min > 0 else ""
     return (f"{cfg.width}x{cfg.height} stack, {cfg.gray_digits} Gray pairs (LSB = the complementary half-period bit) + "
             f"{cfg.phase_steps}-step phase shift{extra}, projector width {cfg.projector_width} (BASELINE {which})")
