@@ -126,3 +126,43 @@ def test_pointcloud_compact_matches_numpy(built_library, oracle, base_calibratio
     every = rec.pointcloud_compact(xyzw, np.ones_like(mask), capi.SLC_ORDER_REFERENCE)
     assert np.array_equal(every, xyzw.transpose(1, 0, 2).reshape(-1, 4)[:, :3])
     rec.close()
+
+
+def test_pointcloud_and_ingest_error_paths(built_library, base_calibration):
+    """Bad arguments come back as status codes with a message, never as a crash."""
+    import torch
+    from structured_light_calculation_b200 import capi
+    from structured_light_calculation_b200.capi import SlcError
+    from structured_light_calculation_b200.configs import StackConfig
+    cfg = StackConfig(64, 32, 1280, 6, 4)
+    cal, _, planes = make_case(cfg, base_calibration)
+    dev = torch.device("cuda", 0)
+    rec = capi.Reconstructor(cfg, device=0, max_batch=1, num_slots=1)
+    d_u = torch.zeros((32, 64), dtype=torch.float64, device=dev)
+    d_text = torch.empty((43 * 2048 + 32,), dtype=torch.uint8, device=dev)
+    with pytest.raises(SlcError) as ei:                       # calibration not set (CCalculation.cpp:176-181)
+        rec.pointcloud_text_device(d_u.data_ptr(), d_text.data_ptr(), d_text.numel())
+    assert ei.value.status == capi.SLC_ERR_NOT_INITIALISED
+    rec.set_calibration(cal)
+    with pytest.raises(SlcError) as ei:                       # output must be 16-byte aligned
+        rec.pointcloud_text_device(d_u.data_ptr(), d_text.data_ptr() + 4, 1024)
+    assert "aligned" in ei.value.message
+    got = rec.reconstruct(planes)
+    d_xyzw = torch.from_numpy(got["xyzw"][0]).to(dev)
+    d_mask = torch.from_numpy(got["mask"][0]).to(dev)
+    d_xyz = torch.empty((2048, 3), dtype=torch.float32, device=dev)
+    with pytest.raises(SlcError) as ei:                       # unknown order
+        rec.pointcloud_compact_device(d_xyzw.data_ptr(), d_mask.data_ptr(), d_xyz.data_ptr(), 2048, order=7)
+    assert "order" in ei.value.message
+    with pytest.raises(SlcError) as ei:                       # too small: the needed size is reported
+        rec.pointcloud_compact_device(d_xyzw.data_ptr(), d_mask.data_ptr(), d_xyz.data_ptr(), 10)
+    assert "needs" in ei.value.message
+    with pytest.raises(SlcError):                             # NULL map
+        rec.pointcloud_compact_device(0, d_mask.data_ptr(), d_xyz.data_ptr(), 2048)
+    with pytest.raises(SlcError) as ei:                       # a path that does not exist names itself
+        rec.load_bmp_planes(["/nonexistent/vGrayCam0.bmp"], d_mask.data_ptr())
+    assert "vGrayCam0.bmp" in ei.value.message
+    rec.load_bmp_planes([], d_mask.data_ptr())                # nothing to do
+    # the context is still usable after every failure
+    assert rec.pointcloud_compact_device(d_xyzw.data_ptr(), d_mask.data_ptr(), d_xyz.data_ptr(), 2048) == int(got["mask"].sum())
+    rec.close()
