@@ -4,10 +4,11 @@
 // The reference walks the image u outer / v inner, skips pixels whose z is outside
 // [FOV_MIN_DISTANCE, FOV_MAX_DISTANCE] and writes "x y z\n" with ostream << double, i.e.
 // printf("%g") with precision 6.  Here that is a variable-length record emission:
-//   pass 1  pc_emit_kernel<MODE, false>  length of every record, summed per block
-//   pass 2  pc_emit_kernel<MODE, true>   each block sums the counts of the blocks before it, then the
-//                                        records again, block-local scan, staged in shared memory
-//                                        at the output's own 16-byte phase, written as uint4
+//   pass 1  pc_emit_kernel<MODE, false>  length of every record (kept, one byte each), summed per block
+//   pass 2  pc_emit_kernel<MODE, true>   each block sums the counts of the blocks before it, scans the
+//                                        lengths, produces every record straight into its place in a
+//                                        shared-memory chunk laid out at the output's own 16-byte
+//                                        phase, and writes the chunk as uint4
 // MODE 0 records are text lines formatted from f64 x, y, z -- recomputed from the f64
 // ProjectorU plane in the reference's operation order (:686-687, :761-767), so the text is
 // byte-identical to what the reference's doubles print; MODE 1 records are packed float3 xyz
@@ -128,9 +129,28 @@ struct PcArgs {
     const uint8_t* mask;             // MODE 1
     unsigned flags;
     unsigned long long* block_sums;  // [2 * n_blocks + 2]: (bytes, records) per block, totals last
+    uint8_t* rec_len;                // MODE 0: length of every record, written by pass 1 for pass 2
     unsigned char* out;
     unsigned long long capacity;     // bytes
 };
+
+// one line "x y z" + line end of pixel (v, u), or 0 if the reference skips the pixel
+__device__ __forceinline__ int text_line(const KParams& p, double U, int u, int v, char* o, bool exp3, bool crlf)
+{
+    if (U == 0.0) return 0;                                        // :678-682
+    const double z = z_exact(p, U, u, v);                          // :686-687
+    if ((z < p.fov_min) || (z > p.fov_max)) return 0;              // :701-704 and :341-345
+    const double x = __ddiv_rn(__dmul_rn(z, __dsub_rn((double)u, p.cu)), p.fu);   // :766
+    const double y = __ddiv_rn(__dmul_rn(z, __dsub_rn((double)v, p.cv)), p.fv);   // :767
+    int len = format_g6(x, o, exp3);
+    o[len++] = ' ';
+    len += format_g6(y, o + len, exp3);
+    o[len++] = ' ';
+    len += format_g6(z, o + len, exp3);
+    if (crlf) o[len++] = '\r';
+    o[len++] = '\n';
+    return len;
+}
 
 // inclusive scan of `v` over the block; returns the exclusive prefix, *total = block sum
 __device__ __forceinline__ int block_exclusive_scan(int v, int* s_warp, int* total)
@@ -161,7 +181,7 @@ __global__ void __launch_bounds__(kPcThreads)
 pc_emit_kernel(const __grid_constant__ KParams p, const PcArgs a)
 {
     __shared__ __align__(16) unsigned char s_txt[kPcThreads * kPcMaxLine + 32];
-    __shared__ __align__(16) unsigned char s_slot[MODE == 0 ? kPcThreads * kPcSlot : 16];
+    __shared__ __align__(16) unsigned char s_slot[(MODE == 0 && !WRITE) ? kPcThreads * kPcSlot : 16];
     __shared__ int s_warp[kPcThreads / 32];
     const int t = threadIdx.x;
     const long long base = (long long)blockIdx.x * kPcChunk;
@@ -200,37 +220,22 @@ pc_emit_kernel(const __grid_constant__ KParams p, const PcArgs a)
 
     for (int it = 0; it < kPcIters; it++) {
         const long long i = base + (long long)it * kPcThreads + t;
-        int len = 0;
-        float3 rec = make_float3(0.f, 0.f, 0.f);
-        unsigned char* slot = &s_slot[MODE == 0 ? t * kPcSlot : 0];
+        int len = 0, u = 0, v = 0;
+        long long px = 0;
         if (i < a.npx) {
-            int u, v;
             if (a.order == 1) { u = (int)(i / a.H); v = (int)(i - (long long)u * a.H); }
             else { v = (int)(i / a.W); u = (int)(i - (long long)v * a.W); }
-            const long long px = (long long)v * a.W + u;
+            px = (long long)v * a.W + u;
             if (MODE == 0) {
-                const double U = a.proj_u[px];
-                if (U != 0.0) {                                            // :678-682
-                    const double z = z_exact(p, U, u, v);                  // :686-687
-                    if (!((z < p.fov_min) || (z > p.fov_max))) {           // :701-704 and :341-345
-                        const double x = __ddiv_rn(__dmul_rn(z, __dsub_rn((double)u, p.cu)), p.fu);   // :766
-                        const double y = __ddiv_rn(__dmul_rn(z, __dsub_rn((double)v, p.cv)), p.fv);   // :767
-                        char* o = reinterpret_cast<char*>(slot);
-                        len = format_g6(x, o, exp3);
-                        o[len++] = ' ';
-                        len += format_g6(y, o + len, exp3);
-                        o[len++] = ' ';
-                        len += format_g6(z, o + len, exp3);
-                        if (crlf) o[len++] = '\r';
-                        o[len++] = '\n';
-                    }
+                if (!WRITE) {
+                    // pass 1: format into a scratch slot for the length alone, and remember it
+                    len = text_line(p, a.proj_u[px], u, v, reinterpret_cast<char*>(&s_slot[t * kPcSlot]), exp3, crlf);
+                    a.rec_len[i] = (uint8_t)len;
+                } else {
+                    len = a.rec_len[i];
                 }
             } else {
-                if (a.mask[px] != 0) {
-                    const float4 q = a.xyzw[px];
-                    rec = make_float3(q.x, q.y, q.z);
-                    len = 12;
-                }
+                len = (a.mask[px] != 0) ? 12 : 0;
             }
         }
         int total;
@@ -241,12 +246,16 @@ pc_emit_kernel(const __grid_constant__ KParams p, const PcArgs a)
             const unsigned align = (unsigned)(gofs & 15ull);
             if (gofs + (unsigned long long)total <= a.capacity) {
                 unsigned char* dst = &s_txt[align + excl];
-                if (MODE == 0) {
-                    for (int j = 0; j < len; j++) dst[j] = slot[j];
-                } else if (len) {
-                    // 12-byte records: align + excl is a multiple of 4 (gofs is a multiple of 12 from a 16-aligned base)
-                    float* d = reinterpret_cast<float*>(dst);
-                    d[0] = rec.x; d[1] = rec.y; d[2] = rec.z;
+                if (len) {
+                    if (MODE == 0) {
+                        // pass 2: the line is formatted straight into its place in the staged chunk
+                        text_line(p, a.proj_u[px], u, v, reinterpret_cast<char*>(dst), exp3, crlf);
+                    } else {
+                        // 12-byte records: align + excl is a multiple of 4 (gofs is a multiple of 12 from a 16-aligned base)
+                        const float4 q = a.xyzw[px];
+                        float* d = reinterpret_cast<float*>(dst);
+                        d[0] = q.x; d[1] = q.y; d[2] = q.z;
+                    }
                 }
                 __syncthreads();
                 unsigned char* g = a.out + (gofs - align);         // 16-byte aligned
@@ -294,10 +303,15 @@ __global__ void format_g6_kernel(const double* __restrict__ v, long long n, unsi
 
 }  // namespace
 
-size_t pointcloud_scratch_bytes(long long npx)
+static size_t pointcloud_sums_bytes(long long npx)
 {
     const long long blocks = (npx + kPcChunk - 1) / kPcChunk;
-    return (size_t)(2 * blocks + 2) * sizeof(unsigned long long);
+    return ((size_t)(2 * blocks + 2) * sizeof(unsigned long long) + 255) & ~(size_t)255;
+}
+
+size_t pointcloud_scratch_bytes(long long npx)
+{
+    return pointcloud_sums_bytes(npx) + (size_t)npx;      // block sums | one length byte per pixel
 }
 
 // mode 0: text lines from d_proj_u; mode 1: float3 of the valid pixels of (d_xyzw, d_mask).
@@ -315,6 +329,7 @@ cudaError_t launch_pointcloud(const KParams& p, int mode, int order, unsigned fl
     a.mask = d_mask;
     a.flags = flags;
     a.block_sums = static_cast<unsigned long long*>(d_scratch);
+    a.rec_len = static_cast<uint8_t*>(d_scratch) + pointcloud_sums_bytes(p.npx);
     a.out = static_cast<unsigned char*>(d_out);
     a.capacity = capacity;
     if (mode == 0) pc_emit_kernel<0, false><<<blocks, kPcThreads, 0, stream>>>(p, a);
