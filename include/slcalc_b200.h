@@ -183,6 +183,19 @@ int slc_decode_phase_host(slc_context *ctx, const uint8_t *h_phase_planes,
 int slc_triangulate_host(slc_context *ctx, const double *h_proj_u,
                          float *h_xyzw, uint8_t *h_mask);
 
+/* [EXT] both projector coordinates: ProjectorU decoded from the vertical patterns and
+ * ProjectorV from horizontal ones (decode the second stack with a context whose projector_width is the
+ * projector HEIGHT and whose gray_digits is GRAY_H_NUMDIGIT -- what CDecodeGray::SetNumDigit(n, false)
+ * selects, CDecodeGray.cpp:182-185 -- and ask for its proj_u parity plane).  Each coordinate gives one
+ * linear equation in z built from its row of P the way CCalculation.cpp:159-164,686-687 builds the
+ * column one; z is their least-squares solution, in f64.  mask = U != 0 && V != 0 && fov_min <= z <=
+ * fov_max.  The reference itself never uses row 1 of P: there is no reference output to match, the
+ * oracle's restatement of this definition is matched bit for bit. */
+int slc_triangulate_uv_device(slc_context *ctx, const double *d_proj_u, const double *d_proj_v,
+                              float *d_xyzw, uint8_t *d_mask, void *cuda_stream);
+int slc_triangulate_uv_host(slc_context *ctx, const double *h_proj_u, const double *h_proj_v,
+                            float *h_xyzw, uint8_t *h_mask);
+
 /* ---- dynamic frames ("next" row: CCalculation::CalculateOther) ----------- */
 /* Optional parity planes of the dynamic path.  NULL members are skipped. */
 typedef struct {

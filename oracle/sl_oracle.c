@@ -133,6 +133,49 @@ static int cfg_ok(const slo_config *cfg)
     return 1;
 }
 
+/* ---- [EXT] over-determined (u, v) triangulation ------------------------- */
+/* The reference decodes projector columns only and never touches row 1 of P.  Definition: each
+ * decoded projector coordinate gives one linear equation in z, built from its row of P exactly
+ * the way CCalculation.cpp:159-164,686-687 builds the column one,
+ *     (c0 - c2*U) z = B*U - A,      (c1 - c2*V) z = B*V - E,
+ * c_r(u,v) = (u-cu)*fv*P_r0 + (v-cv)*fu*P_r1 + fu*fv*P_r2,  A = fu*fv*P03, E = fu*fv*P13, B = fu*fv*P23,
+ * and z is their least-squares solution.  Valid iff U != 0, V != 0 and fov_min <= z <= fov_max;
+ * x, y as CCalculation.cpp:766-767. */
+void slo_triangulate_uv(const slo_config *cfg, const slo_calib *cal, const double *U, const double *V,
+                        double *xMat, double *yMat, double *zMat, uint8_t *mask)
+{
+    const int W = cfg->width, H = cfg->height;
+    double P[12], A, B;
+    slo_calibration(cfg, cal, &A, &B, NULL, NULL, P);
+    const double fu = cal->cam[0], fv = cal->cam[4], cu = cal->cam[2], cv = cal->cam[5];
+    const double E = fu * fv * P[7];
+    const double k02 = fu * fv * P[2], k12 = fu * fv * P[6], k22 = fu * fv * P[10];
+    for (int v = 0; v < H; v++) {
+        for (int u = 0; u < W; u++) {
+            const size_t p = (size_t)v * W + u;
+            double x = 0, y = 0, z = 0;
+            uint8_t ok = 0;
+            if (U[p] != 0 && V[p] != 0) {
+                const double du = (u - cu) * fv, dv = (v - cv) * fu;
+                const double c0 = du * P[0] + dv * P[1] + k02;
+                const double c1 = du * P[4] + dv * P[5] + k12;
+                const double c2 = du * P[8] + dv * P[9] + k22;
+                const double a1 = c0 - c2 * U[p], b1 = B * U[p] - A;
+                const double a2 = c1 - c2 * V[p], b2 = B * V[p] - E;
+                const double zd = (a1 * b1 + a2 * b2) / (a1 * a1 + a2 * a2);
+                if (!((zd < cfg->fov_min) || (zd > cfg->fov_max))) {
+                    ok = 1;
+                    z = zd;
+                    x = zd * (u - cu) / fu;
+                    y = zd * (v - cv) / fv;
+                }
+            }
+            xMat[p] = x; yMat[p] = y; zMat[p] = z;
+            if (mask) mask[p] = ok;
+        }
+    }
+}
+
 /* ---- point-cloud text: CCalculation::Result (CCalculation.cpp:323-357) ------------------ */
 /* `file << double` with default stream flags is printf("%g") with precision 6 (C++ [ostream.inserters.arithmetic]
  * -> num_put -> printf conversion %g).  glibc's printf converts exactly (round-half-even on the

@@ -119,6 +119,11 @@ void slo_dyna_frame(const slo_config *cfg, const slo_calib *cal, const double *U
                     const double *z0, double *U1, double *x, double *y, double *z, double *deltaZ,
                     uint8_t *mask);
 
+/* [EXT] over-determined triangulation from both projector coordinates; see the
+ * definition above the function.  U, V, x, y, z: f64 [height][width]. */
+void slo_triangulate_uv(const slo_config *cfg, const slo_calib *cal, const double *U, const double *V,
+                        double *x, double *y, double *z, uint8_t *mask);
+
 /* Point-cloud text: CCalculation::Result (CCalculation.cpp:323-357) --
  * u outer / v inner, pixels with z outside [fov_min, fov_max] skipped, "x y z" + line end with
  * each number as `ostream << double` prints it, i.e. printf("%g") (precision 6).  flags bit 0:

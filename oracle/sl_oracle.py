@@ -99,6 +99,7 @@ def lib():
         L.slo_result_text.restype = C.c_longlong
         L.slo_format_g6.argtypes = [C.c_double, C.c_uint, C.c_char_p]
         L.slo_format_g6.restype = C.c_int
+        L.slo_triangulate_uv.argtypes = [C.POINTER(SloConfig), C.POINTER(SloCalib)] + [C.c_void_p] * 6
         _lib = L
     return _lib
 
@@ -302,3 +303,15 @@ def format_g6(v: float, flags: int = 0) -> bytes:
     out = C.create_string_buffer(40)
     n = lib().slo_format_g6(float(v), flags, out)
     return out.raw[:n]
+
+
+def triangulate_uv(cfg: SloConfig, cal: SloCalib, U: np.ndarray, V: np.ndarray) -> dict:
+    """[EXT] least-squares z from the projector column U and row V."""
+    U = np.ascontiguousarray(U, dtype=np.float64)
+    V = np.ascontiguousarray(V, dtype=np.float64)
+    shape = (cfg.height, cfg.width)
+    out = {k: np.empty(shape, np.float64) for k in "xyz"}
+    out["mask"] = np.empty(shape, np.uint8)
+    lib().slo_triangulate_uv(C.byref(cfg), C.byref(cal), U.ctypes.data, V.ctypes.data, out["x"].ctypes.data,
+                             out["y"].ctypes.data, out["z"].ctypes.data, out["mask"].ctypes.data)
+    return out

@@ -126,6 +126,8 @@ def load_library():
     L.slc_decode_gray_host.argtypes = [vp, vp, vp, vp]
     L.slc_decode_phase_host.argtypes = [vp, vp, vp, vp]
     L.slc_triangulate_host.argtypes = [vp, vp, vp, vp]
+    L.slc_triangulate_uv_device.argtypes = [vp, vp, vp, vp, vp, vp]
+    L.slc_triangulate_uv_host.argtypes = [vp, vp, vp, vp, vp]
     L.slc_dyna_track_device.argtypes = [vp, vp, i32, i32, vp, vp, vp, vp, C.POINTER(SlcDynaParity), vp]
     L.slc_dyna_track_host.argtypes = [vp, vp, i32, i32, vp, vp, vp, vp, C.POINTER(SlcDynaParity)]
     L.slc_eval_phase_host.argtypes = [vp, vp, vp, C.c_int64, vp, vp]
@@ -339,6 +341,18 @@ class Reconstructor:
         xyzw = np.empty((cfg.height, cfg.width, 4), np.float32)
         mask = np.empty((cfg.height, cfg.width), np.uint8)
         self._check(self.lib.slc_triangulate_host(self.h, proj_u.ctypes.data, xyzw.ctypes.data, mask.ctypes.data))
+        return xyzw, mask
+
+    def triangulate_uv(self, proj_u: np.ndarray, proj_v: np.ndarray):
+        """[EXT] least-squares triangulation from the projector column and row planes (f64)."""
+        cfg = self.cfg
+        proj_u = np.ascontiguousarray(proj_u, dtype=np.float64)
+        proj_v = np.ascontiguousarray(proj_v, dtype=np.float64)
+        assert proj_u.shape == (cfg.height, cfg.width) and proj_v.shape == proj_u.shape
+        xyzw = np.empty((cfg.height, cfg.width, 4), np.float32)
+        mask = np.empty((cfg.height, cfg.width), np.uint8)
+        self._check(self.lib.slc_triangulate_uv_host(self.h, proj_u.ctypes.data, proj_v.ctypes.data, xyzw.ctypes.data,
+                                                     mask.ctypes.data))
         return xyzw, mask
 
     # -- dynamic frames -----------------------------------------------------

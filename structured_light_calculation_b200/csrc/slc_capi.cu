@@ -402,6 +402,8 @@ int slc_set_calibration(slc_context* ctx, const double cam[9], const double pro[
     p.B = fufv * P[11];       // :152
     p.P00 = P[0]; p.P01 = P[1]; p.fufvP02 = fufv * P[2];     // :159-161
     p.P20 = P[8]; p.P21 = P[9]; p.fufvP22 = fufv * P[10];    // :162-164
+    p.E = fufv * P[7];                                        // [EXT] row 1 of P, same construction
+    p.P10 = P[4]; p.P11 = P[5]; p.fufvP12 = fufv * P[6];
 
     // f32 coefficients of the same rational map, divided through by fu*fv:
     // C(u,v) = fv*P00*(u-cu) + fu*P01*(v-cv) + fu*fv*P02, D likewise with row 2.
@@ -649,6 +651,44 @@ int slc_triangulate_host(slc_context* ctx, const double* h_proj_u, float* h_xyzw
     SLC_CUDA(ctx, slc::launch_triangulate(ctx->kp, (const double*)ctx->d_scratch_in, (float*)ctx->d_scratch_out,
                                           (uint8_t*)ctx->d_scratch_aux, ctx->stream));
     ctx->launches++;
+    SLC_CUDA(ctx, cudaMemcpyAsync(h_xyzw, ctx->d_scratch_out, npx * 16, cudaMemcpyDeviceToHost, ctx->stream));
+    SLC_CUDA(ctx, cudaMemcpyAsync(h_mask, ctx->d_scratch_aux, npx, cudaMemcpyDeviceToHost, ctx->stream));
+    SLC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SLC_OK;
+}
+
+/* ---- [EXT] over-determined (u, v) triangulation ---------------------------- */
+int slc_triangulate_uv_device(slc_context* ctx, const double* d_proj_u, const double* d_proj_v, float* d_xyzw,
+                              uint8_t* d_mask, void* cuda_stream)
+{
+    int rc = check_ready(ctx, d_proj_u, d_xyzw, d_mask, 1);
+    if (rc != SLC_OK) return rc;
+    if (!d_proj_v) return fail(ctx, SLC_ERR_INVALID_ARG, "NULL ProjectorV plane");
+    SLC_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+    cudaStream_t st = cuda_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : ctx->stream;
+    SLC_CUDA(ctx, slc::launch_triangulate_uv(ctx->kp, d_proj_u, d_proj_v, d_xyzw, d_mask, st));
+    ctx->launches++;
+    return SLC_OK;
+}
+
+int slc_triangulate_uv_host(slc_context* ctx, const double* h_proj_u, const double* h_proj_v, float* h_xyzw,
+                            uint8_t* h_mask)
+{
+    int rc = check_ready(ctx, h_proj_u, h_xyzw, h_mask, 1);
+    if (rc != SLC_OK) return rc;
+    if (!h_proj_v) return fail(ctx, SLC_ERR_INVALID_ARG, "NULL ProjectorV plane");
+    SLC_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+    const size_t npx = (size_t)ctx->kp.npx;
+    rc = ensure_scratch(ctx, &ctx->d_scratch_in, &ctx->scratch_in_bytes, 2 * npx * sizeof(double));
+    if (rc == SLC_OK) rc = ensure_scratch(ctx, &ctx->d_scratch_out, &ctx->scratch_out_bytes, npx * 16);
+    if (rc == SLC_OK) rc = ensure_scratch(ctx, &ctx->d_scratch_aux, &ctx->scratch_aux_bytes, npx * sizeof(int16_t));
+    if (rc != SLC_OK) return rc;
+    double* d_u = static_cast<double*>(ctx->d_scratch_in);
+    double* d_v = d_u + npx;
+    SLC_CUDA(ctx, cudaMemcpyAsync(d_u, h_proj_u, npx * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    SLC_CUDA(ctx, cudaMemcpyAsync(d_v, h_proj_v, npx * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    rc = slc_triangulate_uv_device(ctx, d_u, d_v, (float*)ctx->d_scratch_out, (uint8_t*)ctx->d_scratch_aux, ctx->stream);
+    if (rc != SLC_OK) return rc;
     SLC_CUDA(ctx, cudaMemcpyAsync(h_xyzw, ctx->d_scratch_out, npx * 16, cudaMemcpyDeviceToHost, ctx->stream));
     SLC_CUDA(ctx, cudaMemcpyAsync(h_mask, ctx->d_scratch_aux, npx, cudaMemcpyDeviceToHost, ctx->stream));
     SLC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

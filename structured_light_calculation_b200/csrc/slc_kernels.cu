@@ -423,6 +423,46 @@ triangulate_kernel(const __grid_constant__ KParams p, const double* __restrict__
     mask[idx] = (uint8_t)valid;
 }
 
+// [EXT] SURVEY 8(f) rank 4: both projector coordinates decoded (vertical and horizontal patterns;
+// the reference only has the m_vertical switch of its Gray decoder, CDecodeGray.cpp:182-185, and never
+// uses row 1 of P).  Each coordinate gives one linear equation in z, built exactly like the
+// reference's (CCalculation.cpp:159-164,686-687) from its row of P:
+//     (c0 - c2*U) z = B*U - A          (c2*V ... E for the projector row)
+// and z is their least-squares solution (a1*b1 + a2*b2) / (a1^2 + a2^2).  All in f64, one operation per
+// intrinsic, so the oracle's C restatement is matched bit for bit.
+__global__ void __launch_bounds__(kBlock)
+triangulate_uv_kernel(const __grid_constant__ KParams p, const double* __restrict__ proj_u,
+                      const double* __restrict__ proj_v, float4* __restrict__ xyzw, uint8_t* __restrict__ mask)
+{
+    const long long idx = (long long)blockIdx.x * kBlock + threadIdx.x;
+    if (idx >= p.npx) return;
+    const int v = (int)(idx / p.W);
+    const int u = (int)(idx - (long long)v * p.W);
+    const double U = proj_u[idx], V = proj_v[idx];
+    float x = 0.f, y = 0.f, z = 0.f;
+    int valid = 0;
+    if (U != 0.0 && V != 0.0) {
+        const double du = __dmul_rn(__dsub_rn((double)u, p.cu), p.fv);
+        const double dv = __dmul_rn(__dsub_rn((double)v, p.cv), p.fu);
+        const double c0 = __dadd_rn(__dadd_rn(__dmul_rn(du, p.P00), __dmul_rn(dv, p.P01)), p.fufvP02);
+        const double c1 = __dadd_rn(__dadd_rn(__dmul_rn(du, p.P10), __dmul_rn(dv, p.P11)), p.fufvP12);
+        const double c2 = __dadd_rn(__dadd_rn(__dmul_rn(du, p.P20), __dmul_rn(dv, p.P21)), p.fufvP22);
+        const double a1 = __dsub_rn(c0, __dmul_rn(c2, U)), b1 = __dsub_rn(__dmul_rn(p.B, U), p.A);
+        const double a2 = __dsub_rn(c1, __dmul_rn(c2, V)), b2 = __dsub_rn(__dmul_rn(p.B, V), p.E);
+        const double num = __dadd_rn(__dmul_rn(a1, b1), __dmul_rn(a2, b2));
+        const double den = __dadd_rn(__dmul_rn(a1, a1), __dmul_rn(a2, a2));
+        const double zd = __ddiv_rn(num, den);
+        valid = !((zd < p.fov_min) || (zd > p.fov_max));
+        if (valid) {
+            z = (float)zd;
+            x = (float)__ddiv_rn(__dmul_rn(zd, __dsub_rn((double)u, p.cu)), p.fu);
+            y = (float)__ddiv_rn(__dmul_rn(zd, __dsub_rn((double)v, p.cv)), p.fv);
+        }
+    }
+    xyzw[idx] = make_float4(x, y, z, (float)U);
+    mask[idx] = (uint8_t)valid;
+}
+
 // Parity hook: the vector kernel's arctangent + offset arithmetic (safe-range
 // divisions) on caller-supplied (sin, cos) sums.
 __global__ void __launch_bounds__(kBlock)
@@ -590,6 +630,15 @@ cudaError_t launch_triangulate(const KParams& p, const double* d_proj_u, float* 
     const long long blocks = (p.npx + kBlock - 1) / kBlock;
     triangulate_kernel<<<(unsigned)blocks, kBlock, 0, stream>>>(p, d_proj_u, reinterpret_cast<float4*>(d_xyzw),
                                                                 d_mask);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_triangulate_uv(const KParams& p, const double* d_proj_u, const double* d_proj_v, float* d_xyzw,
+                                  uint8_t* d_mask, cudaStream_t stream)
+{
+    const long long blocks = (p.npx + kBlock - 1) / kBlock;
+    triangulate_uv_kernel<<<(unsigned)blocks, kBlock, 0, stream>>>(p, d_proj_u, d_proj_v,
+                                                                   reinterpret_cast<float4*>(d_xyzw), d_mask);
     return cudaGetLastError();
 }
 

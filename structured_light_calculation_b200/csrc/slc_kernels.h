@@ -26,6 +26,9 @@ cudaError_t launch_decode_phase(const KParams& p, const uint8_t* d_planes, doubl
 cudaError_t launch_triangulate(const KParams& p, const double* d_proj_u, float* d_xyzw, uint8_t* d_mask,
                                cudaStream_t stream);
 
+cudaError_t launch_triangulate_uv(const KParams& p, const double* d_proj_u, const double* d_proj_v, float* d_xyzw,
+                                  uint8_t* d_mask, cudaStream_t stream);
+
 cudaError_t launch_eval_phase(const float* d_s, const float* d_c, long long n, float Tf, float* d_deg, float* d_pix,
                               cudaStream_t stream);
 

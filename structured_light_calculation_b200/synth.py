@@ -29,6 +29,7 @@ class Scene:
     U: np.ndarray        # [H,W] f64 true projector column
     lit: np.ndarray      # [H,W] bool: projector column inside [0, PW)
     albedo: np.ndarray   # [H,W] f64 in (0,1]
+    V: np.ndarray = None  # [H,W] f64 true projector row (row 1 of P; the reference never decodes it)
 
 
 def make_scene(cfg: StackConfig, cal: Calibration, plane_z: float = 60.0) -> Scene:
@@ -62,6 +63,7 @@ def make_scene(cfg: StackConfig, cal: Calibration, plane_z: float = 60.0) -> Sce
     num = Xh @ P[0]
     den = Xh @ P[2]
     U = num / den
+    V = (Xh @ P[1]) / den
     lit = (U >= 0.0) & (U < cfg.projector_width)
     # smooth albedo field in [0.25, 1] plus one low-albedo patch
     yy = v / H
@@ -69,7 +71,7 @@ def make_scene(cfg: StackConfig, cal: Calibration, plane_z: float = 60.0) -> Sce
     albedo = 0.625 + 0.375 * np.sin(2 * np.pi * (3 * xx + 0.3)) * np.cos(2 * np.pi * (2 * yy + 0.1))
     albedo = np.broadcast_to(albedo, (H, W)).copy()
     albedo[int(0.70 * H): int(0.80 * H), int(0.10 * W): int(0.25 * W)] = 0.02
-    return Scene(z=z, xyz=xyz, U=U, lit=lit, albedo=albedo)
+    return Scene(z=z, xyz=xyz, U=U, lit=lit, albedo=albedo, V=V)
 
 
 def gray_code(n: np.ndarray) -> np.ndarray:
@@ -77,15 +79,17 @@ def gray_code(n: np.ndarray) -> np.ndarray:
 
 
 def render_stack(cfg: StackConfig, scene: Scene, noise_sigma: float = 1.0, seed: int = 1234,
-                 ambient: float = 6.0, hi: float = 235.0, amp: float = 105.0) -> np.ndarray:
-    """Return the plane-major stack [2G+N][H][W] u8 for one frame set."""
+                 ambient: float = 6.0, hi: float = 235.0, amp: float = 105.0, horizontal: bool = False) -> np.ndarray:
+    """Return the plane-major stack [2G+N][H][W] u8 for one frame set.  horizontal=True renders the
+    patterns along the projector ROWS instead (cfg.projector_width is then the projector height and
+    cfg.gray_digits the horizontal digit count, what SetNumDigit(n, false) selects)."""
     H, W, G, N = cfg.height, cfg.width, cfg.gray_digits, cfg.phase_steps
     gp, T = cfg.gray_period, cfg.phase_period
     rng = np.random.Generator(np.random.PCG64(seed))
     planes = np.empty((cfg.planes, H, W), dtype=np.uint8)
-    U = scene.U
+    U = scene.V if horizontal else scene.U
     alb = scene.albedo
-    lit = scene.lit
+    lit = (scene.lit & (U >= 0.0) & (U < cfg.projector_width)) if horizontal else scene.lit
     kbin = np.clip(np.floor(U / gp), 0, (1 << G) - 1).astype(np.int64)
     g = gray_code(kbin)
 
