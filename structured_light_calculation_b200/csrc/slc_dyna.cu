@@ -365,7 +365,7 @@ struct DynaOut {
 // (C, D, the x / y factors, the output pointers) is computed once, pointers advance by a constant
 // stride per frame, deltaP comes from a shared-memory table addressed with one 32-bit add, the
 // optional planes are template parameters, and the rare f64 re-solve is out of line.
-constexpr int kLutN = 2 * 9 * 19 + 1;               // 3x3 sums of deltas in [-19, 19]: [-171, 171]
+constexpr int kLutN = 2 * 9 * 31 + 1;               // 3x3 sums of deltas; window <= 33: offsets in [-16, 15], deltas in [-31, 31]
 
 __device__ __forceinline__ double lds_f64(uint32_t addr)
 {

@@ -447,8 +447,11 @@ def test_dynamic_frames_match_oracle(built_library, oracle, base_calibration, W,
     cal, scene, planes = make_case(cfg, base_calibration, noise=1.0, seed=9)
     first = oracle_run(oracle, cfg, cal, planes)
     frames = synth.render_dyna_frames(cfg, cal, n_frames, stripe_period=14.0, z_step=0.4, noise_sigma=1.5)
-    if window == 33:   # exercise ties: large flat regions
+    if window == 33:   # exercise ties: large flat regions; and the largest deltas the window allows
         frames[:, : H // 2, :] = 100
+        ramp = (np.arange(W) * 7 % 256).astype(np.uint8)
+        frames[1, H // 2:, :] = ramp                      # extremum at one end of the window ...
+        frames[2, H // 2:, :] = ramp[::-1]                # ... then at the other: |delta| up to 31
     if W in (512, 204):  # ties inside the fast path: flat, saturated and two-level regions
         frames[:, : H // 3, : W // 2] = 255
         frames[1:, H // 3: H // 2, W // 4:] = 0
