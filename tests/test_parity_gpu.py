@@ -486,6 +486,33 @@ def test_dynamic_frames_match_oracle(built_library, oracle, base_calibration, W,
         assert moved > 0     # the tracker saw motion
 
 
+def test_dynamic_frames_long_sequence(built_library, oracle, base_calibration):
+    """40 frames through one launch of the frame-walking kernel: the accumulated ProjectorU and the
+    masks stay bit-exact to the last frame (the plane oscillates, so U returns and leaves again)."""
+    from structured_light_calculation_b200 import synth
+    from structured_light_calculation_b200.configs import StackConfig
+    W, H, n_frames = 136, 72, 40
+    cfg = StackConfig(W, H, 1280, 6, 4)
+    cal, scene, planes = make_case(cfg, base_calibration, noise=1.0, seed=9)
+    first = oracle_run(oracle, cfg, cal, planes)
+    pool = synth.render_dyna_frames(cfg, cal, 6, stripe_period=14.0, z_step=0.4, noise_sigma=1.5)
+    frames = np.stack([pool[k if k < 6 else 10 - k] for k in (f % 10 for f in range(n_frames))])
+    ocfg = oracle.make_config(W, H, cfg.projector_width, cfg.gray_digits, cfg.phase_steps)
+    ocal = oracle.make_calib(cal.cam, cal.pro, cal.R, cal.T)
+    want = oracle.dyna_sequence(ocfg, ocal, first["proj_u"], first["z"], frames, 21)
+    rec = _reconstructor(cfg, cal)
+    got = rec.dyna_track(frames, first["proj_u"], window=21, parity=True)
+    rec.close()
+    tol = XYZ_REL_TOL * (cfg.fov_max - cfg.fov_min)
+    for f, w in enumerate(want):
+        assert bits_equal(got["proj_u"][f], w["proj_u"]), f"ProjectorU frame {f + 1}"
+        assert bits_equal(got["delta_p"][f], w["delta_p"]), f"deltaP frame {f + 1}"
+        assert bits_equal(got["mask"][f], w["mask"]), f"mask frame {f + 1}"
+        assert np.abs(got["xyzw"][f, ..., 2] - w["z"]).max() <= tol
+        assert np.abs(got["delta_z"][f] - w["delta_z"]).max() <= 2 * tol
+    assert any((w["delta_p"] != 0).any() for w in want)
+
+
 def test_smoke_entry_point(built_library):
     import __graft_entry__
     __graft_entry__.smoke()
