@@ -500,6 +500,9 @@ const VecEntry kVecTable[] = {
     SLC_VEC(16, 9, 4),  SLC_VEC(16, 7, 4), SLC_VEC(16, 8, 4), SLC_VEC(16, 0, 0),
     SLC_VEC(4, 9, 4),   SLC_VEC(4, 7, 4), SLC_VEC(4, 8, 4),  SLC_VEC(4, 6, 4), SLC_VEC(4, 8, 8), SLC_VEC(4, 10, 12),
     SLC_VEC(4, 5, 0),   SLC_VEC(4, 6, 0),   SLC_VEC(4, 7, 0),   SLC_VEC(4, 8, 0),   SLC_VEC(4, 9, 0),   SLC_VEC(4, 10, 0),
+    // the remaining legal depths (CDecodeGray.cpp:39: 1..16), so that no geometry falls back to run-time loops
+    SLC_VEC(4, 1, 0),   SLC_VEC(4, 2, 0),   SLC_VEC(4, 3, 0),   SLC_VEC(4, 4, 0),   SLC_VEC(4, 11, 0),  SLC_VEC(4, 12, 0),
+    SLC_VEC(4, 13, 0),  SLC_VEC(4, 14, 0),  SLC_VEC(4, 15, 0),  SLC_VEC(4, 16, 0),
     SLC_VEC(4, 0, 0),
 };
 
