@@ -189,3 +189,29 @@ def test_whole_program_writes_the_reference_programs_bytes(ref, built_library, b
         name = "iFrame.txt" if f == 0 else f"cFrame{f}.txt"
         assert (out / name).read_bytes() == want["clouds"][f], name
     assert len(want["clouds"][0]) > 1000
+
+
+@pytest.mark.gpu
+def test_baseline_config0_full_size_against_reference_binary(ref, built_library, base_calibration):
+    """BASELINE configs[0] as stated: one 1280x1024 stack, 7-bit Gray + 4-step, decoded and triangulated
+    by the reference's own CPU path -- here its compiled sources -- against the fused kernel."""
+    from structured_light_calculation_b200 import capi
+    from structured_light_calculation_b200.configs import CONFIGS
+    cfg = CONFIGS["config1"]
+    cal, scene, planes = make_case(cfg, base_calibration, noise=1.0, seed=7)
+    ws = ref.Workspace(cfg, cal, planes)
+    want = ws.run_first()
+    ws.close()
+    rec = capi.Reconstructor(cfg, device=0, max_batch=1, num_slots=1)
+    rec.set_calibration(cal)
+    got = rec.reconstruct(planes, parity=True)
+    rec.close()
+    assert bits_equal(got["kbin"][0].astype(np.float64) * cfg.gray_period, want["gray"])
+    assert bits_equal(got["phase_pix"][0].astype(np.float64), want["phase"])
+    assert bits_equal(got["proj_u"][0], want["projU"])
+    ref_mask = ((want["projU"] != 0) & (want["z"] >= cfg.fov_min) & (want["z"] <= cfg.fov_max)).astype(np.uint8)
+    assert bits_equal(got["mask"][0], ref_mask) and ref_mask.mean() > 0.8
+    tol = XYZ_REL_TOL * (cfg.fov_max - cfg.fov_min)
+    errs = [float(np.abs(got["xyzw"][0, ..., ch] - want[k]).max()) for ch, k in enumerate("xyz")]
+    print("configs[0] max |dx|, |dy|, |dz| vs the reference binary:", errs)
+    assert max(errs) <= tol
