@@ -238,6 +238,12 @@ int slc_bmp_parse(const void *file_bytes, int64_t n_bytes, slc_bmp_info *info);
  * device: row flip, padding removal, palette / BGR -> gray.  Asynchronous. */
 int slc_bmp_unpack_device(slc_context *ctx, const uint8_t *d_pixels, const slc_bmp_info *info,
                           uint8_t *d_plane, void *cuda_stream);
+/* The same for a whole set of files in ONE launch: pixel array i (d_pixels is a HOST array of n_files
+ * device pointers, infos a host array) -> plane i of d_stack (u8 [n_files][H][W]; every file must have
+ * the context's camera size).  This is the loop of CCalculation::FillFirstProjectorU
+ * (CCalculation.cpp:536-557) over images that are already in device memory.  Asynchronous. */
+int slc_bmp_unpack_batch_device(slc_context *ctx, const uint8_t *const *d_pixels, const slc_bmp_info *infos,
+                                int32_t n_files, uint8_t *d_stack, void *cuda_stream);
 /* The whole file from host memory to a host plane (upload, unpack, download; synchronous): what
  * the file-backed CSensor hands to SetMat. */
 int slc_bmp_decode_host(slc_context *ctx, const void *h_file_bytes, int64_t n_bytes, uint8_t *h_plane,

@@ -1,8 +1,13 @@
 #!/usr/bin/env python
 """A/B of dyna_fused_kernel launch shapes in ONE process (one set of inputs, one GPU):
-for every variant letter the library's SLC_DYNA_FUSED switch knows, check 3 frames against the
-CPU oracle (mask and f32(U) bit-exact, z in tolerance) and time whole sequences with CUDA events.
-Per-kernel times come from the ncu launch list of the same command.
+for every variant name, set SLC_DYNA_FUSED, check 3 frames against the CPU oracle (mask and f32(U)
+bit-exact, z in tolerance) and time whole sequences with CUDA events.  Per-kernel times come from
+the ncu launch list of the same command (profiles/r01_dyna_ab_launches.csv).
+
+The variants lived in a temporary patch of launch_dyna_fused() that read SLC_DYNA_FUSED
+(o = the shipped kernel, a-e / p2-p6 = the shapes and prefetch schemes DESIGN.md 9.1 lists); none
+was faster, so the patch was dropped and the shipped library ignores the variable: run against it,
+every name times the shipped kernel.  Kept as the harness for the next attempt.
 
     python profiles/ab_dyna_fused.py [variants, default "abcde"] [frames, default 100]
 """

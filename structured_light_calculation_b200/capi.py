@@ -134,6 +134,7 @@ def load_library():
     i64p = C.POINTER(C.c_int64)
     L.slc_bmp_parse.argtypes = [vp, C.c_int64, C.POINTER(SlcBmpInfo)]
     L.slc_bmp_unpack_device.argtypes = [vp, vp, C.POINTER(SlcBmpInfo), vp, vp]
+    L.slc_bmp_unpack_batch_device.argtypes = [vp, C.POINTER(vp), C.POINTER(SlcBmpInfo), i32, vp, vp]
     L.slc_bmp_decode_host.argtypes = [vp, vp, C.c_int64, vp, i32, i32]
     L.slc_load_bmp_planes.argtypes = [vp, C.POINTER(C.c_char_p), i32, vp]
     L.slc_pointcloud_text_device.argtypes = [vp, vp, C.c_uint32, vp, C.c_int64, i64p, i64p, vp]
@@ -398,6 +399,14 @@ class Reconstructor:
         eh, ew = expect_shape if expect_shape else (0, 0)
         self._check(self.lib.slc_bmp_decode_host(self.h, file_bytes, len(file_bytes), out.ctypes.data, ew, eh))
         return out
+
+    def bmp_unpack_batch_device(self, d_pixels, infos, d_stack: int, stream: int = 0):
+        """Pixel arrays already on the device (d_pixels: device addresses, infos: SlcBmpInfo of each file)
+        -> planes 0..n-1 of the u8 [n][H][W] stack at d_stack, one launch (slc_bmp_unpack_batch_device)."""
+        n = len(d_pixels)
+        ptrs = (C.c_void_p * n)(*[int(p) for p in d_pixels])
+        arr = (SlcBmpInfo * n)(*infos)
+        self._check(self.lib.slc_bmp_unpack_batch_device(self.h, ptrs, arr, n, d_stack, stream))
 
     def load_bmp_planes(self, paths, d_stack: int):
         arr = (C.c_char_p * len(paths))(*[os.fsencode(p) for p in paths])

@@ -859,6 +859,39 @@ int slc_bmp_unpack_device(slc_context* ctx, const uint8_t* d_pixels, const slc_b
     return bmp_unpack(ctx, d_pixels, info, d_plane, st);
 }
 
+int slc_bmp_unpack_batch_device(slc_context* ctx, const uint8_t* const* d_pixels, const slc_bmp_info* infos,
+                                int32_t n_files, uint8_t* d_stack, void* cuda_stream)
+{
+    if (!ctx) return SLC_ERR_INVALID_ARG;
+    if (!d_pixels || !infos || !d_stack || n_files < 0) return fail(ctx, SLC_ERR_INVALID_ARG, "NULL argument or n_files < 0");
+    if (n_files == 0) return SLC_OK;
+    std::vector<slc::BmpPlane> planes((size_t)n_files);
+    const size_t npx = (size_t)ctx->kp.npx;
+    for (int i = 0; i < n_files; i++) {
+        const slc_bmp_info& f = infos[i];
+        if (!d_pixels[i]) return fail(ctx, SLC_ERR_INVALID_ARG, "file %d: NULL pixel array", i);
+        if (f.width != ctx->kp.W || f.height != ctx->kp.H)
+            return fail(ctx, SLC_ERR_INVALID_ARG, "file %d is %dx%d, the context's camera is %dx%d", i, f.width, f.height,
+                        ctx->kp.W, ctx->kp.H);
+        if ((f.bits_per_pixel != 8 && f.bits_per_pixel != 24 && f.bits_per_pixel != 32) ||
+            (int64_t)f.row_stride < ((int64_t)f.width * f.bits_per_pixel + 7) / 8)
+            return fail(ctx, SLC_ERR_INVALID_ARG, "file %d: not a parsed slc_bmp_info (bpp %d, stride %d)", i,
+                        f.bits_per_pixel, f.row_stride);
+        slc::BmpPlane& a = planes[(size_t)i];
+        a.px = d_pixels[i];
+        a.out = d_stack + (size_t)i * npx;
+        a.width = f.width; a.height = f.height; a.bpp = f.bits_per_pixel; a.top_down = f.top_down;
+        a.row_stride = f.row_stride; a.identity = f.palette_is_identity;
+        a.wide = 0; a.pad_ = 0;
+        std::memcpy(a.gray, f.gray, 256);
+    }
+    SLC_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+    cudaStream_t st = cuda_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : ctx->stream;
+    SLC_CUDA(ctx, slc::launch_bmp_unpack_batch(planes.data(), n_files, st));
+    ctx->launches += (n_files + slc::kBmpBatchMax - 1) / slc::kBmpBatchMax;
+    return SLC_OK;
+}
+
 int slc_bmp_decode_host(slc_context* ctx, const void* h_file_bytes, int64_t n_bytes, uint8_t* h_plane,
                         int32_t expect_width, int32_t expect_height)
 {

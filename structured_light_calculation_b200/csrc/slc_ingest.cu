@@ -55,6 +55,96 @@ bmp_unpack_kernel(const uint8_t* __restrict__ px, const __grid_constant__ BmpArg
     }
 }
 
+
+// ---- a whole set of files in one launch (grid.y = file) ------------------------------------
+// 2.3 MB planes are a few microseconds of HBM time each, so one launch per plane is bound by launch
+// latency; a frame set (2G+N files) unpacked by one grid runs at memory speed.  8-bit files whose
+// rows can be written as aligned uint4 take the wide path: a thread owns 16 consecutive pixels, reads
+// them as aligned 32-bit words (the pixel array of a .bmp starts 1078 bytes into the file, so it is
+// seldom better aligned than that), realigns with funnel shifts, maps through the palette if it is
+// not the identity, and writes one uint4.
+struct BmpBatchArgs {
+    BmpPlane plane[kBmpBatchMax];
+};
+
+__device__ __forceinline__ uint32_t lut4(const uint8_t* g, uint32_t w)
+{
+    return (uint32_t)g[w & 0xFFu] | ((uint32_t)g[(w >> 8) & 0xFFu] << 8) | ((uint32_t)g[(w >> 16) & 0xFFu] << 16) |
+           ((uint32_t)g[w >> 24] << 24);
+}
+
+__global__ void __launch_bounds__(256)
+bmp_unpack_batch_kernel(const __grid_constant__ BmpBatchArgs b)
+{
+    __shared__ uint8_t s_gray[256];
+    const BmpPlane& a = b.plane[blockIdx.y];
+    const bool lut = (a.bpp == 8) && !a.identity;
+    if (lut) {
+        s_gray[threadIdx.x] = a.gray[threadIdx.x];
+        __syncthreads();
+    }
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (a.wide) {
+        const int per_row = a.width >> 4;
+        if (i >= (long long)per_row * a.height) return;
+        const int y = (int)(i / per_row), x0 = (int)(i - (long long)y * per_row) << 4;
+        const int srow = a.top_down ? y : a.height - 1 - y;
+        const uint8_t* src = a.px + (long long)srow * a.row_stride + x0;
+        const unsigned mis = (unsigned)(reinterpret_cast<uintptr_t>(src) & 3u);      // the same for every item of a file
+        uint32_t w[4];
+        if (mis == 0u) {
+            const uint32_t* q = reinterpret_cast<const uint32_t*>(src);
+#pragma unroll
+            for (int k = 0; k < 4; k++) w[k] = __ldg(q + k);
+        } else {
+            // the fifth word reaches up to 3 bytes past the 16 this item needs: the very last item of
+            // the pixel array must not read it
+            const bool at_end = (srow == a.height - 1) && (x0 + 16 >= a.row_stride);
+            const uint32_t* q = reinterpret_cast<const uint32_t*>(src - mis);
+            uint32_t r[5];
+#pragma unroll
+            for (int k = 0; k < 4; k++) r[k] = __ldg(q + k);
+            if (!at_end) {
+                r[4] = __ldg(q + 4);
+            } else {
+                r[4] = 0u;
+                for (unsigned k = 0; k < mis; k++) r[4] |= (uint32_t)src[16 - mis + k] << (8 * k);
+            }
+#pragma unroll
+            for (int k = 0; k < 4; k++) w[k] = __funnelshift_r(r[k], r[k + 1], 8 * mis);
+        }
+        if (lut) {
+#pragma unroll
+            for (int k = 0; k < 4; k++) w[k] = lut4(s_gray, w[k]);
+        }
+        st_stream_u4(a.out + (long long)y * a.width + x0, make_uint4(w[0], w[1], w[2], w[3]));
+        return;
+    }
+    // any other flavour: 4 pixels per thread, as bmp_unpack_kernel
+    const int quads = (a.width + 3) / 4;
+    if (i >= (long long)quads * a.height) return;
+    const int y = (int)(i / quads), x0 = (int)(i - (long long)y * quads) * 4;
+    const uint8_t* src = a.px + (long long)(a.top_down ? y : a.height - 1 - y) * a.row_stride;
+    uint32_t v[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int x = min(x0 + k, a.width - 1);
+        if (a.bpp == 8) {
+            const uint32_t idx = src[x];
+            v[k] = a.identity ? idx : s_gray[idx];
+        } else {
+            const uint8_t* q = src + x * (a.bpp >> 3);
+            v[k] = bgr_gray(q[0], q[1], q[2]);
+        }
+    }
+    uint8_t* dst = a.out + (long long)y * a.width + x0;
+    if (x0 + 4 <= a.width && ((reinterpret_cast<uintptr_t>(dst) & 3) == 0)) {
+        *reinterpret_cast<uint32_t*>(dst) = v[0] | (v[1] << 8) | (v[2] << 16) | (v[3] << 24);
+    } else {
+        for (int k = 0; k < 4 && x0 + k < a.width; k++) dst[k] = (uint8_t)v[k];
+    }
+}
+
 }  // namespace
 
 cudaError_t launch_bmp_unpack(const uint8_t* d_pixels, int width, int height, int bpp, int top_down, int row_stride,
@@ -67,6 +157,28 @@ cudaError_t launch_bmp_unpack(const uint8_t* d_pixels, int width, int height, in
     const long long n = (long long)((width + 3) / 4) * height;
     bmp_unpack_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(d_pixels, a, d_plane);
     return cudaGetLastError();
+}
+
+// planes[i].wide is set here; every plane of one launch shares the grid, sized for the largest.
+cudaError_t launch_bmp_unpack_batch(const BmpPlane* planes, int n, cudaStream_t stream)
+{
+    for (int done = 0; done < n; done += kBmpBatchMax) {
+        const int m = (n - done) < kBmpBatchMax ? (n - done) : kBmpBatchMax;
+        BmpBatchArgs b;
+        long long items = 1;
+        for (int k = 0; k < m; k++) {
+            BmpPlane& a = b.plane[k];
+            a = planes[done + k];
+            a.wide = (a.bpp == 8) && (a.width % 16 == 0) && ((reinterpret_cast<uintptr_t>(a.out) & 15) == 0) ? 1 : 0;
+            const long long it = a.wide ? (long long)(a.width / 16) * a.height : (long long)((a.width + 3) / 4) * a.height;
+            if (it > items) items = it;
+        }
+        dim3 grid((unsigned)((items + 255) / 256), (unsigned)m, 1);
+        bmp_unpack_batch_kernel<<<grid, 256, 0, stream>>>(b);
+        const cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
 }
 
 }  // namespace slc

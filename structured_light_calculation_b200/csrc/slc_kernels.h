@@ -58,6 +58,16 @@ cudaError_t launch_format_g6(const double* d_values, long long n, unsigned flags
 // input ingest (slc_ingest.cu)
 cudaError_t launch_bmp_unpack(const uint8_t* d_pixels, int width, int height, int bpp, int top_down, int row_stride,
                               int identity, const uint8_t* gray256, uint8_t* d_plane, cudaStream_t stream);
+// one file of a batched unpack: pixel array in, one [height][width] u8 plane out
+struct BmpPlane {
+    const uint8_t* px;
+    uint8_t* out;
+    int width, height, bpp, top_down, row_stride, identity;
+    int wide, pad_;               // set by launch_bmp_unpack_batch
+    uint8_t gray[256];
+};
+constexpr int kBmpBatchMax = 64;  // files per launch (the descriptors travel as kernel parameters: 64 x 304 B < 32 KB)
+cudaError_t launch_bmp_unpack_batch(const BmpPlane* planes, int n, cudaStream_t stream);
 
 // tuning hook (bench / tests): pixels per thread of the vector kernel, 4 / 8 / 16
 void set_default_pixels_per_thread(int pxt);

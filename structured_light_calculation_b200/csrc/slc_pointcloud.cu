@@ -4,11 +4,14 @@
 // The reference walks the image u outer / v inner, skips pixels whose z is outside
 // [FOV_MIN_DISTANCE, FOV_MAX_DISTANCE] and writes "x y z\n" with ostream << double, i.e.
 // printf("%g") with precision 6.  Here that is a variable-length record emission:
-//   pass 1  pc_emit_kernel<MODE, false>  length of every record (kept, one byte each), summed per block
+//   pass 1  pc_emit_kernel<MODE, false>  everything that needs f64, once per number: x, y, z and their six
+//                                        exactly rounded digits + decimal exponent (decode_g6), kept as
+//                                        three 32-bit codes + the line length per record (one uint4);
+//                                        lengths summed per block
 //   pass 2  pc_emit_kernel<MODE, true>   each block sums the counts of the blocks before it, scans the
-//                                        lengths, produces every record straight into its place in a
-//                                        shared-memory chunk laid out at the output's own 16-byte
-//                                        phase, and writes the chunk as uint4
+//                                        lengths, writes the characters of every record (emit_g6: integer
+//                                        work only) straight into its place in a shared-memory chunk laid
+//                                        out at the output's own 16-byte phase, and writes the chunk as uint4
 // MODE 0 records are text lines formatted from f64 x, y, z -- recomputed from the f64
 // ProjectorU plane in the reference's operation order (:686-687, :761-767), so the text is
 // byte-identical to what the reference's doubles print; MODE 1 records are packed float3 xyz
@@ -24,7 +27,6 @@ constexpr int kPcIters = 8;                      // records per thread
 constexpr int kPcChunk = kPcThreads * kPcIters;  // records per block
 constexpr int kPcMaxNum = 13;                    // "-1.23457e-005"
 constexpr int kPcMaxLine = 3 * kPcMaxNum + 2 + 2;   // two blanks, "\r\n"
-constexpr int kPcSlot = 44;                      // per-thread staging slot (11 words: conflict-free)
 
 __constant__ double c_pow10[23] = {1e0,  1e1,  1e2,  1e3,  1e4,  1e5,  1e6,  1e7,  1e8,  1e9,  1e10, 1e11,
                                    1e12, 1e13, 1e14, 1e15, 1e16, 1e17, 1e18, 1e19, 1e20, 1e21, 1e22};
@@ -62,21 +64,21 @@ __device__ __forceinline__ Scaled scale10(double ax, int k)
 }
 
 // printf("%g", x) (precision 6, the C locale) == what `ostream << double` writes with default
-// flags.  exp3: three exponent digits (the MSVC 2013 CRT the reference was built with) instead
-// of two.  Returns the number of characters written (<= 13).
-__device__ int format_g6(double x, char* out, bool exp3)
+// flags, in two steps so that the expensive one runs once per number:
+//   decode_g6  the exactly rounded six significant digits D and the decimal exponent E, packed in
+//              32 bits:  [19:0] D (100000..999999; 0 = zero, 1 = inf, 2 = nan), [29:20] E + 512, [31] sign
+//   len_g6 / emit_g6   the characters %g makes of (D, E): notation, stripped zeros, exponent field.
+//              exp3: three exponent digits (the MSVC 2013 CRT the reference was built with), not two.
+constexpr unsigned kG6Zero = 0u, kG6Inf = 1u, kG6Nan = 2u;
+
+__device__ __forceinline__ unsigned decode_g6(double x)
 {
-    int n = 0;
     const unsigned long long bits = (unsigned long long)__double_as_longlong(x);
-    if (bits >> 63) out[n++] = '-';
+    const unsigned sign = (unsigned)(bits >> 63) << 31;
     const double ax = fabs(x);
-    if (ax == 0.0) { out[n++] = '0'; return n; }
+    if (ax == 0.0) return sign | kG6Zero;
     const int bexp = (int)((bits >> 52) & 0x7FFu);
-    if (bexp == 0x7FF) {
-        const bool is_nan = (bits & 0xFFFFFFFFFFFFFull) != 0ull;
-        out[n++] = is_nan ? 'n' : 'i'; out[n++] = is_nan ? 'a' : 'n'; out[n++] = is_nan ? 'n' : 'f';
-        return n;
-    }
+    if (bexp == 0x7FF) return sign | (((bits & 0xFFFFFFFFFFFFFull) != 0ull) ? kG6Nan : kG6Inf);
     // decimal exponent: 10^E <= |x| < 10^(E+1); the estimate is within one, then one fix-up
     int E = (int)floor((double)(bexp == 0 ? -1074 + (63 - __clzll((long long)(bits & 0xFFFFFFFFFFFFFull)))
                                           : bexp - 1023) * 0.30102999566398120);
@@ -90,8 +92,46 @@ __device__ int format_g6(double x, char* out, bool exp3)
     unsigned D = (unsigned)fl;
     if (t > 0.0 || (t == 0.0 && (D & 1u))) D++;
     if (D >= 1000000u) { D = 100000u; E++; }
-    int nd = 6;                                                 // significant digits left after %g strips zeros
-    { unsigned q = D; while (nd > 1 && q % 10u == 0u) { q /= 10u; nd--; } }
+    return sign | ((unsigned)(E + 512) << 20) | D;
+}
+
+// significant digits left after %g strips trailing zeros
+__device__ __forceinline__ int g6_digits(unsigned D)
+{
+    int nd = 6;
+    unsigned q = D;
+    while (nd > 1 && q % 10u == 0u) { q /= 10u; nd--; }
+    return nd;
+}
+
+__device__ __forceinline__ int len_g6(unsigned code, bool exp3)
+{
+    const int neg = (int)(code >> 31);
+    const unsigned D = code & 0xFFFFFu;
+    if (D < 100000u) return neg + (D == kG6Zero ? 1 : 3);
+    const int E = (int)((code >> 20) & 0x3FFu) - 512;
+    const int nd = g6_digits(D);
+    if (E < -4 || E >= 6) {
+        const int ae = E < 0 ? -E : E;
+        return neg + 1 + (nd > 1 ? nd : 0) + 2 + ((exp3 || ae >= 100) ? 3 : 2);
+    }
+    if (E >= 0) return neg + (E + 1) + (nd > E + 1 ? nd - E : 0);
+    return neg + 1 - E + nd;
+}
+
+__device__ __forceinline__ int emit_g6(unsigned code, char* out, bool exp3)
+{
+    int n = 0;
+    if (code >> 31) out[n++] = '-';
+    unsigned D = code & 0xFFFFFu;
+    if (D < 100000u) {
+        if (D == kG6Zero) { out[n++] = '0'; return n; }
+        const bool is_nan = (D == kG6Nan);
+        out[n++] = is_nan ? 'n' : 'i'; out[n++] = is_nan ? 'a' : 'n'; out[n++] = is_nan ? 'n' : 'f';
+        return n;
+    }
+    const int E = (int)((code >> 20) & 0x3FFu) - 512;
+    const int nd = g6_digits(D);
     auto next_digit = [&]() -> char { const unsigned d = D / 100000u; D = (D - d * 100000u) * 10u; return (char)('0' + d); };
     if (E < -4 || E >= 6) {
         out[n++] = next_digit();
@@ -120,6 +160,8 @@ __device__ int format_g6(double x, char* out, bool exp3)
     return n;
 }
 
+__device__ __forceinline__ int format_g6(double x, char* out, bool exp3) { return emit_g6(decode_g6(x), out, exp3); }
+
 struct PcArgs {
     int W, H;
     long long npx;
@@ -129,27 +171,35 @@ struct PcArgs {
     const uint8_t* mask;             // MODE 1
     unsigned flags;
     unsigned long long* block_sums;  // [2 * n_blocks + 2]: (bytes, records) per block, totals last
-    uint8_t* rec_len;                // MODE 0: length of every record, written by pass 1 for pass 2
+    uint4* rec;                      // MODE 0: (x, y, z) as decode_g6 codes + the line length, written by pass 1 for pass 2
     unsigned char* out;
     unsigned long long capacity;     // bytes
 };
 
-// one line "x y z" + line end of pixel (v, u), or 0 if the reference skips the pixel
-__device__ __forceinline__ int text_line(const KParams& p, double U, int u, int v, char* o, bool exp3, bool crlf)
+// the line "x y z" + line end of pixel (v, u) as three decode_g6 codes and its length (0 if the
+// reference skips the pixel)
+__device__ __forceinline__ uint4 text_line_codes(const KParams& p, double U, int u, int v, bool exp3, bool crlf)
 {
-    if (U == 0.0) return 0;                                        // :678-682
+    if (U == 0.0) return make_uint4(0u, 0u, 0u, 0u);                // :678-682
     const double z = z_exact(p, U, u, v);                          // :686-687
-    if ((z < p.fov_min) || (z > p.fov_max)) return 0;              // :701-704 and :341-345
+    if ((z < p.fov_min) || (z > p.fov_max)) return make_uint4(0u, 0u, 0u, 0u);   // :701-704 and :341-345
     const double x = __ddiv_rn(__dmul_rn(z, __dsub_rn((double)u, p.cu)), p.fu);   // :766
     const double y = __ddiv_rn(__dmul_rn(z, __dsub_rn((double)v, p.cv)), p.fv);   // :767
-    int len = format_g6(x, o, exp3);
+    uint4 r;
+    r.x = decode_g6(x); r.y = decode_g6(y); r.z = decode_g6(z);
+    r.w = (unsigned)(len_g6(r.x, exp3) + len_g6(r.y, exp3) + len_g6(r.z, exp3) + 3 + (crlf ? 1 : 0));
+    return r;
+}
+
+__device__ __forceinline__ void text_line_emit(const uint4& r, char* o, bool exp3, bool crlf)
+{
+    int len = emit_g6(r.x, o, exp3);
     o[len++] = ' ';
-    len += format_g6(y, o + len, exp3);
+    len += emit_g6(r.y, o + len, exp3);
     o[len++] = ' ';
-    len += format_g6(z, o + len, exp3);
+    len += emit_g6(r.z, o + len, exp3);
     if (crlf) o[len++] = '\r';
     o[len++] = '\n';
-    return len;
 }
 
 // inclusive scan of `v` over the block; returns the exclusive prefix, *total = block sum
@@ -180,8 +230,7 @@ template <int MODE, bool WRITE>
 __global__ void __launch_bounds__(kPcThreads)
 pc_emit_kernel(const __grid_constant__ KParams p, const PcArgs a)
 {
-    __shared__ __align__(16) unsigned char s_txt[kPcThreads * kPcMaxLine + 32];
-    __shared__ __align__(16) unsigned char s_slot[(MODE == 0 && !WRITE) ? kPcThreads * kPcSlot : 16];
+    __shared__ __align__(16) unsigned char s_txt[WRITE ? kPcThreads * kPcMaxLine + 32 : 16];
     __shared__ int s_warp[kPcThreads / 32];
     const int t = threadIdx.x;
     const long long base = (long long)blockIdx.x * kPcChunk;
@@ -220,23 +269,24 @@ pc_emit_kernel(const __grid_constant__ KParams p, const PcArgs a)
 
     for (int it = 0; it < kPcIters; it++) {
         const long long i = base + (long long)it * kPcThreads + t;
-        int len = 0, u = 0, v = 0;
+        int len = 0;
         long long px = 0;
+        uint4 rec = make_uint4(0u, 0u, 0u, 0u);
         if (i < a.npx) {
-            if (a.order == 1) { u = (int)(i / a.H); v = (int)(i - (long long)u * a.H); }
-            else { v = (int)(i / a.W); u = (int)(i - (long long)v * a.W); }
-            px = (long long)v * a.W + u;
-            if (MODE == 0) {
-                if (!WRITE) {
-                    // pass 1: format into a scratch slot for the length alone, and remember it
-                    len = text_line(p, a.proj_u[px], u, v, reinterpret_cast<char*>(&s_slot[t * kPcSlot]), exp3, crlf);
-                    a.rec_len[i] = (uint8_t)len;
-                } else {
-                    len = a.rec_len[i];
-                }
+            if (MODE == 0 && WRITE) {
+                rec = __ldcs(a.rec + i);                           // pass 2 never touches U or the calibration
             } else {
-                len = (a.mask[px] != 0) ? 12 : 0;
+                int u, v;
+                if (a.order == 1) { u = (int)(i / a.H); v = (int)(i - (long long)u * a.H); }
+                else { v = (int)(i / a.W); u = (int)(i - (long long)v * a.W); }
+                px = (long long)v * a.W + u;
+                if (MODE == 0) {
+                    // pass 1: everything that needs f64 -- x, y, z and their six exact digits -- once
+                    rec = text_line_codes(p, a.proj_u[px], u, v, exp3, crlf);
+                    __stcs(a.rec + i, rec);
+                }
             }
+            len = (MODE == 0) ? (int)rec.w : ((a.mask[px] != 0) ? 12 : 0);
         }
         int total;
         const int excl = block_exclusive_scan(len, s_warp, &total);
@@ -248,8 +298,8 @@ pc_emit_kernel(const __grid_constant__ KParams p, const PcArgs a)
                 unsigned char* dst = &s_txt[align + excl];
                 if (len) {
                     if (MODE == 0) {
-                        // pass 2: the line is formatted straight into its place in the staged chunk
-                        text_line(p, a.proj_u[px], u, v, reinterpret_cast<char*>(dst), exp3, crlf);
+                        // pass 2: the characters go straight into the line's place in the staged chunk
+                        text_line_emit(rec, reinterpret_cast<char*>(dst), exp3, crlf);
                     } else {
                         // 12-byte records: align + excl is a multiple of 4 (gofs is a multiple of 12 from a 16-aligned base)
                         const float4 q = a.xyzw[px];
@@ -311,7 +361,7 @@ static size_t pointcloud_sums_bytes(long long npx)
 
 size_t pointcloud_scratch_bytes(long long npx)
 {
-    return pointcloud_sums_bytes(npx) + (size_t)npx;      // block sums | one length byte per pixel
+    return pointcloud_sums_bytes(npx) + 16 * (size_t)npx;  // block sums | one uint4 (three number codes, length) per pixel
 }
 
 // mode 0: text lines from d_proj_u; mode 1: float3 of the valid pixels of (d_xyzw, d_mask).
@@ -329,7 +379,7 @@ cudaError_t launch_pointcloud(const KParams& p, int mode, int order, unsigned fl
     a.mask = d_mask;
     a.flags = flags;
     a.block_sums = static_cast<unsigned long long*>(d_scratch);
-    a.rec_len = static_cast<uint8_t*>(d_scratch) + pointcloud_sums_bytes(p.npx);
+    a.rec = reinterpret_cast<uint4*>(static_cast<uint8_t*>(d_scratch) + pointcloud_sums_bytes(p.npx));
     a.out = static_cast<unsigned char*>(d_out);
     a.capacity = capacity;
     if (mode == 0) pc_emit_kernel<0, false><<<blocks, kPcThreads, 0, stream>>>(p, a);

@@ -101,3 +101,63 @@ def test_stack_from_reference_file_layout(tmp_path, built_library, oracle, base_
     for p in (d_stack, d_xyzw, d_mask):
         rec.device_free(p)
     rec.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("W,H", [(64, 24), (200, 30)])       # wide (uint4) path / generic path
+def test_bmp_batch_unpack_matches_decoder_oracle(built_library, base_calibration, W, H):
+    """slc_bmp_unpack_batch_device: a set of files already in device memory -> the plane-major stack
+    in one launch.  Covers every source misalignment (the pixel array of a .bmp starts 1078 bytes
+    into the file), identity and colour palettes, 24-bit, top-down, pixel arrays that end exactly at
+    the end of their allocation, and the bytes around the stack (canaries)."""
+    import torch
+    from oracle.bmp_oracle import decode_bmp_gray
+    from structured_light_calculation_b200 import capi, synth
+    from structured_light_calculation_b200.configs import StackConfig
+    rng = np.random.default_rng(W * 1000 + H)
+    cfg = StackConfig(W, H, 1280, 6, 4)
+    cal, _, _ = make_case(cfg, base_calibration)
+    rec = capi.Reconstructor(cfg, device=0, max_batch=1, num_slots=1)
+    rec.set_calibration(cal)
+    dev = torch.device("cuda", 0)
+    files = []
+    for k in range(9):
+        img = rng.integers(0, 256, (H, W), dtype=np.uint8)
+        data = bytearray(synth.encode_bmp(img, bpp=24 if k == 7 else 8, top_down=(k in (3, 8))))
+        if k in (4, 5):                       # a colour palette: index -> gray through the fixed-point weights
+            pal = rng.integers(0, 256, (256, 4), dtype=np.uint8)
+            data[54:54 + 1024] = pal.tobytes()
+        files.append(bytes(data))
+    infos = [capi.bmp_parse(f) for f in files]
+    want = np.stack([decode_bmp_gray(f) for f in files])
+    keep, ptrs = [], []
+    for k, (f, info) in enumerate(zip(files, infos)):
+        raw = np.frombuffer(f, np.uint8)[info.pixel_offset:]
+        mis = k % 4                           # the pixel array starts `mis` bytes into a tensor and ends with it
+        t = torch.empty(mis + raw.size, dtype=torch.uint8, device=dev)
+        t[mis:].copy_(torch.from_numpy(raw.copy()))
+        keep.append(t)
+        ptrs.append(t.data_ptr() + mis)
+    PAD, CAN = 4096, 0x5A
+    n, npx = len(files), W * H
+    stack = torch.full((n * npx + 2 * PAD,), CAN, dtype=torch.uint8, device=dev)
+    rec.bmp_unpack_batch_device(ptrs, infos, stack.data_ptr() + PAD)
+    rec.synchronize()
+    got = stack[PAD:PAD + n * npx].cpu().numpy().reshape(n, H, W)
+    for k in range(n):
+        assert np.array_equal(got[k], want[k]), f"file {k}"
+    assert bool((stack[:PAD] == CAN).all()) and bool((stack[PAD + n * npx:] == CAN).all())
+    # the single-plane entry point writes the same planes
+    one = torch.empty((H, W), dtype=torch.uint8, device=dev)
+    for k in range(n):
+        rec._check(rec.lib.slc_bmp_unpack_device(rec.h, ptrs[k], infos[k], one.data_ptr(), None))
+        rec.synchronize()
+        assert np.array_equal(one.cpu().numpy(), want[k])
+    # errors: a file of another size, a NULL pixel array
+    other = capi.bmp_parse(synth.encode_bmp(np.zeros((8, 16), np.uint8)))
+    with pytest.raises(capi.SlcError):
+        rec.bmp_unpack_batch_device(ptrs[:1], [other], stack.data_ptr() + PAD)
+    with pytest.raises(capi.SlcError):
+        rec.bmp_unpack_batch_device([0], infos[:1], stack.data_ptr() + PAD)
+    rec.bmp_unpack_batch_device([], [], stack.data_ptr() + PAD)      # empty set: nothing to do
+    rec.close()
