@@ -60,9 +60,11 @@ bmp_unpack_kernel(const uint8_t* __restrict__ px, const __grid_constant__ BmpArg
 // 2.3 MB planes are a few microseconds of HBM time each, so one launch per plane is bound by launch
 // latency; a frame set (2G+N files) unpacked by one grid runs at memory speed.  8-bit files whose
 // rows can be written as aligned uint4 take the wide path: a thread owns 16 consecutive pixels, reads
-// them as aligned 32-bit words (the pixel array of a .bmp starts 1078 bytes into the file, so it is
+// them as aligned vectors (the pixel array of a .bmp starts 1078 bytes into the file, so it is
 // seldom better aligned than that), realigns with funnel shifts, maps through the palette if it is
 // not the identity, and writes one uint4.
+constexpr int kWideItems = 4;
+
 struct BmpBatchArgs {
     BmpPlane plane[kBmpBatchMax];
 };
@@ -83,43 +85,75 @@ bmp_unpack_batch_kernel(const __grid_constant__ BmpBatchArgs b)
         s_gray[threadIdx.x] = a.gray[threadIdx.x];
         __syncthreads();
     }
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (a.wide) {
+        // kWideItems 16-pixel items per thread, all loads first: one item per thread leaves too few
+        // bytes in flight to cover the memory latency (measured 0.60 of the copy bandwidth)
         const int per_row = a.width >> 4;
-        if (i >= (long long)per_row * a.height) return;
-        const int y = (int)(i / per_row), x0 = (int)(i - (long long)y * per_row) << 4;
-        const int srow = a.top_down ? y : a.height - 1 - y;
-        const uint8_t* src = a.px + (long long)srow * a.row_stride + x0;
-        const unsigned mis = (unsigned)(reinterpret_cast<uintptr_t>(src) & 3u);      // the same for every item of a file
-        uint32_t w[4];
-        if (mis == 0u) {
-            const uint32_t* q = reinterpret_cast<const uint32_t*>(src);
+        const long long n_items = (long long)per_row * a.height;
+        const long long i0 = (long long)blockIdx.x * (256 * kWideItems) + threadIdx.x;
+        const unsigned mis = (unsigned)(reinterpret_cast<uintptr_t>(a.px) & 15u);
+        // (row_stride and x0 are multiples of 16 here, so every item of a file has the misalignment of px)
+        uint4 A[kWideItems], B[kWideItems];
+        long long dsto[kWideItems];
 #pragma unroll
-            for (int k = 0; k < 4; k++) w[k] = __ldg(q + k);
-        } else {
-            // the fifth word reaches up to 3 bytes past the 16 this item needs: the very last item of
-            // the pixel array must not read it
-            const bool at_end = (srow == a.height - 1) && (x0 + 16 >= a.row_stride);
-            const uint32_t* q = reinterpret_cast<const uint32_t*>(src - mis);
-            uint32_t r[5];
-#pragma unroll
-            for (int k = 0; k < 4; k++) r[k] = __ldg(q + k);
-            if (!at_end) {
-                r[4] = __ldg(q + 4);
-            } else {
-                r[4] = 0u;
-                for (unsigned k = 0; k < mis; k++) r[4] |= (uint32_t)src[16 - mis + k] << (8 * k);
+        for (int k = 0; k < kWideItems; k++) {
+            const long long i = i0 + 256 * k;
+            dsto[k] = -1;
+            A[k] = B[k] = make_uint4(0u, 0u, 0u, 0u);
+            if (i < n_items) {
+                const int y = (int)(i / per_row), x0 = (int)(i - (long long)y * per_row) << 4;
+                const int srow = a.top_down ? y : a.height - 1 - y;
+                const uint8_t* src = a.px + (long long)srow * a.row_stride + x0;
+                dsto[k] = (long long)y * a.width + x0;
+                const uint4* q = reinterpret_cast<const uint4*>(src - mis);
+                A[k] = __ldg(q);
+                if (mis != 0u) {
+                    // the second vector reaches up to 15 bytes past the 16 this item needs: the very
+                    // last item of the pixel array gathers its tail bytewise instead
+                    const bool at_end = (srow == a.height - 1) && (x0 + 16 == a.width);
+                    if (!at_end) {
+                        B[k] = __ldg(q + 1);
+                    } else {
+                        uint32_t t4[4] = {0u, 0u, 0u, 0u};
+                        for (unsigned m = 0; m < mis; m++) t4[m >> 2] |= (uint32_t)src[16 - mis + m] << (8 * (m & 3));
+                        B[k] = make_uint4(t4[0], t4[1], t4[2], t4[3]);
+                    }
+                }
             }
-#pragma unroll
-            for (int k = 0; k < 4; k++) w[k] = __funnelshift_r(r[k], r[k + 1], 8 * mis);
         }
-        if (lut) {
+        const unsigned bs = 8u * (mis & 3u);
 #pragma unroll
-            for (int k = 0; k < 4; k++) w[k] = lut4(s_gray, w[k]);
+        for (int k = 0; k < kWideItems; k++) {
+            if (dsto[k] < 0) continue;
+            const uint32_t r[8] = {A[k].x, A[k].y, A[k].z, A[k].w, B[k].x, B[k].y, B[k].z, B[k].w};
+            uint32_t w[4];
+            switch (mis >> 2) {               // uniform per file
+            case 0:
+#pragma unroll
+                for (int j = 0; j < 4; j++) w[j] = __funnelshift_r(r[j], r[j + 1], bs);
+                break;
+            case 1:
+#pragma unroll
+                for (int j = 0; j < 4; j++) w[j] = __funnelshift_r(r[j + 1], r[j + 2], bs);
+                break;
+            case 2:
+#pragma unroll
+                for (int j = 0; j < 4; j++) w[j] = __funnelshift_r(r[j + 2], r[j + 3], bs);
+                break;
+            default:
+#pragma unroll
+                for (int j = 0; j < 4; j++) w[j] = __funnelshift_r(r[j + 3], r[j + 4], bs);
+                break;
+            }
+            if (lut) {
+#pragma unroll
+                for (int j = 0; j < 4; j++) w[j] = lut4(s_gray, w[j]);
+            }
+            st_stream_u4(a.out + dsto[k], make_uint4(w[0], w[1], w[2], w[3]));
         }
-        st_stream_u4(a.out + (long long)y * a.width + x0, make_uint4(w[0], w[1], w[2], w[3]));
         return;
     }
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     // any other flavour: 4 pixels per thread, as bmp_unpack_kernel
     const int quads = (a.width + 3) / 4;
     if (i >= (long long)quads * a.height) return;
@@ -169,8 +203,11 @@ cudaError_t launch_bmp_unpack_batch(const BmpPlane* planes, int n, cudaStream_t 
         for (int k = 0; k < m; k++) {
             BmpPlane& a = b.plane[k];
             a = planes[done + k];
-            a.wide = (a.bpp == 8) && (a.width % 16 == 0) && ((reinterpret_cast<uintptr_t>(a.out) & 15) == 0) ? 1 : 0;
-            const long long it = a.wide ? (long long)(a.width / 16) * a.height : (long long)((a.width + 3) / 4) * a.height;
+            a.wide = (a.bpp == 8) && (a.width % 16 == 0) && (a.row_stride % 16 == 0) &&
+                     ((reinterpret_cast<uintptr_t>(a.out) & 15) == 0) ? 1 : 0;
+            // blocks needed, in units of 256 threads: a wide thread takes kWideItems 16-pixel items
+            const long long it = a.wide ? ((long long)(a.width / 16) * a.height + kWideItems - 1) / kWideItems
+                                        : (long long)((a.width + 3) / 4) * a.height;
             if (it > items) items = it;
         }
         dim3 grid((unsigned)((items + 255) / 256), (unsigned)m, 1);
