@@ -148,7 +148,8 @@ int slc_synchronize(slc_context *ctx);
  * (CCalculation.cpp:666-771), for n_stacks independent frame sets, as ONE
  * fused kernel launch.  All pointers are DEVICE pointers; cuda_stream is a
  * cudaStream_t passed as void* (NULL = the context's own stream; the legacy default stream, whose handle is 0, cannot be named).
- * Asynchronous with respect to the host. */
+ * Asynchronous with respect to the host.  n_stacks == 0 is a no-op (SLC_OK, no launch, buffers
+ * may be NULL), here and in slc_reconstruct_host; n_stacks < 0 is SLC_ERR_INVALID_ARG. */
 int slc_reconstruct_device(slc_context *ctx, const uint8_t *d_stack, int32_t n_stacks,
                            float *d_xyzw, uint8_t *d_mask,
                            const slc_parity_planes *d_parity, void *cuda_stream);

@@ -17,6 +17,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <new>
 #include <string>
 #include <vector>
@@ -139,8 +140,9 @@ int check_ready(slc_context* ctx, const void* a, const void* b, const void* c, i
     if (!ctx) return SLC_ERR_INVALID_ARG;
     if (!ctx->calibrated)
         return fail(ctx, SLC_ERR_NOT_INITIALISED, "calibration not set: call slc_set_calibration first");
-    if (!a || !b || !c) return fail(ctx, SLC_ERR_INVALID_ARG, "NULL buffer");
     if (n_stacks < 0) return fail(ctx, SLC_ERR_INVALID_ARG, "n_stacks < 0");
+    if (n_stacks == 0) return SLC_OK;             // an empty batch is a no-op: buffers may be NULL
+    if (!a || !b || !c) return fail(ctx, SLC_ERR_INVALID_ARG, "NULL buffer");
     return SLC_OK;
 }
 
@@ -544,6 +546,7 @@ int slc_reconstruct_host(slc_context* ctx, const uint8_t* h_stack, int32_t n_sta
 {
     int rc = check_ready(ctx, h_stack, h_xyzw, h_mask, n_stacks);
     if (rc != SLC_OK) return rc;
+    if (n_stacks == 0) return SLC_OK;
     SLC_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
     const size_t npx = (size_t)ctx->kp.npx;
     const int chunk = ctx->cfg.max_batch;
@@ -555,7 +558,11 @@ int slc_reconstruct_host(slc_context* ctx, const uint8_t* h_stack, int32_t n_sta
         Slot& s = ctx->slots[slot];
         rc = enqueue_chunk(ctx, s, h_stack + (size_t)done * stack_bytes(ctx), n, h_xyzw + (size_t)done * npx * 4,
                            h_mask + (size_t)done * npx, h_parity, (size_t)done * npx);
-        if (rc != SLC_OK) return rc;
+        if (rc != SLC_OK) {
+            // earlier chunks are still copying into the caller's buffers: drain them before returning
+            for (Slot& q : ctx->slots) { cudaStreamSynchronize(q.stream); q.busy = false; }
+            return rc;
+        }
         slot = (slot + 1) % (int)ctx->slots.size();
     }
     for (Slot& s : ctx->slots) { SLC_CUDA(ctx, cudaStreamSynchronize(s.stream)); s.busy = false; }
@@ -1000,13 +1007,14 @@ int slc_load_bmp_planes(slc_context* ctx, const char* const* paths, int32_t n_fi
             break;
         }
         const size_t raw = (size_t)info.row_stride * info.height;
+        cudaStream_t fs = ctx->stream;
         cudaError_t e = cudaMemcpyAsync(ctx->d_bmp[k], static_cast<uint8_t*>(ctx->h_bmp[k]) + info.pixel_offset, raw,
-                                        cudaMemcpyHostToDevice, ctx->stream);
+                                        cudaMemcpyHostToDevice, fs);
         if (e == cudaSuccess)
             e = slc::launch_bmp_unpack(static_cast<const uint8_t*>(ctx->d_bmp[k]), info.width, info.height, info.bits_per_pixel,
                                        info.top_down, info.row_stride, info.palette_is_identity, info.gray,
-                                       d_stack + (size_t)i * npx, ctx->stream);
-        if (e == cudaSuccess) e = cudaEventRecord(ctx->bmp_done[k], ctx->stream);
+                                       d_stack + (size_t)i * npx, fs);
+        if (e == cudaSuccess) e = cudaEventRecord(ctx->bmp_done[k], fs);
         if (e != cudaSuccess) { rc = fail(ctx, SLC_ERR_CUDA, "BMP upload / unpack failed: %s", cudaGetErrorString(e)); break; }
         ctx->launches++;
         // hand the slot of an older file back to the readers once its upload + unpack are done

@@ -411,6 +411,29 @@ def test_error_paths(built_library, base_calibration):
         capi.Reconstructor(cfg, device=1000)
 
 
+def test_empty_batch_is_a_no_op(built_library, base_calibration):
+    """Zero frame sets: every reconstruct entry point returns SLC_OK without touching a buffer (NULL
+    pointers allowed) or launching anything; a dynamic sequence needs its first frame (n_frames >= 1)."""
+    from structured_light_calculation_b200 import capi
+    from structured_light_calculation_b200.configs import CONFIGS
+    cfg = CONFIGS["config1"].with_(width=64, height=32)
+    cal, _, _ = make_case(cfg, base_calibration)
+    rec = _reconstructor(cfg, cal)
+    before = rec.launch_count()
+    out = rec.reconstruct(np.zeros((0, cfg.planes, cfg.height, cfg.width), np.uint8), parity=True)
+    assert out["xyzw"].shape == (0, cfg.height, cfg.width, 4) and out["mask"].shape == (0, cfg.height, cfg.width)
+    rec._check(rec.lib.slc_reconstruct_host(rec.h, None, 0, None, None, None))
+    rec._check(rec.lib.slc_reconstruct_device(rec.h, None, 0, None, None, None, None))
+    assert rec.launch_count() == before
+    with pytest.raises(capi.SlcError):
+        rec._check(rec.lib.slc_reconstruct_host(rec.h, None, 1, None, None, None))       # NULL buffers, one frame set
+    with pytest.raises(capi.SlcError):
+        rec._check(rec.lib.slc_reconstruct_device(rec.h, None, -1, None, None, None, None))
+    with pytest.raises(capi.SlcError):
+        rec._check(rec.lib.slc_dyna_track_device(rec.h, None, 0, 21, None, None, None, None, None, None))
+    rec.close()
+
+
 @pytest.mark.parametrize("name", ["config1", "config2", "config3", "config5"])
 def test_full_size_properties(built_library, oracle, base_calibration, name):
     """BASELINE sizes: full parity against the (multi-threaded) oracle on one stack, plus
