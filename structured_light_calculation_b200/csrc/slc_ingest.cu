@@ -33,7 +33,7 @@ bmp_unpack_kernel(const uint8_t* __restrict__ px, const __grid_constant__ BmpArg
     const int quads = (a.width + 3) / 4;
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (long long)quads * a.height) return;
-    const int y = (int)(i / quads), x0 = (int)(i - (long long)y * quads) * 4;
+    const int y = (int)((unsigned)i / (unsigned)quads), x0 = (int)((unsigned)i - (unsigned)y * (unsigned)quads) * 4;   // i < W * H < 2^31
     const uint8_t* src = px + (long long)(a.top_down ? y : a.height - 1 - y) * a.row_stride;
     uint32_t v[4];
 #pragma unroll
@@ -101,7 +101,9 @@ bmp_unpack_batch_kernel(const __grid_constant__ BmpBatchArgs b)
             dsto[k] = -1;
             A[k] = B[k] = make_uint4(0u, 0u, 0u, 0u);
             if (i < n_items) {
-                const int y = (int)(i / per_row), x0 = (int)(i - (long long)y * per_row) << 4;
+                // fewer than 2^27 items (W * H < 2^31): 32-bit division, not the 64-bit emulation
+                const unsigned yu = (unsigned)i / (unsigned)per_row;
+                const int y = (int)yu, x0 = (int)((unsigned)i - yu * (unsigned)per_row) << 4;
                 const int srow = a.top_down ? y : a.height - 1 - y;
                 const uint8_t* src = a.px + (long long)srow * a.row_stride + x0;
                 dsto[k] = (long long)y * a.width + x0;
@@ -157,7 +159,7 @@ bmp_unpack_batch_kernel(const __grid_constant__ BmpBatchArgs b)
     // any other flavour: 4 pixels per thread, as bmp_unpack_kernel
     const int quads = (a.width + 3) / 4;
     if (i >= (long long)quads * a.height) return;
-    const int y = (int)(i / quads), x0 = (int)(i - (long long)y * quads) * 4;
+    const int y = (int)((unsigned)i / (unsigned)quads), x0 = (int)((unsigned)i - (unsigned)y * (unsigned)quads) * 4;   // i < W * H < 2^31
     const uint8_t* src = a.px + (long long)(a.top_down ? y : a.height - 1 - y) * a.row_stride;
     uint32_t v[4];
 #pragma unroll

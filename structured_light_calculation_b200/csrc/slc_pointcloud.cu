@@ -104,13 +104,13 @@ __device__ __forceinline__ int g6_digits(unsigned D)
     return nd;
 }
 
-__device__ __forceinline__ int len_g6(unsigned code, bool exp3)
+// characters emit_g6 writes for (code, nd = g6_digits(D))
+__device__ __forceinline__ int len_g6(unsigned code, int nd, bool exp3)
 {
     const int neg = (int)(code >> 31);
     const unsigned D = code & 0xFFFFFu;
     if (D < 100000u) return neg + (D == kG6Zero ? 1 : 3);
     const int E = (int)((code >> 20) & 0x3FFu) - 512;
-    const int nd = g6_digits(D);
     if (E < -4 || E >= 6) {
         const int ae = E < 0 ? -E : E;
         return neg + 1 + (nd > 1 ? nd : 0) + 2 + ((exp3 || ae >= 100) ? 3 : 2);
@@ -160,7 +160,37 @@ __device__ __forceinline__ int emit_g6(unsigned code, char* out, bool exp3)
     return n;
 }
 
-__device__ __forceinline__ int format_g6(double x, char* out, bool exp3) { return emit_g6(decode_g6(x), out, exp3); }
+// emit_g6 without loops for the numbers a point cloud is made of: 1 <= |x| < 10^6, i.e. fixed notation
+// "ddd.ddd".  The six ASCII digits are made once (two divisions by 1000 / 100 / 10 as multiply-shift) and
+// every character is one predicated byte store at a position known from (E, nd): digit k sits at
+// k + (k > E), the point at E + 1, and digits at or beyond max(nd, E + 1) are not written.  Anything
+// else (|x| < 1, exponent notation, zero, inf, nan) takes emit_g6.  nd = g6_digits(D).
+__device__ __forceinline__ int emit_g6_fast(unsigned code, int nd, char* out, bool exp3)
+{
+    const unsigned D = code & 0xFFFFFu;
+    const int E = (int)((code >> 20) & 0x3FFu) - 512;
+    if (D < 100000u || (unsigned)E > 5u) return emit_g6(code, out, exp3);
+    const unsigned hi = D / 1000u, lo = D - hi * 1000u;
+    const unsigned a0 = hi / 100u, r0 = hi - a0 * 100u, b0 = r0 / 10u, c0 = r0 - b0 * 10u;
+    const unsigned a1 = lo / 100u, r1 = lo - a1 * 100u, b1 = r1 / 10u, c1 = r1 - b1 * 10u;
+    const unsigned dg[6] = {a0, b0, c0, a1, b1, c1};
+    const int neg = (int)(code >> 31);
+    if (neg) out[0] = '-';
+    char* q = out + neg;
+    const int last = max(nd, E + 1);                 // digits written (those past nd are the zeros of D)
+#pragma unroll
+    for (int k = 0; k < 6; k++)
+        if (k < last) q[k + (k > E ? 1 : 0)] = (char)('0' + dg[k]);
+    const int point = (nd > E + 1) ? 1 : 0;
+    if (point) q[E + 1] = '.';
+    return neg + last + point;
+}
+
+__device__ __forceinline__ int format_g6(double x, char* out, bool exp3)
+{
+    const unsigned code = decode_g6(x);
+    return emit_g6_fast(code, g6_digits(code & 0xFFFFFu), out, exp3);
+}
 
 struct PcArgs {
     int W, H;
@@ -176,8 +206,8 @@ struct PcArgs {
     unsigned long long capacity;     // bytes
 };
 
-// the line "x y z" + line end of pixel (v, u) as three decode_g6 codes and its length (0 if the
-// reference skips the pixel)
+// the line "x y z" + line end of pixel (v, u) as three decode_g6 codes and (length, digit counts); length 0
+// if the reference skips the pixel
 __device__ __forceinline__ uint4 text_line_codes(const KParams& p, double U, int u, int v, bool exp3, bool crlf)
 {
     if (U == 0.0) return make_uint4(0u, 0u, 0u, 0u);                // :678-682
@@ -187,17 +217,21 @@ __device__ __forceinline__ uint4 text_line_codes(const KParams& p, double U, int
     const double y = __ddiv_rn(__dmul_rn(z, __dsub_rn((double)v, p.cv)), p.fv);   // :767
     uint4 r;
     r.x = decode_g6(x); r.y = decode_g6(y); r.z = decode_g6(z);
-    r.w = (unsigned)(len_g6(r.x, exp3) + len_g6(r.y, exp3) + len_g6(r.z, exp3) + 3 + (crlf ? 1 : 0));
+    // w: [5:0] line length, [8:6] / [11:9] / [14:12] significant digits of x / y / z after zero stripping
+    const unsigned ndx = (unsigned)g6_digits(r.x & 0xFFFFFu), ndy = (unsigned)g6_digits(r.y & 0xFFFFFu),
+                   ndz = (unsigned)g6_digits(r.z & 0xFFFFFu);
+    r.w = (unsigned)(len_g6(r.x, (int)ndx, exp3) + len_g6(r.y, (int)ndy, exp3) + len_g6(r.z, (int)ndz, exp3) + 3 + (crlf ? 1 : 0)) |
+          (ndx << 6) | (ndy << 9) | (ndz << 12);
     return r;
 }
 
 __device__ __forceinline__ void text_line_emit(const uint4& r, char* o, bool exp3, bool crlf)
 {
-    int len = emit_g6(r.x, o, exp3);
+    int len = emit_g6_fast(r.x, (int)((r.w >> 6) & 7u), o, exp3);
     o[len++] = ' ';
-    len += emit_g6(r.y, o + len, exp3);
+    len += emit_g6_fast(r.y, (int)((r.w >> 9) & 7u), o + len, exp3);
     o[len++] = ' ';
-    len += emit_g6(r.z, o + len, exp3);
+    len += emit_g6_fast(r.z, (int)((r.w >> 12) & 7u), o + len, exp3);
     if (crlf) o[len++] = '\r';
     o[len++] = '\n';
 }
@@ -276,17 +310,19 @@ pc_emit_kernel(const __grid_constant__ KParams p, const PcArgs a)
             if (MODE == 0 && WRITE) {
                 rec = __ldcs(a.rec + i);                           // pass 2 never touches U or the calibration
             } else {
-                int u, v;
-                if (a.order == 1) { u = (int)(i / a.H); v = (int)(i - (long long)u * a.H); }
-                else { v = (int)(i / a.W); u = (int)(i - (long long)v * a.W); }
+                // npx < 2^31 (slc_create): 32-bit division, not the 64-bit emulation
+                const unsigned ii = (unsigned)i;
+                unsigned u, v;
+                if (a.order == 1) { u = ii / (unsigned)a.H; v = ii - u * (unsigned)a.H; }
+                else { v = ii / (unsigned)a.W; u = ii - v * (unsigned)a.W; }
                 px = (long long)v * a.W + u;
                 if (MODE == 0) {
                     // pass 1: everything that needs f64 -- x, y, z and their six exact digits -- once
-                    rec = text_line_codes(p, a.proj_u[px], u, v, exp3, crlf);
+                    rec = text_line_codes(p, a.proj_u[px], (int)u, (int)v, exp3, crlf);
                     __stcs(a.rec + i, rec);
                 }
             }
-            len = (MODE == 0) ? (int)rec.w : ((a.mask[px] != 0) ? 12 : 0);
+            len = (MODE == 0) ? (int)(rec.w & 63u) : ((a.mask[px] != 0) ? 12 : 0);
         }
         int total;
         const int excl = block_exclusive_scan(len, s_warp, &total);
