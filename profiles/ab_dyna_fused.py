@@ -45,7 +45,8 @@ def main():
     ocfg = O.make_config(cfg.width, cfg.height, cfg.projector_width, cfg.gray_digits, cfg.phase_steps)
     ocal = O.make_calib(cal.cam, cal.pro, cal.R, cal.T)
     first = O.reconstruct(ocfg, ocal, stack)
-    want = O.dyna_sequence(ocfg, ocal, first["proj_u"], first["z"], frames[:4], window)
+    NCHK = 12
+    want = O.dyna_sequence(ocfg, ocal, first["proj_u"], first["z"], frames[:NCHK + 1], window)
     tol = 1e-5 * (cfg.fov_max - cfg.fov_min)
 
     d_frames = torch.empty((S, F, cfg.height, cfg.width), dtype=torch.uint8, device=dev)
@@ -64,18 +65,24 @@ def main():
                                   d_mask[i].data_ptr(), d_dz[i].data_ptr(), window, stream.cuda_stream)
 
     for v in variants:
-        os.environ["SLC_DYNA_FUSED"] = v
+        # "name" -> SLC_DYNA_FUSED=name (the dropped kernel-shape patch); "pipe:C:P:K" -> SLC_DYNA_PIPE="C,P,K"
+        # (chunks of C frames, strip stream priority P, strip blocks per SM capped at K; the pipeline experiment)
+        os.environ.pop("SLC_DYNA_PIPE", None)
+        if v.startswith("pipe:"):
+            os.environ["SLC_DYNA_PIPE"] = v[5:].replace(":", ",")
+        else:
+            os.environ["SLC_DYNA_FUSED"] = v
         d_xyzw.zero_(); d_mask.zero_(); d_dz.zero_()
         for _ in range(3):
             step()
         torch.cuda.synchronize()
-        xyzw = d_xyzw[0, :3].cpu().numpy(); mask = d_mask[0, :3].cpu().numpy(); dz = d_dz[0, :3].cpu().numpy()
+        xyzw = d_xyzw[0, :NCHK].cpu().numpy(); mask = d_mask[0, :NCHK].cpu().numpy(); dz = d_dz[0, :NCHK].cpu().numpy()
         ok = all(np.array_equal(mask[f], want[f]["mask"]) and
                  np.array_equal(xyzw[f, ..., 3], want[f]["proj_u"].astype(np.float32)) and
-                 np.abs(xyzw[f, ..., 2] - want[f]["z"]).max() <= tol for f in range(3))
+                 np.abs(xyzw[f, ..., 2] - want[f]["z"]).max() <= tol for f in range(NCHK))
         zprev = first["z"]
         dz_err = 0.0
-        for f in range(3):
+        for f in range(NCHK):
             dz_err = max(dz_err, float(np.abs(dz[f] - (want[f]["z"] - zprev)).max()))
             zprev = want[f]["z"]
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
