@@ -63,6 +63,7 @@ struct slc_context {
     void* d_pc_scratch = nullptr;  size_t pc_scratch_bytes = 0;  // point cloud: block sums
     void* d_pc_in = nullptr;       size_t pc_in_bytes = 0;       // point cloud: staging for the host entry points
     void* d_pc_out = nullptr;      size_t pc_out_bytes = 0;
+    void* h_pc_totals = nullptr;                                   // point cloud: pinned (bytes, records) read-back
     void* d_bmp[kBmpSlots] = {};   size_t bmp_bytes[kBmpSlots] = {};     // ingest: raw file staging (device)
     void* h_bmp[kBmpSlots] = {};   size_t h_bmp_bytes[kBmpSlots] = {};   // ingest: raw file staging (pinned)
     cudaEvent_t bmp_done[kBmpSlots] = {};
@@ -331,6 +332,7 @@ void slc_destroy(slc_context* ctx)
     cudaFree(ctx->d_scratch_in); cudaFree(ctx->d_scratch_out); cudaFree(ctx->d_scratch_aux);
     cudaFree(ctx->d_strips); cudaFree(ctx->d_dsums); cudaFree(ctx->d_dyna);
     cudaFree(ctx->d_pc_scratch); cudaFree(ctx->d_pc_in); cudaFree(ctx->d_pc_out);
+    if (ctx->h_pc_totals) cudaFreeHost(ctx->h_pc_totals);
     for (int k = 0; k < kBmpSlots; k++) {
         cudaFree(ctx->d_bmp[k]);
         if (ctx->h_bmp[k]) cudaFreeHost(ctx->h_bmp[k]);
@@ -1050,8 +1052,10 @@ int pointcloud_run(slc_context* ctx, int mode, int order, uint32_t flags, const 
     SLC_CUDA(ctx, slc::launch_pointcloud(ctx->kp, mode, order, flags, d_proj_u, d_xyzw, d_mask, d_out,
                                          (unsigned long long)capacity_bytes, ctx->d_pc_scratch, &d_totals, st));
     ctx->launches += 2;
-    unsigned long long totals[2] = {0, 0};
-    SLC_CUDA(ctx, cudaMemcpyAsync(totals, d_totals, sizeof(totals), cudaMemcpyDeviceToHost, st));
+    // the counts come back through a pinned word pair (a pageable destination costs a staged copy per call)
+    if (!ctx->h_pc_totals) SLC_CUDA(ctx, cudaHostAlloc(&ctx->h_pc_totals, 2 * sizeof(unsigned long long), cudaHostAllocDefault));
+    unsigned long long* totals = static_cast<unsigned long long*>(ctx->h_pc_totals);
+    SLC_CUDA(ctx, cudaMemcpyAsync(totals, d_totals, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
     SLC_CUDA(ctx, cudaStreamSynchronize(st));
     if (bytes) *bytes = (int64_t)totals[0];
     if (records) *records = (int64_t)totals[1];
