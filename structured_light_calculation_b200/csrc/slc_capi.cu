@@ -874,7 +874,12 @@ int slc_bmp_unpack_batch_device(slc_context* ctx, const uint8_t* const* d_pixels
     if (!ctx) return SLC_ERR_INVALID_ARG;
     if (!d_pixels || !infos || !d_stack || n_files < 0) return fail(ctx, SLC_ERR_INVALID_ARG, "NULL argument or n_files < 0");
     if (n_files == 0) return SLC_OK;
-    std::vector<slc::BmpPlane> planes((size_t)n_files);
+    std::vector<slc::BmpPlane> planes;
+    try {
+        planes.resize((size_t)n_files);
+    } catch (const std::exception&) {             // no exception leaves the C ABI
+        return fail(ctx, SLC_ERR_OUT_OF_MEMORY, "host allocation for %d file descriptors failed", n_files);
+    }
     const size_t npx = (size_t)ctx->kp.npx;
     for (int i = 0; i < n_files; i++) {
         const slc_bmp_info& f = infos[i];
@@ -927,7 +932,18 @@ int slc_bmp_decode_host(slc_context* ctx, const void* h_file_bytes, int64_t n_by
     return SLC_OK;
 }
 
+static int load_bmp_planes_impl(slc_context* ctx, const char* const* paths, int32_t n_files, uint8_t* d_stack);
+
 int slc_load_bmp_planes(slc_context* ctx, const char* const* paths, int32_t n_files, uint8_t* d_stack)
+{
+    try {
+        return load_bmp_planes_impl(ctx, paths, n_files, d_stack);
+    } catch (const std::exception& ex) {          // no exception leaves the C ABI (host allocations before any thread starts)
+        return fail(ctx, SLC_ERR_OUT_OF_MEMORY, "slc_load_bmp_planes: %s", ex.what());
+    }
+}
+
+static int load_bmp_planes_impl(slc_context* ctx, const char* const* paths, int32_t n_files, uint8_t* d_stack)
 {
     if (!ctx) return SLC_ERR_INVALID_ARG;
     if (!paths || !d_stack || n_files < 0) return fail(ctx, SLC_ERR_INVALID_ARG, "NULL argument or n_files < 0");
@@ -985,12 +1001,19 @@ int slc_load_bmp_planes(slc_context* ctx, const char* const* paths, int32_t n_fi
         }
     };
     std::vector<std::thread> threads;
-    for (int r = 0; r < R; r++) threads.emplace_back(reader, r);
     auto stop = [&] {
         { std::lock_guard<std::mutex> lk(mu); abort_all = true; }
         cv.notify_all();
-        for (auto& th : threads) th.join();
+        for (auto& th : threads)
+            if (th.joinable()) th.join();
     };
+    try {
+        threads.reserve((size_t)R);
+        for (int r = 0; r < R; r++) threads.emplace_back(reader, r);
+    } catch (const std::exception& ex) {          // no exception leaves the C ABI; readers already started are joined
+        stop();
+        return fail(ctx, SLC_ERR_STATE, "could not start the reader threads: %s", ex.what());
+    }
     int rc = SLC_OK;
     for (int i = 0; i < n_files && rc == SLC_OK; i++) {
         const int k = i % K;

@@ -68,6 +68,7 @@ constexpr int kWideItems = 4;
 struct BmpBatchArgs {
     BmpPlane plane[kBmpBatchMax];
 };
+static_assert(sizeof(BmpBatchArgs) <= 32764, "kernel parameters are limited to 32764 bytes (CUDA 12.1+, sm_70+)");
 
 __device__ __forceinline__ uint32_t lut4(const uint8_t* g, uint32_t w)
 {
