@@ -9,8 +9,9 @@
 // or 4): one PXT-byte load per u8 plane, so a warp reads 32*PXT contiguous
 // bytes of every plane (whole 128 B lines).  Results are float4 per pixel; to
 // keep the stores whole-line too, each warp transposes its 32*PXT float4
-// through a private, XOR-swizzled (bank-conflict-free) shared-memory tile and
-// writes 512 contiguous bytes per store instruction.  Loads are
+// through a private shared-memory tile padded to an odd row stride (PXT+1
+// slots: bank-conflict-free both ways) and writes 512 contiguous bytes per
+// store instruction.  Loads are
 // ld.global.nc.L1::no_allocate, stores st.global.cs: every
 // byte is touched exactly once.  Nothing here is a contraction, so tensor
 // cores / TMEM are not used; the bound is HBM bandwidth.
