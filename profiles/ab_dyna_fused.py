@@ -68,7 +68,10 @@ def main():
         # "name" -> SLC_DYNA_FUSED=name (the dropped kernel-shape patch); "pipe:C:P:K" -> SLC_DYNA_PIPE="C,P,K"
         # (chunks of C frames, strip stream priority P, strip blocks per SM capped at K; the pipeline experiment)
         os.environ.pop("SLC_DYNA_PIPE", None)
-        if v.startswith("pipe:"):
+        os.environ.pop("SLC_DYNA_LEAN", None)
+        if v.startswith("lean:"):          # row constants recomputed per frame; 3 or 4 blocks per SM
+            os.environ["SLC_DYNA_LEAN"] = v[5:]
+        elif v.startswith("pipe:"):
             os.environ["SLC_DYNA_PIPE"] = v[5:].replace(":", ",")
         else:
             os.environ["SLC_DYNA_FUSED"] = v
