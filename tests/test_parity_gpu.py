@@ -113,6 +113,40 @@ def test_fused_kernel_matches_oracle(built_library, oracle, base_calibration, ca
     del capi
 
 
+def test_random_geometries_match_oracle(built_library, oracle, base_calibration):
+    """A seeded sweep over geometries nobody picked by hand: Gray depth 1..12, 3..16 phase steps, widths
+    that are and are not multiples of 4 / 8 / 16 (vector and scalar kernels), projector widths with and
+    without a remainder in PW / 2^G, noise and modulation thresholds.  Every output is held to the same bar
+    as the named cases, and the kernel instances without parity planes must reproduce the checked one."""
+    from structured_light_calculation_b200.configs import StackConfig
+    rng = np.random.default_rng(20261018)
+    done = 0
+    for trial in range(40):
+        G = int(rng.integers(1, 13))
+        N = int(rng.integers(3, 17))
+        gp = int(rng.integers(1, 12))
+        PW = gp * (1 << G) + int(rng.integers(0, 2)) * int(rng.integers(0, 1 << G))   # sometimes not a multiple of 2^G
+        if PW > 8192:
+            continue
+        W = int(rng.choice([40, 52, 64, 72, 97, 128, 136, 200]))
+        H = int(rng.integers(9, 49))
+        mod = float(rng.choice([0.0, 0.0, 3.0, 10.0]))
+        noise = float(rng.choice([0.0, 1.0, 2.5]))
+        cfg = StackConfig(W, H, PW, G, N, modulation_min=mod, name=f"rand{trial}")
+        cal, scene, planes = make_case(cfg, base_calibration, noise=noise, seed=1000 + trial)
+        rec = _reconstructor(cfg, cal)
+        got = rec.reconstruct(planes, parity=True)
+        check_fast_modes(rec, planes, got)
+        rec.close()
+        want = oracle_run(oracle, cfg, cal, planes)
+        try:
+            check_parity(got, want, cfg)
+        except AssertionError as e:
+            raise AssertionError(f"trial {trial}: W={W} H={H} PW={PW} G={G} N={N} mod={mod} noise={noise}: {e}") from e
+        done += 1
+    assert done >= 25
+
+
 @pytest.mark.parametrize("flags_name", ["z_fp64", "scalar"])
 def test_kernel_modes_match_oracle(built_library, oracle, base_calibration, flags_name):
     from structured_light_calculation_b200 import capi
