@@ -546,6 +546,54 @@ def test_dynamic_frames_match_oracle(built_library, oracle, base_calibration, W,
         assert moved > 0     # the tracker saw motion
 
 
+def test_dynamic_frames_random_sweep(built_library, oracle, base_calibration):
+    """Seeded sweep of the dynamic path: widths that take the fused kernel (W % 8 == 0) and the generic
+    kernels, every odd window 3..33, heights around the tile sizes, and image content made of rendered
+    stripes, pure noise, constant and two-level regions (ties in the window minimum / maximum)."""
+    from structured_light_calculation_b200 import synth
+    from structured_light_calculation_b200.configs import StackConfig
+    rng = np.random.default_rng(977)
+    for trial in range(14):
+        W = int(rng.choice([64, 72, 96, 128, 136, 150, 168, 256, 260, 384]))
+        H = int(rng.choice([40, 47, 64, 65, 72, 96, 130]))
+        window = int(rng.choice(np.arange(3, 35, 2)))
+        if W <= window or H <= window:
+            continue
+        n_frames = int(rng.integers(2, 7))
+        cfg = StackConfig(W, H, 1280, 6, 4)
+        cal, scene, planes = make_case(cfg, base_calibration, noise=1.0, seed=300 + trial)
+        first = oracle_run(oracle, cfg, cal, planes)
+        frames = synth.render_dyna_frames(cfg, cal, n_frames, stripe_period=float(rng.choice([9.0, 14.0, 23.0])),
+                                          z_step=0.4, noise_sigma=1.5)
+        kind = trial % 4
+        if kind == 1:      # pure noise: extrema anywhere in the window, large deltas
+            frames = rng.integers(0, 256, frames.shape, dtype=np.uint8)
+        elif kind == 2:    # coarse levels: many equal column sums
+            frames = (frames // 64 * 64).astype(np.uint8)
+        elif kind == 3:    # flat and saturated blocks next to stripes
+            frames[:, : H // 2, : W // 2] = 255
+            frames[1:, H // 2:, W // 3: 2 * W // 3] = 0
+        ocfg = oracle.make_config(W, H, cfg.projector_width, cfg.gray_digits, cfg.phase_steps)
+        ocal = oracle.make_calib(cal.cam, cal.pro, cal.R, cal.T)
+        want = oracle.dyna_sequence(ocfg, ocal, first["proj_u"], first["z"], frames, window)
+        rec = _reconstructor(cfg, cal)
+        got = rec.dyna_track(frames, first["proj_u"], window=window, parity=True)
+        plain = rec.dyna_track(frames, first["proj_u"], window=window, parity=False)
+        rec.close()
+        tag = f"trial {trial}: W={W} H={H} window={window} frames={n_frames} kind={kind}"
+        assert bits_equal(plain["xyzw"], got["xyzw"]) and bits_equal(plain["mask"], got["mask"]), tag
+        tol = XYZ_REL_TOL * (cfg.fov_max - cfg.fov_min)
+        for f, w in enumerate(want):
+            assert bits_equal(got["strips"][f + 1, ..., 0].astype(np.float32), w["strip_b"]), f"{tag}: stripB frame {f + 1}"
+            assert bits_equal(got["strips"][f + 1, ..., 1].astype(np.float32), w["strip_w"]), f"{tag}: stripW frame {f + 1}"
+            assert bits_equal(got["delta_p"][f], w["delta_p"]), f"{tag}: deltaP frame {f + 1}"
+            assert bits_equal(got["proj_u"][f], w["proj_u"]), f"{tag}: ProjectorU frame {f + 1}"
+            assert bits_equal(got["mask"][f], w["mask"]), f"{tag}: mask frame {f + 1}"
+            for ch, key in enumerate("xyz"):
+                assert np.abs(got["xyzw"][f, ..., ch] - w[key]).max() <= tol, (tag, f, key)
+            assert np.abs(got["delta_z"][f] - w["delta_z"]).max() <= 2 * tol, f"{tag}: deltaZ frame {f + 1}"
+
+
 def test_dynamic_frames_long_sequence(built_library, oracle, base_calibration):
     """40 frames through one launch of the frame-walking kernel: the accumulated ProjectorU and the
     masks stay bit-exact to the last frame (the plane oscillates, so U returns and leaves again)."""
