@@ -22,8 +22,11 @@ rank processes its own `--batch` frame sets per step).
 `roofline` = algorithmic bytes (39 B/px: 22 u8 planes read + float4 XYZ + u8
            mask written) per launch / mean launch duration (CUDA events on the
            launching stream), against the measured HBM copy bandwidth.
-`cpu_baseline` = the CPU oracle (a line-by-line port of the reference's loops)
-           timed on this box's host cores on a bounded sample, rank 0, N == 1.
+`cpu_baseline` = the reference's own compiled sources (oracle/_ref/dynaframe_ref, kind
+           "reference"; one single-threaded process per host thread) timed on this box's
+           host cores on a bounded sample, rank 0, N == 1, with the oracle port's 1-thread
+           and OpenMP numbers beside it; kind "port" where the reference cannot run the
+           geometry (N != 4, modulation mask) or its binary is absent.
 """
 from __future__ import annotations
 
