@@ -1,15 +1,18 @@
 #!/usr/bin/env python
 """A/B of dyna_fused_kernel launch shapes in ONE process (one set of inputs, one GPU):
-for every variant name, set SLC_DYNA_FUSED, check 3 frames against the CPU oracle (mask and f32(U)
-bit-exact, z in tolerance) and time whole sequences with CUDA events.  Per-kernel times come from
+for every variant name, set the variant's environment switch, check 12 frames against the CPU oracle
+(mask and f32(U) bit-exact, z and deltaZ in tolerance) and time whole sequences with CUDA events.  Per-kernel times come from
 the ncu launch list of the same command (profiles/r01_dyna_ab_launches.csv).
 
 The variants lived in a temporary patch of launch_dyna_fused() that read SLC_DYNA_FUSED
 (o = the shipped kernel, a-e / p2-p6 = the shapes and prefetch schemes DESIGN.md 9.1 lists); none
 was faster, so the patch was dropped and the shipped library ignores the variable: run against it,
-every name times the shipped kernel.  Kept as the harness for the next attempt.
+every name times the shipped kernel.  The same holds for the later patches behind "pipe:C:P:K"
+(SLC_DYNA_PIPE: frame-chunked strip / fused pipeline on two streams) and "lean:3" / "lean:4"
+(SLC_DYNA_LEAN: row constants recomputed per frame, 3 or 4 blocks per SM).  Kept as the harness for the
+next attempt.
 
-    python profiles/ab_dyna_fused.py [variants, default "abcde"] [frames, default 100]
+    python profiles/ab_dyna_fused.py [comma-separated variants, default "a,b,c,d,e"] [frames, default 100]
 """
 import os
 import sys
