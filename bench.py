@@ -441,6 +441,28 @@ def run_pointcloud(args):
     launches = int(D.sum_over_ranks(rec.launch_count() - launches0, dev))
     value = world * F * args.steps / (ms * 1e-3)
 
+    # the binary companion (float3 of the valid pixels of the first-frame map, reference order), same timing
+    d_xyzw = torch.from_numpy(first["xyzw"][0]).to(dev)
+    d_msk = torch.from_numpy(first["mask"][0]).to(dev)
+    d_xyz = torch.empty((npx, 3), dtype=torch.float32, device=dev)
+    n_compact = 0
+    for _ in range(3):
+        n_compact = rec.pointcloud_compact_device(d_xyzw.data_ptr(), d_msk.data_ptr(), d_xyz.data_ptr(), npx,
+                                                  capi.SLC_ORDER_REFERENCE, stream.cuda_stream)
+    torch.cuda.synchronize()
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    c0.record(stream)
+    for _ in range(F * args.steps):
+        rec.pointcloud_compact_device(d_xyzw.data_ptr(), d_msk.data_ptr(), d_xyz.data_ptr(), npx,
+                                      capi.SLC_ORDER_REFERENCE, stream.cuda_stream)
+    c1.record(stream)
+    torch.cuda.synchronize()
+    compact_ms = c0.elapsed_time(c1) / (F * args.steps)
+    xyz_host = d_xyz[:n_compact].cpu().numpy()
+    m = first["mask"][0].T.astype(bool)                         # reference order: u outer, v inner
+    compact_ok = bool(n_compact == int(m.sum()) and
+                      np.array_equal(xyz_host, np.transpose(first["xyzw"][0][..., :3], (1, 0, 2))[m]))
+
     # end to end: host f64 plane in, host text out
     e2e_reps = 10
     h_u = capi.PinnedArray((cfg.height, cfg.width), np.float64)
@@ -470,6 +492,10 @@ def run_pointcloud(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"Result() text cloud of a {cfg.width}x{cfg.height} frame ({npts} points, "
                                    f"{nbytes} bytes), {F} frame(s) per step"},
+            "binary_cloud": {"frames_per_s": 1e3 / compact_ms, "points": n_compact, "bytes": 12 * n_compact,
+                             "gb_per_s": (17 * npx + 12 * n_compact) / (compact_ms * 1e-3) / 1e9,
+                             "api": "slc_pointcloud_compact_device (float3 of the valid pixels, reference order)",
+                             "checked": compact_ok},
             "points_per_s": value * npts, "text_gb_per_s": value * nbytes / 1e9,
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": 8 * npx, "d2h_bytes_per_step": nbytes,
                     "api": "capi.Reconstructor.pointcloud_text_into -> slc_pointcloud_text_host, pinned host buffers"},
