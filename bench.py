@@ -65,13 +65,40 @@ def hbm_peak():
 
 
 def ncu_traffic_per_stack(cfg_name):
-    """DRAM bytes per frame set from the committed ncu --set full capture, if any."""
+    """DRAM bytes per frame set: dram__bytes_read.sum + dram__bytes_write.sum of one full-size launch in
+    the committed ncu launch list of this same command (profiles/traffic.json), divided by its frame sets."""
     path = os.path.join(ROOT, "profiles", "traffic.json")
     try:
         with open(path) as f:
-            return float(json.load(f)[cfg_name]["dram_bytes_per_stack"])
+            e = json.load(f)[cfg_name]
+        if "dram_bytes_per_launch" in e:
+            return float(e["dram_bytes_per_launch"]) / float(e["launch_frame_sets"])
+        return float(e["dram_bytes_per_stack"])
     except Exception:
         return None
+
+
+def link_ceiling(n_gpus: int):
+    """Probed host-link ceiling for GPUs 0..N-1 together (profiles/hostlink_ceiling.json, written by
+    profiles/hostlink_probe.py on this pool's boxes): {h2d_gbs, d2h_gbs, bidir_gbs} or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "hostlink_ceiling.json")) as f:
+            return json.load(f)["per_n"].get(str(n_gpus))
+    except Exception:
+        return None
+
+
+def bench_config(cfg, args, world):
+    """`config` of the JSON line: the workload and how it is run -- the SAME object in the b200 arm and the
+    reference arm (both are launched with the same flags), so the driver's same_config holds."""
+    return {"workload": workload_name(cfg), "planes": cfg.planes,
+            "bytes_per_pixel_algorithmic": cfg.algorithmic_bytes_per_pixel,
+            "frame_sets_per_step_per_gpu": args.batch,
+            "l2_policy": f"inputs larger than L2: {args.batch * cfg.stack_bytes / 1e9:.1f} GB read + "
+                         f"{args.batch * cfg.pixels * 17 / 1e9:.1f} GB written per step on the GPU arm (the CPU arm "
+                         f"times a bounded sample of the same frame sets, see cpu_baseline.sample)",
+            "parallelism": f"frame sets sharded over {world} GPU(s), no collective",
+            "distinct_stacks_in_pool": args.pool}
 
 
 class ClockSampler:
@@ -214,9 +241,10 @@ def run_reference(args, cfg):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(cfg), "frame_sets_per_step": per_step, "note": note},
+        "config": bench_config(cfg, args, world),
         "mpix_per_s": value * cfg.pixels / 1e6,
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample,
+                         "frame_sets_per_step": per_step, "note": note},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "wall_s": wall,
     }
@@ -270,7 +298,7 @@ def cpu_baseline(cfg, cal, stack):
     return out
 
 
-def run_dynamic(args):
+def run_dynamic(args, emit=True):
     """--path dynamic: the reference's CalculateOther mode -- a sequence of
     single stripe images tracked frame to frame (StripRegression + FillOtherDeltaProU +
     FillCoordinate), at the reference's own geometry (1280x1024, 100 frames, window 21).
@@ -280,6 +308,7 @@ def run_dynamic(args):
     from oracle import sl_oracle as O   # U0 for the synthetic sequence + CPU baseline only
 
     rank, local_rank, world = D.env_rank_world()
+    line = None
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
@@ -384,12 +413,13 @@ def run_dynamic(args):
                              "sample": "3 dynamic frames, oracle port, 1 thread"},
             "checked_against_oracle": bool(checked),
         }
-        print(json.dumps(line), flush=True)
+        if emit:
+            print(json.dumps(line), flush=True)
     rec.close()
-    return 0
+    return line if rank == 0 else None
 
 
-def run_pointcloud(args):
+def run_pointcloud(args, emit=True):
     """--path pointcloud: CCalculation::Result (SURVEY 8f rank 2) -- the text cloud of one
     1920x1200 frame (BASELINE configs[1] geometry) formatted on the device from the f64
     ProjectorU plane.  A step is `--pc-frames` frames, two kernel launches each."""
@@ -398,6 +428,7 @@ def run_pointcloud(args):
     from oracle import sl_oracle as O   # CPU baseline + byte check only
 
     rank, local_rank, world = D.env_rank_world()
+    line = None
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
@@ -509,12 +540,13 @@ def run_pointcloud(args):
                              "sample": "one frame, oracle Result() restatement (snprintf %g), 1 thread, no file I/O"},
             "checked_against_oracle": bool(text == wtext and wn == npts),
         }
-        print(json.dumps(line), flush=True)
+        if emit:
+            print(json.dumps(line), flush=True)
     rec.close()
-    return 0
+    return line if rank == 0 else None
 
 
-def run_ingest(args):
+def run_ingest(args, emit=True):
     """--path ingest: CSensor::LoadDatas (SURVEY 8f rank 3) -- the 2G+N .bmp files of one frame set
     (reference file layout, 8-bit gray palette, tmpfs) read, uploaded and unpacked on the device
     straight into the plane-major stack.  value = frame sets/s of the batched unpack (one
@@ -526,6 +558,7 @@ def run_ingest(args):
     from oracle.bmp_oracle import decode_bmp_gray      # CPU baseline + check only
 
     rank, local_rank, world = D.env_rank_world()
+    line = None
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
@@ -611,11 +644,12 @@ def run_ingest(args):
                                  "sample": "6 files through the numpy restatement of imread's BMP decoder, scaled to one frame set"},
                 "checked_against_oracle": ok,
             }
-            print(json.dumps(line), flush=True)
+            if emit:
+                print(json.dumps(line), flush=True)
         rec.close()
     finally:
         shutil.rmtree(tmp, ignore_errors=True)
-    return 0
+    return line if rank == 0 else None
 
 
 def run_app(args):
@@ -688,6 +722,191 @@ def run_app(args):
     return 0
 
 
+def time_e2e(call, steps, dev):
+    """`steps` blocking host calls between barriers; returns the slowest rank's seconds."""
+    import torch
+    call()
+    call()
+    D.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        call()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    D.barrier()
+    return D.max_over_ranks(dt, dev)
+
+
+def e2e_entry(value, h2d, d2h, E, steps, seconds, api, world, ceiling):
+    """One end-to-end entry; `roofline` puts the bytes it moved against the probed host-link ceiling."""
+    out = {"value": value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+           "frame_sets_per_step_per_gpu": E, "steps": steps, "ms_per_step": 1e3 * seconds / steps, "api": api}
+    up = world * h2d * steps / seconds / 1e9
+    down = world * d2h * steps / seconds / 1e9
+    out["link_gbs"] = {"h2d": up, "d2h": down, "total": up + down}
+    if ceiling:
+        # the path is bound by whichever direction is closer to its own ceiling, or by the two together
+        fr = {k: v for k, v in (("h2d", up / ceiling["h2d_gbs"] if ceiling.get("h2d_gbs") else None),
+                                ("d2h", down / ceiling["d2h_gbs"] if ceiling.get("d2h_gbs") else None),
+                                ("bidir", (up + down) / ceiling["bidir_gbs"] if ceiling.get("bidir_gbs") else None))
+              if v is not None}
+        bound = max(fr, key=fr.get)
+        out["roofline"] = {"bound": f"host link ({bound})", "link_peak_gbs": ceiling.get(f"{bound}_gbs"),
+                           "achieved_gbs": {"h2d": up, "d2h": down, "bidir": up + down}[bound], "frac": fr[bound],
+                           "fractions": fr, "source": "profiles/hostlink_ceiling.json (profiles/hostlink_probe.py)"}
+    return out
+
+
+def run_sequence(args, cfg):
+    """--config config4: BASELINE configs[3] as written -- ONE dynamic sequence of 4096 frame sets at
+    1920x1200, strong-scaled: rank r owns the contiguous shard slc_shard_range(4096, r, N).  Timed: the
+    whole sequence, device-resident (launches over a resident ring of distinct frame sets: 4096 x 89.9 MB
+    does not fit one GPU) and streamed from / to pinned host rings through the public host call."""
+    import torch
+    from structured_light_calculation_b200 import capi
+
+    rank, local_rank, world = D.env_rank_world()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        D.init_process_group("nccl")
+    total = args.sequence
+    lo, hi = capi.shard_range(total, rank, world)
+    mine = hi - lo
+    cal, scene, stacks = build_inputs(cfg, args.pool)
+    rec = capi.Reconstructor(cfg, device=local_rank, max_batch=args.e2e_chunk, num_slots=args.e2e_slots)
+    rec.set_calibration(cal)
+    ring = min(args.batch, max(mine, 1))
+    d_in = torch.empty((ring, cfg.planes, cfg.height, cfg.width), dtype=torch.uint8, device=dev)
+    d_xyzw = torch.empty((ring, cfg.height, cfg.width, 4), dtype=torch.float32, device=dev)
+    d_mask = torch.empty((ring, cfg.height, cfg.width), dtype=torch.uint8, device=dev)
+    pool_dev = [torch.from_numpy(st).to(dev) for st in stacks]
+    for i in range(ring):
+        d_in[i].copy_(pool_dev[(lo + i) % len(pool_dev)])
+    del pool_dev
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+
+    def sequence():
+        for done in range(0, mine, ring):
+            rec.reconstruct_device(d_in.data_ptr(), min(ring, mine - done), d_xyzw.data_ptr(), d_mask.data_ptr(), None,
+                                   stream.cuda_stream)
+
+    for _ in range(args.warmup):
+        sequence()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = rec.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    D.barrier()
+    torch.cuda.synchronize()
+    e0.record(stream)
+    for _ in range(args.steps):
+        sequence()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    D.barrier()
+    ms = D.max_over_ranks(e0.elapsed_time(e1), dev) / args.steps          # one whole sequence, slowest rank
+    launches = int(D.sum_over_ranks(rec.launch_count() - l0, dev))
+    clocks = sampler.stop() if rank == 0 else None
+
+    # streamed: the shard through slc_reconstruct_host, E frame sets per call from a pinned host ring
+    E = args.e2e_stacks
+    h_in = capi.PinnedArray((E, cfg.planes, cfg.height, cfg.width), np.uint8)
+    h_xyzw = capi.PinnedArray((E, cfg.height, cfg.width, 4), np.float32)
+    h_mask = capi.PinnedArray((E, cfg.height, cfg.width), np.uint8)
+    for i in range(E):
+        h_in.array[i] = stacks[i % len(stacks)]
+
+    def streamed():
+        for done in range(0, mine, E):
+            rec.reconstruct_into(h_in, min(E, mine - done), h_xyzw, h_mask)
+
+    rec.reconstruct_into(h_in, min(E, max(mine, 1)), h_xyzw, h_mask)
+    D.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    streamed()
+    torch.cuda.synchronize()
+    s_stream = D.max_over_ranks(time.perf_counter() - t0, dev)
+    D.barrier()
+
+    if rank == 0:
+        from oracle import sl_oracle as O
+        ocfg = O.make_config(cfg.width, cfg.height, cfg.projector_width, cfg.gray_digits, cfg.phase_steps,
+                             cfg.fov_min, cfg.fov_max, cfg.modulation_min, host_threads())
+        want = O.reconstruct(ocfg, O.make_calib(cal.cam, cal.pro, cal.R, cal.T), stacks[lo % len(stacks)])
+        tol = 1e-5 * (cfg.fov_max - cfg.fov_min)
+        checked = bool(np.array_equal(d_mask[0].cpu().numpy(), want["mask"]) and
+                       np.abs(d_xyzw[0, :, :, 2].cpu().numpy() - want["z"]).max() <= tol and
+                       np.array_equal(h_mask.array[0], O.reconstruct(ocfg, O.make_calib(cal.cam, cal.pro, cal.R, cal.T),
+                                                                     stacks[0])["mask"]))
+        peak, peak_kind = hbm_peak()
+        alg = cfg.algorithmic_bytes_per_pixel * cfg.pixels * total
+        bound_ms = alg / world / (peak * 1e9) * 1e3
+        per_gpu = -(-total // world)
+        ceiling = link_ceiling(world)
+        h2d, d2h = per_gpu * cfg.stack_bytes, per_gpu * cfg.pixels * 17
+        line = {
+            "metric": METRIC, "value": total / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"one dynamic sequence of {total} frame sets: " + workload_name(cfg),
+                       "frame_sets_total": total, "frame_sets_per_gpu": per_gpu,
+                       "l2_policy": f"device-resident ring of {ring} distinct-address frame sets per GPU "
+                                    f"({ring * cfg.stack_bytes / 1e9:.1f} GB read + {ring * cfg.pixels * 17 / 1e9:.1f} GB "
+                                    f"written per launch, far beyond L2); {total} x {cfg.algorithmic_bytes_per_pixel * cfg.pixels / 1e6:.1f} MB "
+                                    f"does not fit one GPU",
+                       "parallelism": f"contiguous shards (slc_shard_range) over {world} GPU(s), no collective"},
+            "mpix_per_s": total / (ms * 1e-3) * cfg.pixels / 1e6,
+            "sequence": {"frame_sets": total, "device_resident_ms": ms, "hbm_bound_ms": bound_ms,
+                         "frac_of_bound": bound_ms / ms, "streamed_s": s_stream, "streamed_value": total / s_stream},
+            "e2e": e2e_entry(total / s_stream, h2d, d2h, per_gpu, 1, s_stream,
+                             f"capi.Reconstructor.reconstruct_into -> slc_reconstruct_host, the rank's whole shard, pinned host "
+                             f"rings of {E} frame sets, {args.e2e_slots} stream slots x {args.e2e_chunk} frame sets", world, ceiling),
+            "gpu_launches": launches,
+            "roofline": {"bound": "hbm", "achieved": alg / world / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": bound_ms / ms, "traffic": None, "peak_kind": f"of {peak_kind}",
+                         "kernel": "slc::reconstruct_vec_kernel", "algorithmic_bytes_per_sequence": alg},
+            "cpu_baseline": None, "clocks": clocks, "checked_against_oracle": checked,
+        }
+        print(json.dumps(line), flush=True)
+    rec.close()
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+    return 0
+
+
+def next_rows(args):
+    """The SURVEY 8(f) rows in the default line: each path's own bench at a bounded size (timed regions
+    well under 2 s), reduced to {value, unit, roofline_frac, e2e, checked}."""
+    import copy
+    out = {}
+    small = copy.copy(args)
+    small.steps, small.warmup = 3, 3
+    small.batch = 64                    # dynamic: one sequence of 100 frames per step
+    small.pc_frames, small.ingest_reps, small.dyna_e2e_frames = 4, 8, 12
+    for name, fn in (("dynamic", run_dynamic), ("pointcloud", run_pointcloud), ("ingest", run_ingest)):
+        try:
+            t0 = time.perf_counter()
+            ln = fn(small, emit=False)
+            out[name] = {"metric": ln["metric"], "value": ln["value"], "unit": ln["unit"],
+                         "roofline_frac": ln["roofline"]["frac"], "kernel": ln["roofline"]["kernel"],
+                         "e2e_value": ln["e2e"]["value"], "checked": ln["checked_against_oracle"],
+                         "workload": ln["config"]["workload"], "wall_s": time.perf_counter() - t0}
+            if name == "pointcloud":
+                out[name]["binary_cloud"] = ln.get("binary_cloud")
+        except Exception as e:      # a next row must never take the headline line down
+            out[name] = {"error": repr(e)}
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -700,9 +919,14 @@ def main():
     ap.add_argument("--e2e-stacks", type=int, default=24, help="frame sets per end-to-end step")
     ap.add_argument("--e2e-chunk", type=int, default=2, help="frame sets per upload/launch/download chunk")
     ap.add_argument("--e2e-slots", type=int, default=4)
+    ap.add_argument("--e2e-mem", default="pinned", choices=["pinned", "wc", "huge"],
+                    help="host memory of the end-to-end input ring: cudaHostAlloc, write-combined, 2 MB pages")
     ap.add_argument("--pxt", type=int, default=0, help="tuning: pixels per thread (4/8/16)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-numa-bind", action="store_true")
+    ap.add_argument("--no-next-rows", action="store_true")
+    ap.add_argument("--sustained-seconds", type=float, default=2.2)
+    ap.add_argument("--sequence", type=int, default=4096, help="--config config4: frame sets of the sequence")
     ap.add_argument("--path", default="first", choices=["first", "dynamic", "pointcloud", "ingest", "app"],
                     help="first = the headline first-frame path; dynamic = CalculateOther sequences; "
                          "pointcloud = Result() text formatting; ingest = .bmp files -> device stack")
@@ -719,13 +943,18 @@ def main():
     if args.impl == "reference":
         return run_reference(args, cfg)
     if args.path == "dynamic":
-        return run_dynamic(args)
+        run_dynamic(args)
+        return 0
     if args.path == "pointcloud":
-        return run_pointcloud(args)
+        run_pointcloud(args)
+        return 0
     if args.path == "ingest":
-        return run_ingest(args)
+        run_ingest(args)
+        return 0
     if args.path == "app":
         return run_app(args)
+    if args.config == "config4":
+        return run_sequence(args, cfg)
 
     import torch
     from structured_light_calculation_b200 import capi
@@ -740,13 +969,13 @@ def main():
     numa = D.bind_to_gpu_numa_node(local_rank) if not args.no_numa_bind else {"bound": False}
     if world > 1:
         D.init_process_group("nccl")
-    if args.pxt:
-        capi.load_library().slc_tune_pixels_per_thread(args.pxt)
 
     F = args.batch
     cal, scene, stacks = build_inputs(cfg, args.pool)
     rec = capi.Reconstructor(cfg, device=local_rank, max_batch=args.e2e_chunk, num_slots=args.e2e_slots)
     rec.set_calibration(cal)
+    if args.pxt:
+        rec.set_pixels_per_thread(args.pxt)
     info = rec.info()
 
     # ---- device-resident batch (torch owns the memory; the kernel is ours) ----
@@ -789,28 +1018,110 @@ def main():
     total_ms_max = D.max_over_ranks(total_ms, dev)
     launches_all = int(D.sum_over_ranks(launches, dev))
     value = world * F * args.steps / (total_ms_max * 1e-3)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- the same kernel for >= 2 s back to back: does the burst figure hold at sustained clocks? ----
+    sustained = None
+    if args.sustained_seconds > 0:
+        n_sus = max(args.steps, int(args.sustained_seconds / (statistics.fmean(per_launch_ms) * 1e-3)) + 1)
+        sampler2 = ClockSampler(local_rank)
+        if rank == 0:
+            sampler2.start()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        D.barrier()
+        torch.cuda.synchronize()
+        s0.record(stream)
+        for _ in range(n_sus):
+            step()
+        s1.record(stream)
+        torch.cuda.synchronize()
+        D.barrier()
+        sus_ms = D.max_over_ranks(s0.elapsed_time(s1), dev)
+        clocks2 = sampler2.stop() if rank == 0 else None
+        peak_s, _ = hbm_peak()
+        sus_gbs = cfg.algorithmic_bytes_per_pixel * cfg.pixels * F * n_sus / (sus_ms * 1e-3) / 1e9
+        sustained = {"seconds": sus_ms * 1e-3, "launches_per_gpu": n_sus, "value": world * F * n_sus / (sus_ms * 1e-3),
+                     "unit": UNIT, "achieved_gbs_per_gpu": sus_gbs, "frac": sus_gbs / peak_s, "clocks": clocks2}
+
+    # ---- the DEPTH layout of the same kernel (z + bit mask: 4.125 instead of 17 B/px written) ----
+    d_depth = d_xyzw.view(-1)[: F * cfg.pixels].view(F, cfg.height, cfg.width)
+    d_bits = d_mask.view(-1)[: (F * capi.bits_bytes(cfg.pixels) + 3) // 4 * 4]
+    res_depth = capi.make_result(capi.SLC_RESULT_DEPTH, depth=d_depth.data_ptr(), mask_bits=d_bits.data_ptr())
+    for _ in range(3):
+        rec.reconstruct_device_ex(d_in.data_ptr(), F, res_depth, stream.cuda_stream)
+    q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    q0.record(stream)
+    for _ in range(args.steps):
+        rec.reconstruct_device_ex(d_in.data_ptr(), F, res_depth, stream.cuda_stream)
+    q1.record(stream)
+    torch.cuda.synchronize()
+    depth_ms = D.max_over_ranks(q0.elapsed_time(q1), dev) / args.steps
+    depth_bytes = (cfg.planes + 4.125) * cfg.pixels * F
+    depth_z = d_depth[0].cpu().numpy()
+    depth_bits = d_bits[: capi.bits_bytes(cfg.pixels)].cpu().numpy()
+    step()                                # the spot check below reads the xyzw + mask layout again
+    torch.cuda.synchronize()
 
     # ---- end to end through the public host call, pinned host buffers ----
     E = args.e2e_stacks
-    h_in = capi.PinnedArray((E, cfg.planes, cfg.height, cfg.width), np.uint8)
-    h_xyzw = capi.PinnedArray((E, cfg.height, cfg.width, 4), np.float32)
-    h_mask = capi.PinnedArray((E, cfg.height, cfg.width), np.uint8)
+    memflag = {"pinned": 0, "wc": capi.SLC_HOST_WRITE_COMBINED, "huge": capi.SLC_HOST_HUGE_PAGES}[args.e2e_mem]
+    h_in = capi.PinnedArray((E, cfg.planes, cfg.height, cfg.width), np.uint8, memflag)
+    outflag = capi.SLC_HOST_HUGE_PAGES if args.e2e_mem == "huge" else 0
+    h_xyzw = capi.PinnedArray((E, cfg.height, cfg.width, 4), np.float32, outflag)
+    h_mask = capi.PinnedArray((E, cfg.height, cfg.width), np.uint8, outflag)
     for i in range(E):
         h_in.array[i] = stacks[i % len(stacks)]
     e2e_steps = args.steps
-    for _ in range(2):
-        rec.reconstruct_into(h_in, E, h_xyzw, h_mask)
-    D.barrier()
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        rec.reconstruct_into(h_in, E, h_xyzw, h_mask)     # blocking: returns with results in host memory
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    D.barrier()
-    e2e_s_max = D.max_over_ranks(e2e_s, dev)
-    e2e_value = world * E * e2e_steps / e2e_s_max
-    clocks = sampler.stop() if rank == 0 else None
+    ceiling = link_ceiling(world)
+    slots_note = f"pinned host buffers ({args.e2e_mem}), {args.e2e_slots} stream slots x {args.e2e_chunk} frame sets"
+    e2e_s = time_e2e(lambda: rec.reconstruct_into(h_in, E, h_xyzw, h_mask), e2e_steps, dev)
+    e2e = e2e_entry(world * E * e2e_steps / e2e_s, E * cfg.stack_bytes, E * cfg.pixels * 17, E, e2e_steps, e2e_s,
+                    "capi.Reconstructor.reconstruct_into -> slc_reconstruct_host, " + slots_note, world, ceiling)
+
+    # ---- the same with the reduced result formats (fewer bytes back over the link) ----
+    e2e_compact = {}
+    bufs_d, res_d = capi.alloc_result(cfg, E, capi.SLC_RESULT_DEPTH, pinned=True)
+    s_d = time_e2e(lambda: rec.reconstruct_into_ex(h_in, E, res_d), e2e_steps, dev)
+    e2e_compact["depth"] = e2e_entry(world * E * e2e_steps / s_d, E * cfg.stack_bytes,
+                                     E * (cfg.pixels * 4 + capi.bits_bytes(cfg.pixels)), E, e2e_steps, s_d,
+                                     "slc_reconstruct_host_ex SLC_RESULT_DEPTH (z + bit mask), " + slots_note, world, ceiling)
+    bufs_p, res_p = capi.alloc_result(cfg, E, capi.SLC_RESULT_POINTS, capi.SLC_ORDER_REFERENCE, pinned=True)
+    s_p = time_e2e(lambda: rec.reconstruct_into_ex(h_in, E, res_p), e2e_steps, dev)
+    n_pts = int(bufs_p["n_points"].array.sum())
+    e2e_compact["points"] = e2e_entry(world * E * e2e_steps / s_p, E * cfg.stack_bytes,
+                                      12 * n_pts + E * capi.bits_bytes(cfg.pixels) + 8 * E, E, e2e_steps, s_p,
+                                      "slc_reconstruct_host_ex SLC_RESULT_POINTS (float3 of the valid pixels in Result()'s "
+                                      "order + bit mask), " + slots_note, world, ceiling)
+    e2e_compact["points"]["valid_fraction"] = n_pts / (E * cfg.pixels)
+
+    # ---- one process, a feeder thread per GPU (slc_pool): rank 0 drives every GPU, the other ranks wait ----
+    e2e_pool = None
+    if world > 1:
+        D.barrier()
+        if rank == 0:
+            pool = capi.Pool(cfg, list(range(world)), max_batch=args.e2e_chunk, num_slots=args.e2e_slots)
+            pool.set_calibration(cal)
+            PE = E * world
+            p_in = capi.PinnedArray((PE, cfg.planes, cfg.height, cfg.width), np.uint8, memflag)
+            for i in range(PE):
+                p_in.array[i] = stacks[i % len(stacks)]
+            pb, pres = capi.alloc_result(cfg, PE, capi.SLC_RESULT_XYZW, pinned=True)
+            for _ in range(2):
+                pool.reconstruct_into_ex(p_in, PE, pres)
+            t0 = time.perf_counter()
+            for _ in range(e2e_steps):
+                pool.reconstruct_into_ex(p_in, PE, pres)
+            ps = time.perf_counter() - t0
+            same = bool(np.array_equal(pb["mask"].array[E], h_mask.array[0]) and
+                        np.array_equal(pb["xyzw"].array[PE - E], h_xyzw.array[0]))
+            e2e_pool = e2e_entry(PE * e2e_steps / ps, E * cfg.stack_bytes, E * cfg.pixels * 17, E, e2e_steps, ps,
+                                 f"capi.Pool.reconstruct_into_ex -> slc_pool_reconstruct_host: ONE process, {world} feeder "
+                                 f"threads (the other ranks idle at a barrier), " + slots_note, world, ceiling)
+            e2e_pool["equals_per_rank_result"] = same
+            pool.close()
+            del p_in, pb
+        D.barrier()
 
     os.sched_setaffinity(0, orig_affinity)   # the CPU baseline below may use every core again
     # ---- spot check of what was just computed (not timed) ----
@@ -827,8 +1138,22 @@ def main():
         checked = bool(np.array_equal(m_dev, want["mask"]) and np.abs(z_dev - want["z"]).max() <= tol
                        and np.array_equal(h_mask.array[0], want["mask"])
                        and np.abs(h_xyzw.array[0, :, :, 2] - want["z"]).max() <= tol)
+        # the reduced formats are selections of that output, bit for bit
+        sel = np.transpose(h_xyzw.array[0, ..., :3], (1, 0, 2))[h_mask.array[0].T.astype(bool)]
+        formats_ok = bool(np.array_equal(depth_z, z_dev) and
+                          np.array_equal(np.unpackbits(depth_bits, bitorder="little")[: cfg.pixels], m_dev.reshape(-1)) and
+                          np.array_equal(bufs_d["depth"].array[0], h_xyzw.array[0, :, :, 2]) and
+                          int(bufs_p["n_points"].array[0]) == len(sel) and
+                          np.array_equal(bufs_p["points"].array[0, : len(sel)], sel))
+        e2e_compact["checked_bit_equal_to_full_map"] = formats_ok
         if world == 1 and not args.no_cpu_baseline:
             cpu = cpu_baseline(cfg, cal, stacks[0])
+    del d_in, d_xyzw, d_mask, d_depth, d_bits
+    torch.cuda.empty_cache()
+    rows = None
+    if world == 1 and not args.no_next_rows and args.config == "config2":
+        rec.close()
+        rows = next_rows(args)
 
     if rank == 0:
         peak, peak_kind = hbm_peak()
@@ -840,24 +1165,28 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms_max / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(cfg), "frame_sets_per_step_per_gpu": F,
-                       "planes": cfg.planes, "bytes_per_pixel_algorithmic": cfg.algorithmic_bytes_per_pixel,
-                       "l2_policy": f"inputs larger than L2: {F * cfg.stack_bytes / 1e9:.1f} GB read + "
-                                    f"{F * cfg.pixels * 17 / 1e9:.1f} GB written per step",
-                       "parallelism": f"frame sets sharded over {world} GPU(s), no collective",
-                       "distinct_stacks_in_pool": len(stacks)},
+            "config": bench_config(cfg, args, world),
             "mpix_per_s": value * cfg.pixels / 1e6,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": E * cfg.stack_bytes,
-                    "d2h_bytes_per_step": E * cfg.pixels * 17, "frame_sets_per_step_per_gpu": E,
-                    "steps": e2e_steps, "ms_per_step": 1e3 * e2e_s_max / e2e_steps,
-                    "api": "capi.Reconstructor.reconstruct_into -> slc_reconstruct_host, pinned host buffers, "
-                           f"{args.e2e_slots} stream slots x {args.e2e_chunk} frame sets"},
+            "e2e": e2e,
+            "e2e_compact": e2e_compact,
+            "e2e_pool": e2e_pool,
             "gpu_launches": launches_all,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": (traffic_ps * F if traffic_ps else None),
-                         "peak_kind": f"of {peak_kind}", "kernel": "slc::reconstruct_vec_kernel",
+                         "traffic_source": "ncu launch list of this command at 256 frame sets per launch "
+                                           "(profiles/traffic.json), scaled to the batch",
+                         "peak_kind": f"of {peak_kind} copy bandwidth (a read+write copy; a write-only stream measures "
+                                      f"higher on this part, so frac can exceed 1)",
+                         "kernel": "slc::reconstruct_vec_kernel",
                          "algorithmic_bytes_per_launch": alg_bytes, "mean_launch_ms": mean_launch_ms,
                          "min_launch_ms": min(per_launch_ms), "max_launch_ms": max(per_launch_ms)},
+            "sustained": sustained,
+            "depth_layout": {"value": world * F / (depth_ms * 1e-3), "unit": UNIT, "ms_per_launch": depth_ms,
+                             "algorithmic_bytes_per_launch": depth_bytes,
+                             "achieved_gbs": depth_bytes / (depth_ms * 1e-3) / 1e9,
+                             "frac": depth_bytes / (depth_ms * 1e-3) / 1e9 / peak,
+                             "api": "slc_reconstruct_device_ex SLC_RESULT_DEPTH: the fused kernel writes z + one bit per pixel"},
+            "next_rows": rows,
             "cpu_baseline": cpu,
             "clocks": clocks,
             "kernel": {"variant": info.kernel_variant, "regs": info.kernel_regs, "block": info.kernel_block,
@@ -866,7 +1195,8 @@ def main():
             "numa": numa,
         }
         print(json.dumps(line), flush=True)
-    rec.close()
+    if rows is None:
+        rec.close()
     if world > 1:
         import torch.distributed as dist
         dist.destroy_process_group()

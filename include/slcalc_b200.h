@@ -16,7 +16,13 @@
  *     failed slc_create).  The reference's bool + ErrorHandling(string)
  *     convention (GlobalFunction.cpp:3-8) maps to status != SLC_OK + message;
  *   - a context is bound to one CUDA device and is single-caller; distinct
- *     contexts may be driven from distinct host threads (one per GPU);
+ *     contexts may be driven from distinct host threads (one per GPU) -- there is
+ *     no process-wide mutable state.  Calls on ONE context must be stream-ordered:
+ *     the context owns scratch buffers (look-back state, strips, staging) that an
+ *     asynchronous _device call is still using until the work it queued has
+ *     finished, so a second _device call on the same context must go to the same
+ *     stream or wait for the first.  slc_pool runs several contexts (one feeder
+ *     thread each) behind one call;
  *   - there is NO CPU fallback: without a CUDA device slc_create fails with
  *     SLC_ERR_NO_DEVICE.
  *
@@ -44,7 +50,7 @@
 extern "C" {
 #endif
 
-#define SLC_ABI_VERSION 1
+#define SLC_ABI_VERSION 2
 
 typedef enum {
     SLC_OK = 0,
@@ -132,6 +138,9 @@ int slc_set_gray_lut(slc_context *ctx, const int16_t *gray2bin, int32_t n);
 
 /* ---- memory helpers --------------------------------------------------- */
 void *slc_host_alloc(size_t bytes);            /* pinned host memory */
+#define SLC_HOST_WRITE_COMBINED (1u << 0)      /* upload-only staging: fast for the CPU to fill, slow to read back */
+#define SLC_HOST_HUGE_PAGES     (1u << 1)      /* 2 MB pages (hugetlb pool if the box has one, else transparent) */
+void *slc_host_alloc_ex(size_t bytes, uint32_t flags);   /* free with slc_host_free */
 void slc_host_free(void *p);
 int slc_host_register(void *p, size_t bytes);  /* pin caller-owned memory */
 int slc_host_unregister(void *p);
@@ -169,6 +178,76 @@ int slc_reconstruct_host(slc_context *ctx, const uint8_t *h_stack, int32_t n_sta
 int slc_submit_host(slc_context *ctx, int32_t slot, const uint8_t *h_stack, int32_t n_stacks,
                     float *h_xyzw, uint8_t *h_mask);
 int slc_wait(slc_context *ctx, int32_t slot);
+
+/* ---- result formats ---------------------------------------------------- */
+/* What a reconstruct call hands back.  The reference's only consumer of the maps,
+ * CCalculation::Result (CCalculation.cpp:336-346), keeps the pixels with FOV_MIN <= z <= FOV_MAX and
+ * drops the rest, so the full float4 map + byte mask (17 B/px) is more than anything downstream reads;
+ * on the host path the result bytes cross PCIe, which is what bounds it.  Every format is defined as
+ * a selection of the SLC_RESULT_XYZW output, bit for bit:
+ *   SLC_RESULT_XYZW    xyzw [n][H][W][4] + mask [n][H][W]                         17     B/px
+ *   SLC_RESULT_DEPTH   depth [n][H][W] = z (0 where invalid) + mask_bits            4.125 B/px
+ *                      (x = z*(u-cu)/fu, y = z*(v-cv)/fv: CCalculation.cpp:766-767)
+ *   SLC_RESULT_POINTS  points [n][point_stride][3] = (x, y, z) of the valid pixels only, in `order`
+ *                      (SLC_ORDER_ROW_MAJOR, or SLC_ORDER_REFERENCE = the order Result() walks),
+ *                      n_points [n], + mask_bits                                    12 B/valid px + 0.125 B/px
+ * mask_bits: u8 [n][(H*W+7)/8], bit (i & 7) of byte (i >> 3) = pixel i valid (numpy packbits,
+ * bitorder "little"); 4-byte aligned, total size padded to a multiple of 4 bytes. */
+#define SLC_RESULT_XYZW   0
+#define SLC_RESULT_DEPTH  1
+#define SLC_RESULT_POINTS 2
+#define SLC_ORDER_ROW_MAJOR 0   /* v outer, u inner: the memory order of the maps */
+#define SLC_ORDER_REFERENCE 1   /* u outer, v inner: the order Result() walks (CCalculation.cpp:336-338) */
+
+typedef struct {
+    int32_t  format;        /* SLC_RESULT_* */
+    int32_t  order;         /* POINTS: SLC_ORDER_* */
+    float   *xyzw;          /* XYZW: required.  POINTS: optional on the host path, required on the device path
+                               (the maps the points are taken from are written there) */
+    uint8_t *mask;          /* as xyzw */
+    float   *depth;         /* DEPTH */
+    uint8_t *mask_bits;     /* DEPTH: required.  POINTS: optional */
+    float   *points;        /* POINTS */
+    int64_t  point_stride;  /* POINTS: points reserved per frame set; a frame set with more valid pixels keeps the
+                               first point_stride of them, n_points still reports them all, and the call returns
+                               SLC_ERR_INVALID_ARG after writing everything that fits */
+    int64_t *n_points;      /* POINTS: [n] */
+} slc_result;
+
+/* slc_reconstruct_device / _host with a result format.  XYZW is exactly the plain call.  DEPTH is
+ * written by the fused kernel itself (26.1 instead of 39 B/px of HBM traffic at 1920x1200 G9 N4);
+ * POINTS adds ONE chained-scan launch per call (slc_compact.cu).  On the host path only the selected
+ * bytes are downloaded; POINTS downloads exactly 12 * n_points[i] bytes per frame set. */
+int slc_reconstruct_device_ex(slc_context *ctx, const uint8_t *d_stack, int32_t n_stacks,
+                              const slc_result *d_out, void *cuda_stream);
+int slc_reconstruct_host_ex(slc_context *ctx, const uint8_t *h_stack, int32_t n_stacks,
+                            const slc_result *h_out);
+
+/* ---- several GPUs behind one call --------------------------- */
+/* replaces: the frame loop of CCalculation::CalculateOther (CCalculation.cpp:221) seen as independent
+ * frame sets, i.e. what main.cpp:42-45 would shard.  A pool owns one context per listed device (a device
+ * may be listed more than once) and one feeder thread per context; calibration and Gray table are
+ * replicated.  Frame sets are split into contiguous shards (slc_shard_range) and every feeder runs the
+ * pinned multi-slot upload / kernel / download pipeline of its context on its shard; there is no
+ * data-path collective.  cfg->device is ignored. */
+typedef struct slc_pool slc_pool;
+int slc_pool_create(const slc_config *cfg, const int32_t *devices, int32_t n_devices, slc_pool **out);
+void slc_pool_destroy(slc_pool *pool);
+const char *slc_pool_last_error(const slc_pool *pool);   /* slc_pool_last_error(NULL): a failed slc_pool_create */
+int slc_pool_size(const slc_pool *pool);
+slc_context *slc_pool_context(slc_pool *pool, int32_t member);   /* for per-GPU calls (device_alloc, info ...) */
+int slc_pool_set_calibration(slc_pool *pool, const double cam[9], const double pro[9],
+                             const double R[9], const double T[3]);
+int slc_pool_set_gray_lut(slc_pool *pool, const int16_t *gray2bin, int32_t n);
+/* contiguous block [*lo, *hi) of n_items for shard `index` of `n_shards`; sizes differ by at most one */
+int slc_shard_range(int64_t n_items, int32_t index, int32_t n_shards, int64_t *lo, int64_t *hi);
+/* n_stacks frame sets in host memory -> results in host memory, all members at once; blocks. */
+int slc_pool_reconstruct_host(slc_pool *pool, const uint8_t *h_stack, int32_t n_stacks,
+                              const slc_result *h_out);
+/* Device-resident shards: member i runs n_stacks[i] frame sets from d_stack[i] into d_out[i] (device
+ * pointers on that member's GPU) and the call returns when every GPU has finished. */
+int slc_pool_reconstruct_device(slc_pool *pool, const uint8_t *const *d_stack, const int32_t *n_stacks,
+                                const slc_result *d_out);
 
 /* ---- the decoder objects on their own --------------------------------- */
 /* replaces: CDecodeGray::Decode + GetResult (CDecodeGray.cpp:108-147): 2G
@@ -257,8 +336,6 @@ int slc_bmp_decode_host(slc_context *ctx, const void *h_file_bytes, int64_t n_by
 int slc_load_bmp_planes(slc_context *ctx, const char *const *paths, int32_t n_files, uint8_t *d_stack);
 
 /* ---- point-cloud output ("next" row: CCalculation::Result) ----------------- */
-#define SLC_ORDER_ROW_MAJOR 0   /* v outer, u inner: the memory order of the maps */
-#define SLC_ORDER_REFERENCE 1   /* u outer, v inner: the order Result() walks (CCalculation.cpp:336-338) */
 #define SLC_TEXT_CRLF (1u << 0) /* "\r\n" line ends: what the reference's text-mode fstream writes on its platform */
 #define SLC_TEXT_EXP3 (1u << 1) /* three exponent digits (the MSVC 2013 CRT of the reference build) instead of two */
 
@@ -301,9 +378,9 @@ int slc_time_reconstruct_device(slc_context *ctx, const uint8_t *d_stack, int32_
                                 float *ms_per_launch);
 /* Number of kernels this library has launched on this context so far. */
 int64_t slc_launch_count(const slc_context *ctx);
-/* Tuning hook for bench/tests: pixels owned by one thread of the vector kernel
- * (4, 8 or 16; 0 = chosen per geometry, the default; process-wide).  Results do not depend on it. */
-void slc_tune_pixels_per_thread(int32_t pxt);
+/* Tuning hook for bench/tests: pixels owned by one thread of this context's vector kernel
+ * (4, 8 or 16; 0 = chosen per geometry, the default).  Results do not depend on it. */
+int slc_set_pixels_per_thread(slc_context *ctx, int32_t pxt);
 
 #ifdef __cplusplus
 }

@@ -18,8 +18,6 @@ peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if 
     os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
 base = load_calibration(os.path.join(ROOT, "tests", "golden", "Result.yml"))
 dev = torch.device("cuda", 0)
-if os.environ.get("SWEEP_PXT"):                 # pixels per thread of the vector kernel: 4 / 8 / 16
-    capi.load_library().slc_tune_pixels_per_thread(int(os.environ["SWEEP_PXT"]))
 cases = [(1280, 1024, 1280, 6, 4), (1280, 1024, 1280, 7, 4), (1280, 1024, 1280, 8, 4), (1280, 1024, 2560, 9, 4),
          (1920, 1200, 2560, 6, 4), (1920, 1200, 2560, 7, 4), (1920, 1200, 2560, 8, 4), (1920, 1200, 2560, 9, 4),
          (1280, 1040, 1280, 7, 4), (1296, 1024, 1280, 7, 4),
@@ -32,6 +30,8 @@ for W, H, PW, G, N in cases:
     cal = synth.synthetic_calibration(cfg, base)
     rec = capi.Reconstructor(cfg, device=0, max_batch=1, num_slots=1)
     rec.set_calibration(cal)
+    if os.environ.get("SWEEP_PXT"):                 # pixels per thread of the vector kernel: 4 / 8 / 16
+        rec.set_pixels_per_thread(int(os.environ["SWEEP_PXT"]))
     F = 16 if os.environ.get("SWEEP_QUICK") else max(8, int(6e9 // (cfg.planes * cfg.pixels)))
     scene = synth.make_scene(cfg, cal)                   # rendered stack (random bytes would make most pixels invalid)
     stack = torch.from_numpy(synth.render_stack(cfg, scene, noise_sigma=1.0, seed=5)).to(dev)

@@ -33,6 +33,13 @@ SLC_ORDER_REFERENCE = 1
 SLC_TEXT_CRLF = 1 << 0
 SLC_TEXT_EXP3 = 1 << 1
 
+SLC_RESULT_XYZW = 0
+SLC_RESULT_DEPTH = 1
+SLC_RESULT_POINTS = 2
+
+SLC_HOST_WRITE_COMBINED = 1 << 0
+SLC_HOST_HUGE_PAGES = 1 << 1
+
 
 class SlcError(RuntimeError):
     def __init__(self, status: int, message: str):
@@ -68,6 +75,12 @@ class SlcBmpInfo(C.Structure):
 
 class SlcDynaParity(C.Structure):
     _fields_ = [("strips", C.c_void_p), ("delta_p", C.c_void_p), ("proj_u", C.c_void_p)]
+
+
+class SlcResult(C.Structure):
+    _fields_ = [("format", C.c_int32), ("order", C.c_int32), ("xyzw", C.c_void_p), ("mask", C.c_void_p),
+                ("depth", C.c_void_p), ("mask_bits", C.c_void_p), ("points", C.c_void_p),
+                ("point_stride", C.c_int64), ("n_points", C.c_void_p)]
 
 
 class SlcParityPlanes(C.Structure):
@@ -110,6 +123,8 @@ def load_library():
     L.slc_host_alloc.restype = vp
     L.slc_host_free.argtypes = [vp]
     L.slc_host_free.restype = None
+    L.slc_host_alloc_ex.argtypes = [C.c_size_t, C.c_uint32]
+    L.slc_host_alloc_ex.restype = vp
     L.slc_host_register.argtypes = [vp, C.c_size_t]
     L.slc_host_unregister.argtypes = [vp]
     L.slc_device_alloc.argtypes = [vp, C.c_size_t]
@@ -123,6 +138,21 @@ def load_library():
     L.slc_reconstruct_host.argtypes = [vp, vp, i32, vp, vp, C.POINTER(SlcParityPlanes)]
     L.slc_submit_host.argtypes = [vp, i32, vp, i32, vp, vp]
     L.slc_wait.argtypes = [vp, i32]
+    L.slc_reconstruct_device_ex.argtypes = [vp, vp, i32, C.POINTER(SlcResult), vp]
+    L.slc_reconstruct_host_ex.argtypes = [vp, vp, i32, C.POINTER(SlcResult)]
+    L.slc_pool_create.argtypes = [C.POINTER(SlcConfig), C.POINTER(i32), i32, C.POINTER(vp)]
+    L.slc_pool_destroy.argtypes = [vp]
+    L.slc_pool_destroy.restype = None
+    L.slc_pool_last_error.argtypes = [vp]
+    L.slc_pool_last_error.restype = C.c_char_p
+    L.slc_pool_size.argtypes = [vp]
+    L.slc_pool_context.argtypes = [vp, i32]
+    L.slc_pool_context.restype = vp
+    L.slc_pool_set_calibration.argtypes = [vp, vp, vp, vp, vp]
+    L.slc_pool_set_gray_lut.argtypes = [vp, vp, i32]
+    L.slc_shard_range.argtypes = [C.c_int64, i32, i32, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+    L.slc_pool_reconstruct_host.argtypes = [vp, vp, i32, C.POINTER(SlcResult)]
+    L.slc_pool_reconstruct_device.argtypes = [vp, C.POINTER(vp), C.POINTER(i32), C.POINTER(SlcResult)]
     L.slc_decode_gray_host.argtypes = [vp, vp, vp, vp]
     L.slc_decode_phase_host.argtypes = [vp, vp, vp, vp]
     L.slc_triangulate_host.argtypes = [vp, vp, vp, vp]
@@ -145,8 +175,7 @@ def load_library():
     L.slc_time_reconstruct_device.argtypes = [vp, vp, i32, vp, vp, i32, C.POINTER(C.c_float)]
     L.slc_launch_count.argtypes = [vp]
     L.slc_launch_count.restype = C.c_int64
-    L.slc_tune_pixels_per_thread.argtypes = [i32]
-    L.slc_tune_pixels_per_thread.restype = None
+    L.slc_set_pixels_per_thread.argtypes = [vp, i32]
     _lib = L
     return L
 
@@ -163,14 +192,14 @@ def bmp_parse(file_bytes: bytes) -> SlcBmpInfo:
 class PinnedArray:
     """numpy view over pinned host memory from slc_host_alloc."""
 
-    def __init__(self, shape, dtype):
+    def __init__(self, shape, dtype, flags: int = 0):
         self._lib = load_library()
         self.shape = tuple(int(s) for s in shape)
         self.dtype = np.dtype(dtype)
         nbytes = int(np.prod(self.shape)) * self.dtype.itemsize
-        self.ptr = self._lib.slc_host_alloc(max(nbytes, 1))
+        self.ptr = self._lib.slc_host_alloc_ex(max(nbytes, 1), flags)
         if not self.ptr:
-            raise MemoryError(f"slc_host_alloc({nbytes}) failed")
+            raise MemoryError(f"slc_host_alloc_ex({nbytes}, {flags}) failed")
         buf = (C.c_uint8 * max(nbytes, 1)).from_address(self.ptr)
         self.array = np.frombuffer(buf, dtype=self.dtype, count=int(np.prod(self.shape))).reshape(self.shape)
 
@@ -202,6 +231,59 @@ def _ptr(a):
         assert a.flags["C_CONTIGUOUS"]
         return a.ctypes.data
     return int(a)
+
+
+def shard_range(n_items: int, index: int, n_shards: int) -> tuple[int, int]:
+    """slc_shard_range: the contiguous block of frame sets member `index` of `n_shards` owns."""
+    lo, hi = C.c_int64(0), C.c_int64(0)
+    st = load_library().slc_shard_range(n_items, index, n_shards, C.byref(lo), C.byref(hi))
+    if st != SLC_OK:
+        raise SlcError(st, f"bad shard request n={n_items} index={index} shards={n_shards}")
+    return int(lo.value), int(hi.value)
+
+
+def bits_bytes(npx: int) -> int:
+    return (npx + 7) // 8
+
+
+def make_result(fmt: int, order: int = SLC_ORDER_ROW_MAJOR, xyzw=None, mask=None, depth=None, mask_bits=None,
+                points=None, point_stride: int = 0, n_points=None) -> SlcResult:
+    """slc_result from numpy arrays / PinnedArrays / raw addresses (None = not wanted)."""
+    return SlcResult(fmt, order, _ptr(xyzw), _ptr(mask), _ptr(depth), _ptr(mask_bits), _ptr(points), point_stride,
+                     _ptr(n_points))
+
+
+def alloc_result(cfg: StackConfig, n: int, fmt: int, order: int = SLC_ORDER_ROW_MAJOR, pinned: bool = False,
+                 point_stride: int | None = None, full_maps: bool = False):
+    """Host buffers for `n` frame sets in `fmt` -> (dict of arrays / PinnedArrays, SlcResult)."""
+    H, W, npx = cfg.height, cfg.width, cfg.pixels
+    mk = (lambda shape, dt: PinnedArray(shape, dt)) if pinned else (lambda shape, dt: np.empty(shape, dt))
+    bufs = {}
+    if fmt == SLC_RESULT_XYZW or full_maps:
+        bufs["xyzw"] = mk((n, H, W, 4), np.float32)
+        bufs["mask"] = mk((n, H, W), np.uint8)
+    if fmt == SLC_RESULT_DEPTH:
+        bufs["depth"] = mk((n, H, W), np.float32)
+    if fmt in (SLC_RESULT_DEPTH, SLC_RESULT_POINTS):
+        bufs["mask_bits"] = mk(((n * bits_bytes(npx) + 3) // 4 * 4,), np.uint8)
+    stride = 0
+    if fmt == SLC_RESULT_POINTS:
+        stride = npx if point_stride is None else point_stride
+        bufs["points"] = mk((n, stride, 3), np.float32)
+        bufs["n_points"] = mk((n,), np.int64)
+    res = make_result(fmt, order, bufs.get("xyzw"), bufs.get("mask"), bufs.get("depth"), bufs.get("mask_bits"),
+                      bufs.get("points"), stride, bufs.get("n_points"))
+    return bufs, res
+
+
+def _arr(a):
+    return a.array if isinstance(a, PinnedArray) else a
+
+
+def unpack_mask_bits(bits, n: int, npx: int) -> np.ndarray:
+    """mask_bits [n][(npx+7)/8] -> u8 [n][npx] of 0/1."""
+    b = np.asarray(_arr(bits))[: n * bits_bytes(npx)].reshape(n, bits_bytes(npx))
+    return np.unpackbits(b, axis=1, bitorder="little")[:, :npx]
 
 
 class Reconstructor:
@@ -309,6 +391,25 @@ class Reconstructor:
     def reconstruct_into(self, h_stack, n_stacks: int, h_xyzw, h_mask):
         """Host path into caller-provided (ideally pinned) buffers."""
         self._check(self.lib.slc_reconstruct_host(self.h, _ptr(h_stack), n_stacks, _ptr(h_xyzw), _ptr(h_mask), None))
+
+    def reconstruct_into_ex(self, h_stack, n_stacks: int, result: SlcResult):
+        """Host path with a result format (slc_reconstruct_host_ex)."""
+        self._check(self.lib.slc_reconstruct_host_ex(self.h, _ptr(h_stack), n_stacks, C.byref(result)))
+
+    def reconstruct_device_ex(self, d_stack: int, n_stacks: int, result: SlcResult, stream: int | None = None):
+        self._check(self.lib.slc_reconstruct_device_ex(self.h, d_stack, n_stacks, C.byref(result), stream))
+
+    def reconstruct_ex(self, stacks, fmt: int, order: int = SLC_ORDER_ROW_MAJOR, full_maps: bool = False) -> dict:
+        """numpy in, numpy out, in result format `fmt`."""
+        arr = np.ascontiguousarray(_arr(stacks), dtype=np.uint8)
+        if arr.ndim == 3:
+            arr = arr[None]
+        bufs, res = alloc_result(self.cfg, arr.shape[0], fmt, order, full_maps=full_maps)
+        self.reconstruct_into_ex(arr, arr.shape[0], res)
+        return bufs
+
+    def set_pixels_per_thread(self, pxt: int):
+        self._check(self.lib.slc_set_pixels_per_thread(self.h, pxt))
 
     def submit(self, slot: int, h_stack, n_stacks: int, h_xyzw, h_mask):
         self._check(self.lib.slc_submit_host(self.h, slot, _ptr(h_stack), n_stacks, _ptr(h_xyzw), _ptr(h_mask)))
@@ -485,3 +586,59 @@ class Reconstructor:
 
     def launch_count(self) -> int:
         return int(self.lib.slc_launch_count(self.h))
+
+
+class Pool:
+    """slc_pool: one context + one feeder thread per listed GPU behind one call."""
+
+    def __init__(self, cfg: StackConfig, devices, max_batch: int = 2, num_slots: int = 4, flags: int = 0):
+        self.lib = load_library()
+        self.cfg = cfg
+        c = SlcConfig(cfg.width, cfg.height, cfg.projector_width, cfg.gray_digits, cfg.phase_steps,
+                      float(cfg.fov_min), float(cfg.fov_max), float(cfg.modulation_min), flags, 0, max_batch, num_slots)
+        devs = (C.c_int32 * len(devices))(*devices)
+        h = C.c_void_p()
+        st = self.lib.slc_pool_create(C.byref(c), devs, len(devices), C.byref(h))
+        if st != SLC_OK:
+            raise SlcError(st, (self.lib.slc_pool_last_error(None) or b"").decode())
+        self.h = h
+        self.n = len(devices)
+
+    def _check(self, st: int):
+        if st != SLC_OK:
+            raise SlcError(st, (self.lib.slc_pool_last_error(self.h) or b"").decode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.slc_pool_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_calibration(self, cal):
+        cam = np.ascontiguousarray(cal.cam, dtype=np.float64).reshape(9)
+        pro = np.ascontiguousarray(cal.pro, dtype=np.float64).reshape(9)
+        R = np.ascontiguousarray(cal.R, dtype=np.float64).reshape(9)
+        T = np.ascontiguousarray(cal.T, dtype=np.float64).reshape(3)
+        self._check(self.lib.slc_pool_set_calibration(self.h, cam.ctypes.data, pro.ctypes.data, R.ctypes.data,
+                                                      T.ctypes.data))
+
+    def context(self, member: int) -> int:
+        return self.lib.slc_pool_context(self.h, member)
+
+    def launch_count(self) -> int:
+        return sum(int(self.lib.slc_launch_count(self.context(i))) for i in range(self.n))
+
+    def reconstruct_into_ex(self, h_stack, n_stacks: int, result: SlcResult):
+        self._check(self.lib.slc_pool_reconstruct_host(self.h, _ptr(h_stack), n_stacks, C.byref(result)))
+
+    def reconstruct_device(self, d_stacks, n_stacks, results):
+        """Per-member device shards: d_stacks[i] / results[i] live on member i's GPU."""
+        ptrs = (C.c_void_p * self.n)(*[int(p) for p in d_stacks])
+        ns = (C.c_int32 * self.n)(*n_stacks)
+        res = (SlcResult * self.n)(*results)
+        self._check(self.lib.slc_pool_reconstruct_device(self.h, ptrs, ns, res))

@@ -8,6 +8,8 @@
 #include "../../include/slcalc_b200.h"
 #include "slc_kernels.h"
 
+#include <sys/mman.h>
+
 #include <algorithm>
 #include <condition_variable>
 #include <mutex>
@@ -28,6 +30,10 @@ namespace {
 
 thread_local std::string g_create_error;
 
+// huge-page pinned blocks handed out by slc_host_alloc_ex (they are unmapped, not cudaFreeHost'ed)
+std::mutex g_huge_mu;
+std::vector<std::pair<void*, size_t>> g_huge;
+
 struct Slot {
     cudaStream_t stream = nullptr;
     uint8_t* d_stack = nullptr;
@@ -38,6 +44,16 @@ struct Slot {
     int8_t* d_corr = nullptr;
     float* d_pix = nullptr;
     double* d_proj_u = nullptr;
+    // SLC_RESULT_POINTS, allocated on first use: packed points, bit mask, counts, look-back state
+    float* d_points = nullptr;
+    uint8_t* d_bits = nullptr;
+    unsigned long long* d_counts = nullptr;
+    unsigned long long* d_cstate = nullptr;
+    unsigned long long* h_counts = nullptr;     // pinned
+    cudaEvent_t counts_ready = nullptr;
+    unsigned epoch = 0;
+    // a POINTS chunk whose counts are on their way: its point download is issued once they are known
+    struct { bool active = false; int n = 0; float* h_points = nullptr; int64_t* h_n_points = nullptr; } pending;
     bool busy = false;
 };
 
@@ -68,6 +84,10 @@ struct slc_context {
     void* h_bmp[kBmpSlots] = {};   size_t h_bmp_bytes[kBmpSlots] = {};   // ingest: raw file staging (pinned)
     cudaEvent_t bmp_done[kBmpSlots] = {};
     void* d_dyna = nullptr;        size_t dyna_bytes = 0;        // dynamic frames: staging for the host entry point
+    slc::LaunchPlan plans[3][2];                                 // [mode][output layout], chosen on first use
+    int pxt_override = 0;                                        // slc_set_pixels_per_thread
+    void* d_cstate = nullptr;      size_t cstate_bytes = 0;      // POINTS on the device path: look-back state
+    unsigned cstate_epoch = 0;
     long long launches = 0;
     std::string err;
 };
@@ -117,22 +137,41 @@ int ensure_parity(slc_context* ctx, Slot& s, const slc_parity_planes* want)
     return SLC_OK;
 }
 
+size_t bits_bytes(const slc_context* c) { return ((size_t)c->kp.npx + 7) / 8; }
+
+// the kernel for (mode, output layout) of this context: chosen once, then only launched
+int plan_for(slc_context* ctx, int mode, int out, const slc::LaunchPlan** plan)
+{
+    slc::LaunchPlan& pl = ctx->plans[mode][out];
+    if (!pl.valid) SLC_CUDA(ctx, slc::plan_reconstruct(ctx->kp, mode, out, ctx->pxt_override, &pl));
+    *plan = &pl;
+    return SLC_OK;
+}
+
+// One fused launch.  d_depth != nullptr selects the SLC_RESULT_DEPTH layout (d_bits beside it),
+// otherwise xyzw + mask.
 int launch(slc_context* ctx, const uint8_t* d_stack, int n_stacks, float* d_xyzw, uint8_t* d_mask,
-           const slc_parity_planes* par, cudaStream_t stream)
+           const slc_parity_planes* par, cudaStream_t stream, float* d_depth = nullptr, uint8_t* d_bits = nullptr)
 {
     KParams p = ctx->kp;
     p.n_stacks = n_stacks;
     p.stack = d_stack;
     p.xyzw = reinterpret_cast<float4*>(d_xyzw);
     p.mask = d_mask;
+    p.depth = d_depth;
+    p.mask_bits = d_bits;
+    p.bits_stride = (long long)bits_bytes(ctx);
     p.kbin = par ? par->kbin : nullptr;
     p.corr = par ? par->corr : nullptr;
     p.phase_pix = par ? par->phase_pix : nullptr;
     p.proj_u = par ? par->proj_u : nullptr;
     p.lut = ctx->d_lut;
     const bool scalar = (ctx->cfg.flags & SLC_FLAG_SCALAR_KERNEL) != 0;
-    SLC_CUDA(ctx, slc::launch_reconstruct(p, scalar, stream, nullptr));
-    ctx->launches++;
+    const slc::LaunchPlan* plan = nullptr;
+    int rc = plan_for(ctx, slc::plan_mode(p), d_depth ? 1 : 0, &plan);
+    if (rc != SLC_OK) return rc;
+    SLC_CUDA(ctx, slc::launch_reconstruct(p, *plan, scalar, stream, nullptr));
+    ctx->launches += (n_stacks + 65534) / 65535;
     return SLC_OK;
 }
 
@@ -326,11 +365,14 @@ void slc_destroy(slc_context* ctx)
         if (s.stream) { cudaStreamSynchronize(s.stream); cudaStreamDestroy(s.stream); }
         cudaFree(s.d_stack); cudaFree(s.d_xyzw); cudaFree(s.d_mask);
         cudaFree(s.d_kbin); cudaFree(s.d_corr); cudaFree(s.d_pix); cudaFree(s.d_proj_u);
+        cudaFree(s.d_points); cudaFree(s.d_bits); cudaFree(s.d_counts); cudaFree(s.d_cstate);
+        if (s.h_counts) cudaFreeHost(s.h_counts);
+        if (s.counts_ready) cudaEventDestroy(s.counts_ready);
     }
     if (ctx->stream) { cudaStreamSynchronize(ctx->stream); cudaStreamDestroy(ctx->stream); }
     cudaFree(ctx->d_lut);
     cudaFree(ctx->d_scratch_in); cudaFree(ctx->d_scratch_out); cudaFree(ctx->d_scratch_aux);
-    cudaFree(ctx->d_strips); cudaFree(ctx->d_dsums); cudaFree(ctx->d_dyna);
+    cudaFree(ctx->d_strips); cudaFree(ctx->d_dsums); cudaFree(ctx->d_dyna); cudaFree(ctx->d_cstate);
     cudaFree(ctx->d_pc_scratch); cudaFree(ctx->d_pc_in); cudaFree(ctx->d_pc_out);
     if (ctx->h_pc_totals) cudaFreeHost(ctx->h_pc_totals);
     for (int k = 0; k < kBmpSlots; k++) {
@@ -363,7 +405,10 @@ int slc_get_info(const slc_context* cctx, slc_info* out)
     p.xyzw = reinterpret_cast<float4*>(ctx->slots[0].d_xyzw);
     p.mask = ctx->slots[0].d_mask;
     p.lut = ctx->d_lut;
-    SLC_CUDA(ctx, slc::launch_reconstruct(p, (ctx->cfg.flags & SLC_FLAG_SCALAR_KERNEL) != 0, nullptr, &li));
+    const slc::LaunchPlan* plan = nullptr;
+    int rc = plan_for(ctx, slc::plan_mode(p), 0, &plan);
+    if (rc != SLC_OK) return rc;
+    SLC_CUDA(ctx, slc::launch_reconstruct(p, *plan, (ctx->cfg.flags & SLC_FLAG_SCALAR_KERNEL) != 0, nullptr, &li));
     out->kernel_variant = li.variant;
     out->kernel_regs = li.regs;
     out->kernel_block = li.block;
@@ -468,7 +513,46 @@ void* slc_host_alloc(size_t bytes)
     if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) return nullptr;
     return p;
 }
-void slc_host_free(void* p) { if (p) cudaFreeHost(p); }
+void slc_host_free(void* p)
+{
+    if (!p) return;
+    size_t huge = 0;
+    {
+        std::lock_guard<std::mutex> lk(g_huge_mu);
+        for (size_t i = 0; i < g_huge.size(); i++)
+            if (g_huge[i].first == p) { huge = g_huge[i].second; g_huge.erase(g_huge.begin() + (long)i); break; }
+    }
+    if (huge) { cudaHostUnregister(p); munmap(p, huge); }
+    else cudaFreeHost(p);
+}
+void* slc_host_alloc_ex(size_t bytes, uint32_t flags)
+{
+    if (bytes == 0) bytes = 1;
+    if (flags & SLC_HOST_HUGE_PAGES) {
+        const size_t two_mb = (size_t)2 << 20, len = (bytes + two_mb - 1) & ~(two_mb - 1);
+        void* p = mmap(nullptr, len, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_HUGETLB, -1, 0);
+        if (p == MAP_FAILED) {
+            // no hugetlb pool: an aligned anonymous mapping the kernel may back with transparent huge pages
+            void* raw = mmap(nullptr, len + two_mb, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+            if (raw == MAP_FAILED) return nullptr;
+            const uintptr_t a = (reinterpret_cast<uintptr_t>(raw) + two_mb - 1) & ~(uintptr_t)(two_mb - 1);
+            if (a > reinterpret_cast<uintptr_t>(raw)) munmap(raw, a - reinterpret_cast<uintptr_t>(raw));
+            const uintptr_t end = reinterpret_cast<uintptr_t>(raw) + len + two_mb;
+            if (end > a + len) munmap(reinterpret_cast<void*>(a + len), end - (a + len));
+            p = reinterpret_cast<void*>(a);
+            madvise(p, len, MADV_HUGEPAGE);
+        }
+        std::memset(p, 0, len);   // fault the pages in before pinning them
+        if (cudaHostRegister(p, len, cudaHostRegisterPortable) != cudaSuccess) { cudaGetLastError(); munmap(p, len); return nullptr; }
+        std::lock_guard<std::mutex> lk(g_huge_mu);
+        g_huge.emplace_back(p, len);
+        return p;
+    }
+    void* p = nullptr;
+    const unsigned f = cudaHostAllocPortable | ((flags & SLC_HOST_WRITE_COMBINED) ? cudaHostAllocWriteCombined : 0u);
+    if (cudaHostAlloc(&p, bytes, f) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
 int slc_host_register(void* p, size_t bytes)
 {
     return cudaHostRegister(p, bytes, cudaHostRegisterPortable) == cudaSuccess ? SLC_OK : SLC_ERR_CUDA;
@@ -524,23 +608,8 @@ int slc_reconstruct_device(slc_context* ctx, const uint8_t* d_stack, int32_t n_s
     if (n_stacks == 0) return SLC_OK;
     SLC_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
     cudaStream_t st = cuda_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : ctx->stream;
-    // one launch covers up to 65535 stacks (grid.y); split beyond that
-    const size_t npx = (size_t)ctx->kp.npx;
-    for (int done = 0; done < n_stacks;) {
-        const int n = (n_stacks - done) > 65535 ? 65535 : (n_stacks - done);
-        slc_parity_planes par{};
-        if (d_parity) {
-            par.kbin = d_parity->kbin ? d_parity->kbin + (size_t)done * npx : nullptr;
-            par.corr = d_parity->corr ? d_parity->corr + (size_t)done * npx : nullptr;
-            par.phase_pix = d_parity->phase_pix ? d_parity->phase_pix + (size_t)done * npx : nullptr;
-            par.proj_u = d_parity->proj_u ? d_parity->proj_u + (size_t)done * npx : nullptr;
-        }
-        rc = launch(ctx, d_stack + (size_t)done * stack_bytes(ctx), n, d_xyzw + (size_t)done * npx * 4,
-                    d_mask + (size_t)done * npx, d_parity ? &par : nullptr, st);
-        if (rc != SLC_OK) return rc;
-        done += n;
-    }
-    return SLC_OK;
+    // any number of frame sets: launch_reconstruct splits beyond the 65535 of grid.y
+    return launch(ctx, d_stack, n_stacks, d_xyzw, d_mask, d_parity, st);
 }
 
 int slc_reconstruct_host(slc_context* ctx, const uint8_t* h_stack, int32_t n_stacks, float* h_xyzw,
@@ -593,6 +662,206 @@ int slc_wait(slc_context* ctx, int32_t slot)
     SLC_CUDA(ctx, cudaStreamSynchronize(ctx->slots[slot].stream));
     ctx->slots[slot].busy = false;
     return SLC_OK;
+}
+
+/* ---- result formats ---------------------------------------------------- */
+namespace {
+
+int check_result(slc_context* ctx, const slc_result* r, bool device_path)
+{
+    if (!r) return fail(ctx, SLC_ERR_INVALID_ARG, "NULL slc_result");
+    switch (r->format) {
+    case SLC_RESULT_XYZW:
+        if (!r->xyzw || !r->mask) return fail(ctx, SLC_ERR_INVALID_ARG, "SLC_RESULT_XYZW needs xyzw and mask");
+        break;
+    case SLC_RESULT_DEPTH:
+        if (!r->depth || !r->mask_bits) return fail(ctx, SLC_ERR_INVALID_ARG, "SLC_RESULT_DEPTH needs depth and mask_bits");
+        if (device_path && (reinterpret_cast<uintptr_t>(r->mask_bits) & 3))
+            return fail(ctx, SLC_ERR_INVALID_ARG, "mask_bits must be 4-byte aligned");
+        break;
+    case SLC_RESULT_POINTS:
+        if (!r->points || !r->n_points || r->point_stride < 0)
+            return fail(ctx, SLC_ERR_INVALID_ARG, "SLC_RESULT_POINTS needs points, n_points and point_stride >= 0");
+        if (r->order != SLC_ORDER_ROW_MAJOR && r->order != SLC_ORDER_REFERENCE)
+            return fail(ctx, SLC_ERR_INVALID_ARG, "order %d is neither SLC_ORDER_ROW_MAJOR nor SLC_ORDER_REFERENCE", r->order);
+        if (device_path && (!r->xyzw || !r->mask))
+            return fail(ctx, SLC_ERR_INVALID_ARG, "SLC_RESULT_POINTS on the device path needs xyzw and mask (the maps the points are taken from)");
+        if (ctx->kp.W % 8 != 0 || ctx->kp.H >= 65536)
+            return fail(ctx, SLC_ERR_INVALID_ARG, "SLC_RESULT_POINTS needs a camera width that is a multiple of 8 and a height below 65536");
+        break;
+    default:
+        return fail(ctx, SLC_ERR_INVALID_ARG, "unknown result format %d", r->format);
+    }
+    return SLC_OK;
+}
+
+// per-slot buffers of the POINTS pipeline, on first use
+int ensure_points(slc_context* ctx, Slot& s)
+{
+    const size_t nb = (size_t)ctx->cfg.max_batch, npx = (size_t)ctx->kp.npx;
+    if (!s.d_points) SLC_CUDA(ctx, cudaMalloc(&s.d_points, nb * npx * 12));
+    if (!s.d_bits) SLC_CUDA(ctx, cudaMalloc(&s.d_bits, (nb * bits_bytes(ctx) + 3) & ~(size_t)3));
+    if (!s.d_counts) SLC_CUDA(ctx, cudaMalloc(&s.d_counts, nb * sizeof(unsigned long long)));
+    if (!s.d_cstate) {
+        const size_t bytes = slc::compact_state_bytes(ctx->kp.W, ctx->kp.H, (int)nb);
+        SLC_CUDA(ctx, cudaMalloc(&s.d_cstate, bytes));
+        SLC_CUDA(ctx, cudaMemsetAsync(s.d_cstate, 0, bytes, s.stream));
+        s.epoch = 0;
+    }
+    if (!s.h_counts) SLC_CUDA(ctx, cudaHostAlloc(&s.h_counts, nb * sizeof(unsigned long long), cudaHostAllocDefault));
+    if (!s.counts_ready) SLC_CUDA(ctx, cudaEventCreateWithFlags(&s.counts_ready, cudaEventDisableTiming));
+    return SLC_OK;
+}
+
+// The counts of the slot's POINTS chunk are on their way (or there): once known, download exactly
+// 12 * count bytes per frame set.
+int finish_points(slc_context* ctx, Slot& s, int64_t point_stride, bool* overflow)
+{
+    if (!s.pending.active) return SLC_OK;
+    s.pending.active = false;
+    SLC_CUDA(ctx, cudaEventSynchronize(s.counts_ready));
+    const size_t npx = (size_t)ctx->kp.npx;
+    for (int i = 0; i < s.pending.n; i++) {
+        const int64_t cnt = (int64_t)s.h_counts[i];
+        s.pending.h_n_points[i] = cnt;
+        if (cnt > point_stride) *overflow = true;
+        const int64_t m = cnt < point_stride ? cnt : point_stride;
+        if (m > 0)
+            SLC_CUDA(ctx, cudaMemcpyAsync(s.pending.h_points + (size_t)i * (size_t)point_stride * 3,
+                                          s.d_points + (size_t)i * npx * 3, (size_t)m * 12, cudaMemcpyDeviceToHost, s.stream));
+    }
+    return SLC_OK;
+}
+
+// Upload + kernel(s) + download of one chunk in DEPTH or POINTS format; `o` already points at this chunk.
+int enqueue_chunk_fmt(slc_context* ctx, Slot& s, const uint8_t* h_stack, int n, const slc_result& o)
+{
+    const size_t npx = (size_t)ctx->kp.npx, bb = bits_bytes(ctx);
+    SLC_CUDA(ctx, cudaMemcpyAsync(s.d_stack, h_stack, stack_bytes(ctx) * n, cudaMemcpyHostToDevice, s.stream));
+    if (o.format == SLC_RESULT_DEPTH) {
+        // the slot's xyzw / mask buffers hold the (smaller) depth plane / bit mask
+        int rc = launch(ctx, s.d_stack, n, nullptr, nullptr, nullptr, s.stream, s.d_xyzw, s.d_mask);
+        if (rc != SLC_OK) return rc;
+        SLC_CUDA(ctx, cudaMemcpyAsync(o.depth, s.d_xyzw, npx * 4 * n, cudaMemcpyDeviceToHost, s.stream));
+        SLC_CUDA(ctx, cudaMemcpyAsync(o.mask_bits, s.d_mask, bb * n, cudaMemcpyDeviceToHost, s.stream));
+    } else {
+        int rc = ensure_points(ctx, s);
+        if (rc == SLC_OK) rc = launch(ctx, s.d_stack, n, s.d_xyzw, s.d_mask, nullptr, s.stream);
+        if (rc != SLC_OK) return rc;
+        SLC_CUDA(ctx, slc::launch_compact(ctx->kp.W, ctx->kp.H, n, o.order, s.d_xyzw, s.d_mask, s.d_points, (long long)npx,
+                                          o.mask_bits ? s.d_bits : nullptr, (long long)bb, s.d_counts, s.d_cstate,
+                                          ++s.epoch, s.stream));
+        ctx->launches++;
+        SLC_CUDA(ctx, cudaMemcpyAsync(s.h_counts, s.d_counts, sizeof(unsigned long long) * n, cudaMemcpyDeviceToHost, s.stream));
+        SLC_CUDA(ctx, cudaEventRecord(s.counts_ready, s.stream));
+        if (o.xyzw) SLC_CUDA(ctx, cudaMemcpyAsync(o.xyzw, s.d_xyzw, npx * 16 * n, cudaMemcpyDeviceToHost, s.stream));
+        if (o.mask) SLC_CUDA(ctx, cudaMemcpyAsync(o.mask, s.d_mask, npx * n, cudaMemcpyDeviceToHost, s.stream));
+        if (o.mask_bits) SLC_CUDA(ctx, cudaMemcpyAsync(o.mask_bits, s.d_bits, bb * n, cudaMemcpyDeviceToHost, s.stream));
+        s.pending.active = true;
+        s.pending.n = n;
+        s.pending.h_points = o.points;
+        s.pending.h_n_points = o.n_points;
+    }
+    s.busy = true;
+    return SLC_OK;
+}
+
+// look-back state of the chained scan for n_stacks maps (context-owned: calls are stream-ordered)
+int ensure_cstate(slc_context* ctx, int n_stacks, cudaStream_t st)
+{
+    const size_t want = slc::compact_state_bytes(ctx->kp.W, ctx->kp.H, n_stacks);
+    if (ctx->cstate_bytes < want) {
+        int rc = ensure_scratch(ctx, &ctx->d_cstate, &ctx->cstate_bytes, want);
+        if (rc != SLC_OK) return rc;
+        SLC_CUDA(ctx, cudaMemsetAsync(ctx->d_cstate, 0, want, st));
+        ctx->cstate_epoch = 0;
+    }
+    return SLC_OK;
+}
+
+// `r` advanced by `done` frame sets
+slc_result result_at(const slc_context* ctx, const slc_result& r, size_t done)
+{
+    const size_t npx = (size_t)ctx->kp.npx;
+    slc_result o = r;
+    if (r.xyzw) o.xyzw = r.xyzw + done * npx * 4;
+    if (r.mask) o.mask = r.mask + done * npx;
+    if (r.depth) o.depth = r.depth + done * npx;
+    if (r.mask_bits) o.mask_bits = r.mask_bits + done * bits_bytes(ctx);
+    if (r.points) o.points = r.points + done * (size_t)r.point_stride * 3;
+    if (r.n_points) o.n_points = r.n_points + done;
+    return o;
+}
+
+}  // namespace
+
+int slc_reconstruct_device_ex(slc_context* ctx, const uint8_t* d_stack, int32_t n_stacks, const slc_result* d_out,
+                              void* cuda_stream)
+{
+    int rc = check_ready(ctx, d_stack, d_out, d_out, n_stacks);
+    if (rc != SLC_OK) return rc;
+    if (n_stacks == 0) return SLC_OK;
+    rc = check_result(ctx, d_out, true);
+    if (rc != SLC_OK) return rc;
+    if (d_out->format == SLC_RESULT_XYZW)
+        return slc_reconstruct_device(ctx, d_stack, n_stacks, d_out->xyzw, d_out->mask, nullptr, cuda_stream);
+    SLC_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+    cudaStream_t st = cuda_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : ctx->stream;
+    if (d_out->format == SLC_RESULT_DEPTH)
+        return launch(ctx, d_stack, n_stacks, nullptr, nullptr, nullptr, st, d_out->depth, d_out->mask_bits);
+    // POINTS: the maps, then one chained-scan launch over the whole batch
+    rc = launch(ctx, d_stack, n_stacks, d_out->xyzw, d_out->mask, nullptr, st);
+    if (rc != SLC_OK) return rc;
+    if (!slc::compact_supported(ctx->kp.W, ctx->kp.H, d_out->mask, d_out->xyzw))
+        return fail(ctx, SLC_ERR_INVALID_ARG, "SLC_RESULT_POINTS needs 16-byte aligned xyzw and 8-byte aligned mask");
+    rc = ensure_cstate(ctx, n_stacks, st);
+    if (rc != SLC_OK) return rc;
+    SLC_CUDA(ctx, slc::launch_compact(ctx->kp.W, ctx->kp.H, n_stacks, d_out->order, d_out->xyzw, d_out->mask, d_out->points,
+                                      (long long)d_out->point_stride, d_out->mask_bits, (long long)bits_bytes(ctx),
+                                      reinterpret_cast<unsigned long long*>(d_out->n_points),
+                                      static_cast<unsigned long long*>(ctx->d_cstate), ++ctx->cstate_epoch, st));
+    ctx->launches += (n_stacks + 65534) / 65535;
+    return SLC_OK;
+}
+
+int slc_reconstruct_host_ex(slc_context* ctx, const uint8_t* h_stack, int32_t n_stacks, const slc_result* h_out)
+{
+    int rc = check_ready(ctx, h_stack, h_out, h_out, n_stacks);
+    if (rc != SLC_OK) return rc;
+    if (n_stacks == 0) return SLC_OK;
+    rc = check_result(ctx, h_out, false);
+    if (rc != SLC_OK) return rc;
+    if (h_out->format == SLC_RESULT_XYZW)
+        return slc_reconstruct_host(ctx, h_stack, n_stacks, h_out->xyzw, h_out->mask, nullptr);
+    SLC_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+    const int chunk = ctx->cfg.max_batch, S = (int)ctx->slots.size();
+    const bool points = h_out->format == SLC_RESULT_POINTS;
+    bool overflow = false;
+    int slot = 0;
+    rc = SLC_OK;
+    for (int done = 0; done < n_stacks && rc == SLC_OK; done += chunk) {
+        const int n = (n_stacks - done) < chunk ? (n_stacks - done) : chunk;
+        Slot& s = ctx->slots[slot];
+        // the chunk this slot ran S chunks ago: its counts are known by now, queue its point download
+        if (points) rc = finish_points(ctx, s, h_out->point_stride, &overflow);
+        if (rc == SLC_OK)
+            rc = enqueue_chunk_fmt(ctx, s, h_stack + (size_t)done * stack_bytes(ctx), n, result_at(ctx, *h_out, (size_t)done));
+        slot = (slot + 1) % S;
+    }
+    for (int k = 0; k < S && points; k++) {       // oldest first
+        const int rc2 = finish_points(ctx, ctx->slots[(slot + k) % S], h_out->point_stride, &overflow);
+        if (rc == SLC_OK) rc = rc2;
+    }
+    for (Slot& s : ctx->slots) {
+        const cudaError_t e = cudaStreamSynchronize(s.stream);
+        s.busy = false;
+        s.pending.active = false;
+        if (e != cudaSuccess && rc == SLC_OK) rc = fail(ctx, SLC_ERR_CUDA, "cudaStreamSynchronize failed: %s", cudaGetErrorString(e));
+    }
+    if (rc == SLC_OK && overflow)
+        return fail(ctx, SLC_ERR_INVALID_ARG, "a frame set has more valid pixels than point_stride = %lld: its list was cut (n_points holds the full counts)",
+                    (long long)h_out->point_stride);
+    return rc;
 }
 
 /* ---- decoder objects -------------------------------------------------- */
@@ -1090,6 +1359,38 @@ int pointcloud_run(slc_context* ctx, int mode, int order, uint32_t flags, const 
 
 }  // namespace
 
+namespace {
+
+// float3 of the valid pixels of ONE map: the chained-scan kernel of slc_compact.cu (one launch) where the
+// geometry allows it, else the two-pass record emitter.
+int compact_run(slc_context* ctx, int order, const float* d_xyzw, const uint8_t* d_mask, float* d_xyz,
+                int64_t capacity_points, int64_t* points, cudaStream_t st)
+{
+    if (!slc::compact_supported(ctx->kp.W, ctx->kp.H, d_mask, d_xyzw))
+        return pointcloud_run(ctx, 1, order, 0u, nullptr, d_xyzw, d_mask, d_xyz, capacity_points * 12, nullptr, points, st);
+    if (capacity_points < 0 || !d_xyz) return fail(ctx, SLC_ERR_INVALID_ARG, "NULL output or negative capacity");
+    if (order != SLC_ORDER_ROW_MAJOR && order != SLC_ORDER_REFERENCE)
+        return fail(ctx, SLC_ERR_INVALID_ARG, "order %d is neither SLC_ORDER_ROW_MAJOR nor SLC_ORDER_REFERENCE", order);
+    int rc = ensure_cstate(ctx, 1, st);
+    if (rc == SLC_OK) rc = ensure_scratch(ctx, &ctx->d_pc_scratch, &ctx->pc_scratch_bytes, slc::pointcloud_scratch_bytes(ctx->kp.npx));
+    if (rc != SLC_OK) return rc;
+    unsigned long long* d_count = static_cast<unsigned long long*>(ctx->d_pc_scratch);
+    SLC_CUDA(ctx, slc::launch_compact(ctx->kp.W, ctx->kp.H, 1, order, d_xyzw, d_mask, d_xyz, (long long)capacity_points, nullptr, 0,
+                                      d_count, static_cast<unsigned long long*>(ctx->d_cstate), ++ctx->cstate_epoch, st));
+    ctx->launches++;
+    if (!ctx->h_pc_totals) SLC_CUDA(ctx, cudaHostAlloc(&ctx->h_pc_totals, 2 * sizeof(unsigned long long), cudaHostAllocDefault));
+    unsigned long long* totals = static_cast<unsigned long long*>(ctx->h_pc_totals);
+    SLC_CUDA(ctx, cudaMemcpyAsync(totals, d_count, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    SLC_CUDA(ctx, cudaStreamSynchronize(st));
+    if (points) *points = (int64_t)totals[0];
+    if ((int64_t)totals[0] > capacity_points)
+        return fail(ctx, SLC_ERR_INVALID_ARG, "point cloud has %lld points, buffer holds %lld", (long long)totals[0],
+                    (long long)capacity_points);
+    return SLC_OK;
+}
+
+}  // namespace
+
 int slc_pointcloud_text_device(slc_context* ctx, const double* d_proj_u, uint32_t flags, char* d_text,
                                int64_t capacity, int64_t* bytes, int64_t* points, void* cuda_stream)
 {
@@ -1131,7 +1432,7 @@ int slc_pointcloud_compact_device(slc_context* ctx, const float* d_xyzw, const u
     if (!d_xyzw || !d_mask) return fail(ctx, SLC_ERR_INVALID_ARG, "NULL map");
     SLC_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
     cudaStream_t st = cuda_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : ctx->stream;
-    return pointcloud_run(ctx, 1, order, 0u, nullptr, d_xyzw, d_mask, d_xyz, capacity_points * 12, nullptr, points, st);
+    return compact_run(ctx, order, d_xyzw, d_mask, d_xyz, capacity_points, points, st);
 }
 
 int slc_pointcloud_compact_host(slc_context* ctx, const float* h_xyzw, const uint8_t* h_mask, int32_t order,
@@ -1151,8 +1452,7 @@ int slc_pointcloud_compact_host(slc_context* ctx, const float* h_xyzw, const uin
     SLC_CUDA(ctx, cudaMemcpyAsync(d_xyzw, h_xyzw, npx * 16, cudaMemcpyHostToDevice, ctx->stream));
     SLC_CUDA(ctx, cudaMemcpyAsync(d_mask, h_mask, npx, cudaMemcpyHostToDevice, ctx->stream));
     int64_t n = 0;
-    rc = pointcloud_run(ctx, 1, order, 0u, nullptr, d_xyzw, d_mask, ctx->d_pc_out, (int64_t)(cap_pts * 12), nullptr, &n,
-                        ctx->stream);
+    rc = compact_run(ctx, order, d_xyzw, d_mask, static_cast<float*>(ctx->d_pc_out), (int64_t)cap_pts, &n, ctx->stream);
     if (points) *points = n;
     if (rc != SLC_OK) return rc;
     SLC_CUDA(ctx, cudaMemcpyAsync(h_xyz, ctx->d_pc_out, (size_t)n * 12, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1212,7 +1512,7 @@ int slc_time_reconstruct_device(slc_context* ctx, const uint8_t* d_stack, int32_
 {
     int rc = check_ready(ctx, d_stack, d_xyzw, d_mask, n_stacks);
     if (rc != SLC_OK) return rc;
-    if (iters < 1 || !ms_per_launch || n_stacks < 1 || n_stacks > 65535)
+    if (iters < 1 || !ms_per_launch || n_stacks < 1)
         return fail(ctx, SLC_ERR_INVALID_ARG, "bad iters / n_stacks / output pointer");
     SLC_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
     cudaEvent_t e0, e1;
@@ -1235,6 +1535,14 @@ int slc_time_reconstruct_device(slc_context* ctx, const uint8_t* d_stack, int32_
 
 int64_t slc_launch_count(const slc_context* ctx) { return ctx ? ctx->launches : 0; }
 
-void slc_tune_pixels_per_thread(int32_t pxt) { slc::set_default_pixels_per_thread(pxt); }
+int slc_set_pixels_per_thread(slc_context* ctx, int32_t pxt)
+{
+    if (!ctx) return SLC_ERR_INVALID_ARG;
+    if (pxt != 0 && pxt != 4 && pxt != 8 && pxt != 16) return fail(ctx, SLC_ERR_INVALID_ARG, "pixels per thread must be 0, 4, 8 or 16");
+    ctx->pxt_override = pxt;
+    for (auto& row : ctx->plans)
+        for (auto& pl : row) pl = slc::LaunchPlan{};      // chosen again on the next launch
+    return SLC_OK;
+}
 
 }  // extern "C"

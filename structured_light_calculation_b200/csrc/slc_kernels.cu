@@ -50,6 +50,19 @@ template <> struct VecLoad<4> {
 // and every address is "per-thread base + compile-time immediate".
 template <int PXT> struct Tile { static constexpr int kStride = PXT + 1; static constexpr int kSlots = 32 * (PXT + 1); };
 
+// What a pixel leaves in its tile slot: the whole float4 (OUT 0: xyzw + u8 mask), or z alone
+// (OUT 1: SLC_RESULT_DEPTH, z plane + one validity bit per pixel).  A pixel awaiting the f64 re-solve
+// parks (gint, pix) in the first two words either way.
+template <int OUT> struct Slot;
+template <> struct Slot<0> {
+    using type = float4;
+    static __device__ __forceinline__ float4 result(const float4& r) { return r; }
+};
+template <> struct Slot<1> {
+    using type = float2;
+    static __device__ __forceinline__ float2 result(const float4& r) { return make_float2(r.z, 0.f); }
+};
+
 // MODE 0: no parity planes, reflected Gray code, f32 z with f64 guard band, no modulation test
 // MODE 1: as 0 with the [EXT] modulation test
 // MODE 2: everything decided at run time (parity planes, custom LUT, SLC_FLAG_Z_FP64, modulation)
@@ -69,19 +82,20 @@ __device__ __forceinline__ uint32_t spread_bits4(uint32_t b) { return ((b & 0xFu
 
 // The fused kernel.  G_T / N_T > 0 bake the digit and step counts in (all plane
 // loops unroll and every load is issued up front); 0 means "read it from p".
-template <int PXT, int G_T, int N_T, int MODE>
+template <int PXT, int G_T, int N_T, int MODE, int OUT>
 __global__ void __launch_bounds__(kBlock)
 reconstruct_vec_kernel(const __grid_constant__ KParams p)
 {
     constexpr int NW = PXT / 4;  // 32-bit words (4 pixels each) per thread
     constexpr int kStride = Tile<PXT>::kStride;
+    using SlotT = typename Slot<OUT>::type;
     extern __shared__ float4 s_tile[];
 
     const int G = G_T > 0 ? G_T : p.G;
     const int N = N_T > 0 ? N_T : p.N;
     const int lane = threadIdx.x & 31;
     const int warp_in_block = threadIdx.x >> 5;
-    float4* tile = s_tile + warp_in_block * Tile<PXT>::kSlots;
+    SlotT* tile = reinterpret_cast<SlotT*>(s_tile) + warp_in_block * Tile<PXT>::kSlots;
 
     // grid.y = stack, grid.x covers the stack's pixel groups: a warp tile never straddles stacks
     const int stack = blockIdx.y;
@@ -89,6 +103,7 @@ reconstruct_vec_kernel(const __grid_constant__ KParams p)
     const unsigned g = blockIdx.x * kBlock + threadIdx.x;       // group inside the stack
     const bool active = g < n_groups;
     const long long out0 = (long long)stack * p.npx;            // first output pixel of the stack
+    uint32_t validbits = 0;
 
     if (active) {
         const unsigned off = g * PXT;             // first pixel of the group inside the stack
@@ -197,8 +212,8 @@ reconstruct_vec_kernel(const __grid_constant__ KParams p)
         // ---- per pixel: arctan, offset, unwrap, f32 triangulation (branch free) ----
         const RowConst rc = make_row_const(p, v);
         const float u0f = (float)u0;
-        float4* trow = tile + lane * kStride;
-        uint32_t validbits = 0, slowbits = 0;
+        SlotT* trow = tile + lane * kStride;
+        uint32_t slowbits = 0;
         const bool z64 = (MODE == 2) && (p.z_fp64 != 0);
 #pragma unroll
         for (int w = 0; w < NW; w++) {
@@ -218,7 +233,8 @@ reconstruct_vec_kernel(const __grid_constant__ KParams p)
                 if (z64) pix = solve_pixel<MODE, true>(p, rc, kbin, sv[i], cv[i], uf, r);
                 else pix = solve_pixel<MODE, false>(p, rc, kbin, sv[i], cv[i], uf, r);
                 // pixels awaiting the f64 re-solve park (gint, pix) in their tile slot
-                trow[i] = make_float4(r.need64 ? r.gint : r.x, r.need64 ? pix : r.y, r.z, r.w);
+                if constexpr (OUT == 0) trow[i] = make_float4(r.need64 ? r.gint : r.x, r.need64 ? pix : r.y, r.z, r.w);
+                else trow[i] = make_float2(r.need64 ? r.gint : r.z, pix);
                 validbits |= (r.valid ? 1u : 0u) << i;
                 slowbits |= (r.need64 ? 1u : 0u) << i;
                 if (MODE == 2) {
@@ -234,37 +250,68 @@ reconstruct_vec_kernel(const __grid_constant__ KParams p)
         while (slowbits != 0u) {
             const int i = __ffs((int)slowbits) - 1;
             slowbits &= slowbits - 1u;
-            const float4 t = trow[i];
+            const SlotT t = trow[i];
             int ok;
-            trow[i] = resolve_f64(p, t.x, t.y, u0 + i, v, &ok);
+            trow[i] = Slot<OUT>::result(resolve_f64(p, t.x, t.y, u0 + i, v, &ok));
             validbits = (validbits & ~(1u << i)) | ((uint32_t)ok << i);
         }
-        // validity mask: PXT contiguous bytes per thread, 32*PXT per warp
-        uint8_t* mptr = p.mask + out0 + off;
-        if constexpr (PXT == 16)
-            st_stream_u4(mptr, make_uint4(spread_bits4(validbits), spread_bits4(validbits >> 4),
-                                          spread_bits4(validbits >> 8), spread_bits4(validbits >> 12)));
-        else if constexpr (PXT == 8)
-            st_stream_u2(mptr, make_uint2(spread_bits4(validbits), spread_bits4(validbits >> 4)));
-        else
-            st_stream_u1(mptr, spread_bits4(validbits));
+        if constexpr (OUT == 0) {
+            // validity mask: PXT contiguous bytes per thread, 32*PXT per warp
+            uint8_t* mptr = p.mask + out0 + off;
+            if constexpr (PXT == 16)
+                st_stream_u4(mptr, make_uint4(spread_bits4(validbits), spread_bits4(validbits >> 4),
+                                              spread_bits4(validbits >> 8), spread_bits4(validbits >> 12)));
+            else if constexpr (PXT == 8)
+                st_stream_u2(mptr, make_uint2(spread_bits4(validbits), spread_bits4(validbits >> 4)));
+            else
+                st_stream_u1(mptr, spread_bits4(validbits));
+        }
     }
 
-    // ---- transposed, fully coalesced float4 stores: 512 contiguous bytes per instruction ----
-    __syncwarp();
-    const unsigned px0 = (blockIdx.x * kBlock + (threadIdx.x & ~31u)) * PXT;  // warp's first pixel in the stack
-    const unsigned stack_px = n_groups * PXT;
-    float4* outp = p.xyzw + out0 + px0 + lane;
-    // pixel it*32 + lane belongs to owner (it*32 + lane) / PXT, element (it*32 + lane) % PXT
-    const float4* tsrc = tile + (lane / PXT) * kStride + (lane % PXT);
-    if (px0 + 32u * PXT <= stack_px) {
+    if constexpr (OUT == 1) {
+        // ---- SLC_RESULT_DEPTH: one validity bit per pixel (32 * PXT / 8 contiguous bytes per warp) and
+        //      the z plane, 512 contiguous bytes per store instruction ----
+        uint8_t* bptr = p.mask_bits + (long long)stack * p.bits_stride + (size_t)(g * (PXT / 4)) / 2;
+        if constexpr (PXT == 4) {
+            // two threads share a byte (n_groups is even: npx % 16 == 0)
+            const uint32_t hi_nib = __shfl_down_sync(0xFFFFFFFFu, validbits, 1);
+            if (active && (lane & 1) == 0) *bptr = (uint8_t)(validbits | (hi_nib << 4));
+        } else if constexpr (PXT == 8) {
+            if (active) *bptr = (uint8_t)validbits;
+        } else {
+            if (active) *reinterpret_cast<uint16_t*>(bptr) = (uint16_t)validbits;
+        }
+        __syncwarp();
+        const unsigned px0 = (blockIdx.x * kBlock + (threadIdx.x & ~31u)) * PXT;
+        const unsigned stack_px = n_groups * PXT;
+        float* zout = p.depth + out0 + px0;
 #pragma unroll
-        for (int it = 0; it < PXT; it++)
-            st_stream_f4(outp + it * 32, tsrc[(it * 32 / PXT) * kStride]);
-    } else {
+        for (int it = 0; it < PXT / 4; it++) {
+            const int q = it * 32 + lane;                 // quad of pixels 4q .. 4q+3 of the warp's 32*PXT
+            const SlotT* src = tile + ((4 * q) / PXT) * kStride + ((4 * q) % PXT);
+            if (px0 + 4u * q < stack_px)
+                st_stream_f4(reinterpret_cast<float4*>(zout + 4 * q), make_float4(src[0].x, src[1].x, src[2].x, src[3].x));
+        }
+        return;
+    }
+
+    if constexpr (OUT == 0) {
+        // ---- transposed, fully coalesced float4 stores: 512 contiguous bytes per instruction ----
+        __syncwarp();
+        const unsigned px0 = (blockIdx.x * kBlock + (threadIdx.x & ~31u)) * PXT;  // warp's first pixel in the stack
+        const unsigned stack_px = n_groups * PXT;
+        float4* outp = p.xyzw + out0 + px0 + lane;
+        // pixel it*32 + lane belongs to owner (it*32 + lane) / PXT, element (it*32 + lane) % PXT
+        const float4* tsrc = tile + (lane / PXT) * kStride + (lane % PXT);
+        if (px0 + 32u * PXT <= stack_px) {
 #pragma unroll
-        for (int it = 0; it < PXT; it++)
-            if (px0 + it * 32 + lane < stack_px) st_stream_f4(outp + it * 32, tsrc[(it * 32 / PXT) * kStride]);
+            for (int it = 0; it < PXT; it++)
+                st_stream_f4(outp + it * 32, tsrc[(it * 32 / PXT) * kStride]);
+        } else {
+#pragma unroll
+            for (int it = 0; it < PXT; it++)
+                if (px0 + it * 32 + lane < stack_px) st_stream_f4(outp + it * 32, tsrc[(it * 32 / PXT) * kStride]);
+        }
     }
 }
 
@@ -328,8 +375,17 @@ reconstruct_scalar_kernel(const __grid_constant__ KParams p)
     float4 outv = make_float4(r.x, r.y, r.z, r.w);
     int ok = r.valid ? 1 : 0;
     if (r.need64) outv = resolve_f64(p, r.gint, pix, u, v, &ok);
-    p.xyzw[idx] = outv;
-    p.mask[idx] = (uint8_t)ok;
+    if (p.depth) {
+        // SLC_RESULT_DEPTH on the any-geometry path: the bit plane was zeroed by the launcher
+        p.depth[idx] = outv.z;
+        if (ok) {
+            const long long bit = (long long)stack * p.bits_stride * 8 + off;
+            atomicOr(reinterpret_cast<unsigned*>(p.mask_bits) + (bit >> 5), 1u << (bit & 31));
+        }
+    } else {
+        p.xyzw[idx] = outv;
+        p.mask[idx] = (uint8_t)ok;
+    }
     if (PARITY) {
         if (p.kbin) p.kbin[idx] = (int16_t)kbin;
         if (p.corr) p.corr[idx] = (int8_t)r.corr;
@@ -480,26 +536,36 @@ eval_phase_kernel(const float* __restrict__ s, const float* __restrict__ c, long
 // ---------------------------------------------------------------------------
 using VecKernel = void (*)(const KParams);
 
-struct VecEntry { int G, N, pxt, mode; VecKernel fn; };
+struct VecEntry { int G, N, pxt, mode, out; VecKernel fn; };
 
+// MODE 0 / 1 (production) come in both output layouts, MODE 2 (parity planes, custom table, Z_FP64)
+// in the xyzw + mask layout only.
 #define SLC_VEC(PXT, G, N) \
-    { G, N, PXT, 0, reconstruct_vec_kernel<PXT, G, N, 0> }, \
-    { G, N, PXT, 1, reconstruct_vec_kernel<PXT, G, N, 1> }, \
-    { G, N, PXT, 2, reconstruct_vec_kernel<PXT, G, N, 2> }
+    { G, N, PXT, 0, 0, reconstruct_vec_kernel<PXT, G, N, 0, 0> }, \
+    { G, N, PXT, 1, 0, reconstruct_vec_kernel<PXT, G, N, 1, 0> }, \
+    { G, N, PXT, 2, 0, reconstruct_vec_kernel<PXT, G, N, 2, 0> }, \
+    { G, N, PXT, 0, 1, reconstruct_vec_kernel<PXT, G, N, 0, 1> }, \
+    { G, N, PXT, 1, 1, reconstruct_vec_kernel<PXT, G, N, 1, 1> }
+// tuning-only shapes (slc_set_pixels_per_thread): xyzw + mask layout
+#define SLC_VEC_TUNE(PXT, G, N) \
+    { G, N, PXT, 0, 0, reconstruct_vec_kernel<PXT, G, N, 0, 0> }, \
+    { G, N, PXT, 1, 0, reconstruct_vec_kernel<PXT, G, N, 1, 0> }, \
+    { G, N, PXT, 2, 0, reconstruct_vec_kernel<PXT, G, N, 2, 0> }
 
 // Specialised <G, N> instances: the reference default, BASELINE.json's configurations and the
 // other 4-step Gray depths (every plane loop unrolled, loads issued ahead of their use); anything
 // else runs the generic (0, 0) instance, which is latency bound (0.58-0.65 of the HBM peak measured
 // at G = 8, N = 4 before that pair got its own instance, profiles/r01_sweep_geometry.txt).
 const VecEntry kVecTable[] = {
-    SLC_VEC(8, 6, 4),   SLC_VEC(8, 7, 4),   SLC_VEC(8, 9, 4),
-    SLC_VEC(8, 5, 4),   SLC_VEC(8, 8, 4),   SLC_VEC(8, 10, 4),
+    SLC_VEC(8, 6, 4),   SLC_VEC(8, 9, 4),   SLC_VEC(8, 5, 4),   SLC_VEC(8, 10, 4),
     SLC_VEC(8, 8, 8),   SLC_VEC(8, 10, 12),
+    SLC_VEC_TUNE(8, 7, 4), SLC_VEC_TUNE(8, 8, 4),
     // Gray depth fixed, any number of phase steps (the Gray planes are most of the loads)
-    SLC_VEC(8, 5, 0),   SLC_VEC(8, 6, 0),   SLC_VEC(8, 7, 0),   SLC_VEC(8, 8, 0),   SLC_VEC(8, 9, 0),   SLC_VEC(8, 10, 0),
-    SLC_VEC(8, 0, 0),
-    SLC_VEC(16, 9, 4),  SLC_VEC(16, 7, 4), SLC_VEC(16, 8, 4), SLC_VEC(16, 0, 0),
-    SLC_VEC(4, 9, 4),   SLC_VEC(4, 7, 4), SLC_VEC(4, 8, 4),  SLC_VEC(4, 6, 4), SLC_VEC(4, 8, 8), SLC_VEC(4, 10, 12),
+    SLC_VEC_TUNE(8, 5, 0),   SLC_VEC_TUNE(8, 6, 0),   SLC_VEC_TUNE(8, 7, 0),   SLC_VEC_TUNE(8, 8, 0),   SLC_VEC_TUNE(8, 9, 0),
+    SLC_VEC_TUNE(8, 10, 0),  SLC_VEC_TUNE(8, 0, 0),
+    SLC_VEC_TUNE(16, 9, 4),  SLC_VEC_TUNE(16, 7, 4), SLC_VEC_TUNE(16, 8, 4), SLC_VEC_TUNE(16, 0, 0),
+    SLC_VEC(4, 7, 4),   SLC_VEC(4, 8, 4),
+    SLC_VEC_TUNE(4, 9, 4),   SLC_VEC_TUNE(4, 6, 4), SLC_VEC_TUNE(4, 8, 8), SLC_VEC_TUNE(4, 10, 12),
     SLC_VEC(4, 5, 0),   SLC_VEC(4, 6, 0),   SLC_VEC(4, 7, 0),   SLC_VEC(4, 8, 0),   SLC_VEC(4, 9, 0),   SLC_VEC(4, 10, 0),
     // the remaining legal depths (CDecodeGray.cpp:39: 1..16), so that no geometry falls back to run-time loops
     SLC_VEC(4, 1, 0),   SLC_VEC(4, 2, 0),   SLC_VEC(4, 3, 0),   SLC_VEC(4, 4, 0),   SLC_VEC(4, 11, 0),  SLC_VEC(4, 12, 0),
@@ -507,11 +573,11 @@ const VecEntry kVecTable[] = {
     SLC_VEC(4, 0, 0),
 };
 
-const VecEntry* find_vec(int G, int N, int pxt, int mode, bool* specialised)
+const VecEntry* find_vec(int G, int N, int pxt, int mode, int out, bool* specialised)
 {
     const VecEntry *generic = nullptr, *gray_only = nullptr;
     for (const VecEntry& e : kVecTable) {
-        if (e.pxt != pxt || e.mode != mode) continue;
+        if (e.pxt != pxt || e.mode != mode || e.out != out) continue;
         if (e.G == G && e.N == N) { *specialised = true; return &e; }
         if (e.G == G && e.N == 0) gray_only = &e;
         if (e.G == 0 && e.N == 0) generic = &e;
@@ -519,8 +585,6 @@ const VecEntry* find_vec(int G, int N, int pxt, int mode, bool* specialised)
     *specialised = false;
     return gray_only ? gray_only : generic;
 }
-
-int g_forced_pxt = 0;      // 0 = pick per geometry
 
 // Pixels per thread: 8 (one 8-byte load per plane, 64 registers, 4 blocks / SM) is the fastest shape
 // for most instances; the 4-step G = 7 and G = 8 instances run at 0.87 / 0.83 of the HBM peak with 8 and
@@ -530,75 +594,113 @@ int preferred_pxt(int G, int N)
 {
     if (N == 4 && (G == 7 || G == 8)) return 4;
     bool exact = false;
-    find_vec(G, N, 8, 0, &exact);
-    return exact ? 8 : 4;
+    const VecEntry* e = find_vec(G, N, 8, 0, 0, &exact);
+    return (e != nullptr && exact) ? 8 : 4;
 }
 
 }  // namespace
 
-void set_default_pixels_per_thread(int pxt)
-{
-    if (pxt == 0 || pxt == 4 || pxt == 8 || pxt == 16) g_forced_pxt = pxt;
-}
-
 bool vector_kernel_applicable(const KParams& p, int pxt)
 {
     // groups must not straddle rows and every plane base must stay PXT-aligned
-    return (p.W % pxt == 0) && (p.npx % 16 == 0) && (reinterpret_cast<uintptr_t>(p.stack) % 16 == 0) &&
-           (reinterpret_cast<uintptr_t>(p.mask) % 16 == 0) && (reinterpret_cast<uintptr_t>(p.xyzw) % 16 == 0);
+    auto a16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+    const bool outs = p.depth ? (a16(p.depth) && (reinterpret_cast<uintptr_t>(p.mask_bits) & 1) == 0 && (p.bits_stride & 1) == 0)
+                              : (a16(p.mask) && a16(p.xyzw));
+    return (p.W % pxt == 0) && (p.npx % 16 == 0) && a16(p.stack) && outs;
 }
 
-cudaError_t launch_reconstruct(KParams p, bool force_scalar, cudaStream_t stream, LaunchInfo* info)
+// Chooses the kernel for (geometry, mode, output layout) ONCE: table scan, dynamic shared-memory
+// attribute and register count are paid here, not per launch.
+cudaError_t plan_reconstruct(const KParams& geom, int mode, int out, int pxt_override, LaunchPlan* plan)
+{
+    *plan = LaunchPlan{};
+    plan->mode = mode;
+    plan->out = out;
+    int pxt = pxt_override ? pxt_override : preferred_pxt(geom.G, geom.N);
+    while (pxt >= 4 && geom.W % pxt != 0) pxt >>= 1;   // groups must not straddle rows
+    cudaFuncAttributes fa;
+    if (pxt >= 4 && geom.npx % 16 == 0 && geom.npx <= 0x7fffffffLL && !(mode == 2 && out == 1)) {
+        bool spec = false;
+        const VecEntry* e = find_vec(geom.G, geom.N, pxt, mode, out, &spec);
+        if (e == nullptr && pxt_override) {             // a forced shape that this (mode, layout) does not have
+            pxt = preferred_pxt(geom.G, geom.N);
+            while (pxt >= 4 && geom.W % pxt != 0) pxt >>= 1;
+            e = pxt >= 4 ? find_vec(geom.G, geom.N, pxt, mode, out, &spec) : nullptr;
+        }
+        if (e != nullptr) {
+            const int slot = out == 0 ? (int)sizeof(float4) : (int)sizeof(float2);
+            const int smem = (kBlock / 32) * 32 * (pxt + 1) * slot;
+            cudaError_t err = cudaFuncSetAttribute(e->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            if (err == cudaSuccess) err = cudaFuncGetAttributes(&fa, e->fn);
+            if (err != cudaSuccess) return err;
+            plan->vec = reinterpret_cast<const void*>(e->fn);
+            plan->pxt = pxt;
+            plan->smem = smem;
+            plan->vec_regs = fa.numRegs;
+            plan->specialised = spec;
+        }
+    }
+    cudaError_t err = cudaFuncGetAttributes(&fa, mode == 2 ? reconstruct_scalar_kernel<true> : reconstruct_scalar_kernel<false>);
+    if (err != cudaSuccess) return err;
+    plan->scalar_regs = fa.numRegs;
+    plan->valid = true;
+    return cudaSuccess;
+}
+
+int plan_mode(const KParams& p)
 {
     const bool parity = p.kbin || p.corr || p.phase_pix || p.proj_u;
-    const int mode = (parity || p.lut != nullptr || p.z_fp64) ? 2 : (p.use_mod ? 1 : 0);
+    return (parity || p.lut != nullptr || p.z_fp64) ? 2 : (p.use_mod ? 1 : 0);
+}
+
+cudaError_t launch_reconstruct(KParams p, const LaunchPlan& plan, bool force_scalar, cudaStream_t stream,
+                               LaunchInfo* info)
+{
     // v = off / W by multiplication: exact while off * W < 2^40 (split_row_col)
     p.row_magic = ((unsigned long long)p.npx * (unsigned long long)p.W < (1ull << 40))
                       ? ((1ull << 40) / (unsigned long long)p.W + 1ull) : 0ull;
-    int pxt = g_forced_pxt ? g_forced_pxt : preferred_pxt(p.G, p.N);
-    while (pxt >= 4 && p.W % pxt != 0) pxt >>= 1;   // groups must not straddle rows
-    if (pxt < 4) pxt = 0;
-    if (!force_scalar && pxt != 0 && vector_kernel_applicable(p, pxt)) {
-        bool spec = false;
-        const VecEntry* e = find_vec(p.G, p.N, pxt, mode, &spec);
-        if (e != nullptr) {
-            p.n_groups = p.npx / pxt;
-            const long long blocks = (p.n_groups + kBlock - 1) / kBlock;
-            const int smem = (kBlock / 32) * 32 * (pxt + 1) * (int)sizeof(float4);
-            if (blocks > 0x7fffffffLL || p.n_stacks > 65535 || p.npx > 0x7fffffffLL)
-                return cudaErrorInvalidConfiguration;
-            cudaError_t err = cudaFuncSetAttribute(e->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    const bool vec = !force_scalar && plan.vec != nullptr && vector_kernel_applicable(p, plan.pxt);
+    if (info) {
+        info->variant = vec ? (plan.specialised ? 0 : 1) : 2;
+        info->regs = vec ? plan.vec_regs : plan.scalar_regs;
+        info->block = kBlock;
+        info->smem = vec ? plan.smem : 0;
+        info->pxt = vec ? plan.pxt : 1;
+        if (info->query_only) return cudaSuccess;
+    }
+    if (p.n_stacks <= 0) return cudaSuccess;
+    if (vec) {
+        VecKernel fn = reinterpret_cast<VecKernel>(const_cast<void*>(plan.vec));
+        p.n_groups = p.npx / plan.pxt;
+        const long long blocks = (p.n_groups + kBlock - 1) / kBlock;
+        if (blocks > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
+        // grid.y carries the frame set: at most 65535 per launch, any number per call
+        const int total = p.n_stacks;
+        for (int done = 0; done < total; done += 65535) {
+            KParams q = p;
+            q.n_stacks = (total - done) < 65535 ? (total - done) : 65535;
+            q.stack = p.stack + (size_t)done * p.P * p.npx;
+            if (p.depth) { q.depth = p.depth + (size_t)done * p.npx; q.mask_bits = p.mask_bits + (size_t)done * p.bits_stride; }
+            else { q.xyzw = p.xyzw + (size_t)done * p.npx; q.mask = p.mask + (size_t)done * p.npx; }
+            if (p.kbin) q.kbin = p.kbin + (size_t)done * p.npx;
+            if (p.corr) q.corr = p.corr + (size_t)done * p.npx;
+            if (p.phase_pix) q.phase_pix = p.phase_pix + (size_t)done * p.npx;
+            if (p.proj_u) q.proj_u = p.proj_u + (size_t)done * p.npx;
+            fn<<<dim3((unsigned)blocks, (unsigned)q.n_stacks), kBlock, plan.smem, stream>>>(q);
+            const cudaError_t err = cudaGetLastError();
             if (err != cudaSuccess) return err;
-            if (info) {
-                cudaFuncAttributes fa;
-                err = cudaFuncGetAttributes(&fa, e->fn);
-                if (err != cudaSuccess) return err;
-                info->variant = spec ? 0 : 1;
-                info->regs = fa.numRegs;
-                info->block = kBlock;
-                info->smem = smem;
-                info->pxt = pxt;
-                if (info->query_only) return cudaSuccess;
-            }
-            e->fn<<<dim3((unsigned)blocks, (unsigned)p.n_stacks), kBlock, smem, stream>>>(p);
-            return cudaGetLastError();
         }
+        return cudaSuccess;
     }
     const long long total = p.npx * (long long)p.n_stacks;
     const long long blocks = (total + kBlock - 1) / kBlock;
     if (blocks > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
-    auto fn = parity ? reconstruct_scalar_kernel<true> : reconstruct_scalar_kernel<false>;
-    if (info) {
-        cudaFuncAttributes fa;
-        cudaError_t err = cudaFuncGetAttributes(&fa, fn);
+    if (p.depth) {
+        // the any-geometry kernel sets validity bits with atomicOr
+        const cudaError_t err = cudaMemsetAsync(p.mask_bits, 0, (size_t)p.bits_stride * p.n_stacks, stream);
         if (err != cudaSuccess) return err;
-        info->variant = 2;
-        info->regs = fa.numRegs;
-        info->block = kBlock;
-        info->smem = 0;
-        info->pxt = 1;
-        if (info->query_only) return cudaSuccess;
     }
+    auto fn = plan.mode == 2 ? reconstruct_scalar_kernel<true> : reconstruct_scalar_kernel<false>;
     fn<<<(unsigned)blocks, kBlock, 0, stream>>>(p);
     return cudaGetLastError();
 }

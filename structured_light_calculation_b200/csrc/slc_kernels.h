@@ -16,8 +16,23 @@ struct LaunchInfo {
     bool query_only = false;
 };
 
-// The fused decode -> unwrap -> triangulate kernel over p.n_stacks stacks.
-cudaError_t launch_reconstruct(KParams p, bool force_scalar, cudaStream_t stream, LaunchInfo* info);
+// Which kernel runs a (geometry, mode, output layout): chosen once per context (plan_reconstruct pays the
+// table scan, the shared-memory attribute and the register query), used by every launch.
+struct LaunchPlan {
+    bool valid = false;
+    int mode = 0;                 // 0 production, 1 + modulation test, 2 parity planes / custom table / Z_FP64
+    int out = 0;                  // 0 xyzw + u8 mask, 1 depth + bit mask (SLC_RESULT_DEPTH)
+    const void* vec = nullptr;    // the vector kernel, or nullptr when the geometry has none
+    int pxt = 0, smem = 0, vec_regs = 0, scalar_regs = 0;
+    bool specialised = false;
+};
+int plan_mode(const KParams& p);   // from the buffers / flags set in p
+cudaError_t plan_reconstruct(const KParams& geom, int mode, int out, int pxt_override, LaunchPlan* plan);
+
+// The fused decode -> unwrap -> triangulate kernel over p.n_stacks stacks (any count: split over
+// launches of 65535).  p.depth != nullptr selects the SLC_RESULT_DEPTH layout.
+cudaError_t launch_reconstruct(KParams p, const LaunchPlan& plan, bool force_scalar, cudaStream_t stream,
+                               LaunchInfo* info);
 
 cudaError_t launch_decode_gray(const KParams& p, const uint8_t* d_planes, double* d_gray_val,
                                int16_t* d_kbin, cudaStream_t stream);
@@ -55,6 +70,15 @@ cudaError_t launch_pointcloud(const KParams& p, int mode, int order, unsigned fl
 cudaError_t launch_format_g6(const double* d_values, long long n, unsigned flags, char* d_text, uint8_t* d_len,
                              cudaStream_t stream);
 
+// valid-only point lists, one launch per batch (slc_compact.cu)
+bool compact_supported(int W, int H, const void* d_mask, const void* d_xyzw);
+int compact_tiles(int W, int H, int order);
+size_t compact_state_bytes(int W, int H, int n_stacks);
+cudaError_t launch_compact(int W, int H, int n_stacks, int order, const float* d_xyzw, const uint8_t* d_mask,
+                           float* d_points, long long point_stride, uint8_t* d_mask_bits, long long bits_stride,
+                           unsigned long long* d_counts, unsigned long long* d_state, unsigned epoch,
+                           cudaStream_t stream);
+
 // input ingest (slc_ingest.cu)
 cudaError_t launch_bmp_unpack(const uint8_t* d_pixels, int width, int height, int bpp, int top_down, int row_stride,
                               int identity, const uint8_t* gray256, uint8_t* d_plane, cudaStream_t stream);
@@ -68,8 +92,5 @@ struct BmpPlane {
 };
 constexpr int kBmpBatchMax = 64;  // files per launch (the descriptors travel as kernel parameters: 64 x 304 B < 32 KB)
 cudaError_t launch_bmp_unpack_batch(const BmpPlane* planes, int n, cudaStream_t stream);
-
-// tuning hook (bench / tests): pixels per thread of the vector kernel, 4 / 8 / 16
-void set_default_pixels_per_thread(int pxt);
 
 }  // namespace slc

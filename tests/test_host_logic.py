@@ -16,7 +16,7 @@ def test_library_exports_every_declared_symbol(built_library):
     assert len(names) >= 25
     for n in names:
         assert hasattr(built_library, n), f"{n} declared in include/slcalc_b200.h but not exported"
-    assert built_library.slc_abi_version() == 1
+    assert built_library.slc_abi_version() == 2
     assert built_library.slc_status_string(4).decode().startswith("no CUDA device")
 
 
@@ -110,6 +110,30 @@ def test_shard_range_partitions():
             assert max(sizes) - min(sizes) <= 1
     with pytest.raises(ValueError):
         shard_range(4, 4, 4)
+
+
+def test_c_shard_range_is_the_same_partition(built_library):
+    """slc_shard_range (what slc_pool and a C++ caller use) == distributed.shard_range (what bench.py's ranks use)."""
+    from structured_light_calculation_b200 import capi
+    from structured_light_calculation_b200.distributed import shard_range
+    for n in (0, 1, 7, 4096, 4099):
+        for world in (1, 2, 3, 8):
+            for r in range(world):
+                assert capi.shard_range(n, r, world) == shard_range(n, r, world)
+    with pytest.raises(capi.SlcError):
+        capi.shard_range(4, 4, 4)
+
+
+def test_pool_without_a_device_fails_loudly(built_library):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from structured_light_calculation_b200 import capi
+    from structured_light_calculation_b200.configs import CONFIGS
+    with pytest.raises(capi.SlcError) as e:
+        capi.Pool(CONFIGS["config1"], [0, 1])
+    assert e.value.status == capi.SLC_ERR_NO_DEVICE and "no CPU path" in e.value.message
+    assert built_library.slc_pool_size(None) == 0
 
 
 def _gloo_worker(rank, world, port, out):

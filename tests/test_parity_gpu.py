@@ -67,6 +67,29 @@ def check_fast_modes(rec, planes, got_parity):
     fast = rec.reconstruct(planes, parity=False)
     assert bits_equal(fast["xyzw"], got_parity["xyzw"]), "MODE 0/1 xyzw differs from MODE 2"
     assert bits_equal(fast["mask"], got_parity["mask"]), "MODE 0/1 mask differs from MODE 2"
+    check_result_formats(rec, planes, got_parity)
+
+
+def check_result_formats(rec, planes, full):
+    """SLC_RESULT_DEPTH / SLC_RESULT_POINTS are selections of the checked xyzw + mask output, bit for bit."""
+    from structured_light_calculation_b200 import capi
+    cfg = rec.cfg
+    n, npx = full["mask"].shape[0], cfg.pixels
+    mask = full["mask"].reshape(n, npx)
+    d = rec.reconstruct_ex(planes, capi.SLC_RESULT_DEPTH)
+    assert bits_equal(d["depth"], np.ascontiguousarray(full["xyzw"][..., 2])), "DEPTH z differs from the xyzw map"
+    assert np.array_equal(capi.unpack_mask_bits(d["mask_bits"], n, npx), mask), "DEPTH bit mask differs from the byte mask"
+    if cfg.width % 8 != 0:
+        return
+    for order in (capi.SLC_ORDER_ROW_MAJOR, capi.SLC_ORDER_REFERENCE):
+        p = rec.reconstruct_ex(planes, capi.SLC_RESULT_POINTS, order)
+        assert np.array_equal(capi.unpack_mask_bits(p["mask_bits"], n, npx), mask), "POINTS bit mask"
+        for i in range(n):
+            xyz, m = full["xyzw"][i, ..., :3], full["mask"][i].astype(bool)
+            want = xyz[m] if order == capi.SLC_ORDER_ROW_MAJOR else np.transpose(xyz, (1, 0, 2))[m.T]
+            assert int(p["n_points"][i]) == want.shape[0], f"POINTS count, order {order}"
+            assert bits_equal(np.ascontiguousarray(p["points"][i, : want.shape[0]]), np.ascontiguousarray(want)), \
+                f"POINTS list differs from mask-selecting the map, order {order}"
 
 
 CASES = [
@@ -98,16 +121,13 @@ def test_fused_kernel_matches_oracle(built_library, oracle, base_calibration, ca
     name, G, N, PW, W, H, noise, mod = case
     cfg = StackConfig(W, H, PW, G, N, modulation_min=mod, name=name)
     cal, scene, planes = make_case(cfg, base_calibration, noise=noise, seed=G * 100 + N)
-    built_library.slc_tune_pixels_per_thread(pxt)
-    try:
-        rec = _reconstructor(cfg, cal)
-        got = rec.reconstruct(planes, parity=True)
-        assert rec.launch_count() == 1
-        assert rec.info().kernel_variant in (0, 1)
-        check_fast_modes(rec, planes, got)
-        rec.close()
-    finally:
-        built_library.slc_tune_pixels_per_thread(0)
+    rec = _reconstructor(cfg, cal)
+    rec.set_pixels_per_thread(pxt)          # per context: nothing process-wide
+    got = rec.reconstruct(planes, parity=True)
+    assert rec.launch_count() == 1
+    assert rec.info().kernel_variant in (0, 1)
+    check_fast_modes(rec, planes, got)
+    rec.close()
     want = oracle_run(oracle, cfg, cal, planes)
     check_parity(got, want, cfg)
     del capi
