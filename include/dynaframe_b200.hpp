@@ -230,6 +230,43 @@ private:
     bool calibrated_ = false;
 };
 
+// Several GPUs behind the reference's call protocol.  The reference's main() runs one
+// CCalculation over one sequence (main.cpp:42-45); its frame loop (CCalculation.cpp:221) is what a
+// multi-GPU user would shard.  CCalculationPool keeps Init() -> Calculate...() -> bool + ErrorHandling:
+// Init() reads the same parameters.yml / vGrayCode.txt as CCalculation::Init and replicates them to one
+// context per listed device; CalculateFirstBatch() runs n independent frame sets (each the 2G+N images
+// CalculateFirst would pull from the sensor, plane-major, contiguous) through slc_pool_reconstruct_host:
+// contiguous shards, one feeder thread + pinned multi-slot pipeline per GPU, no collective.
+class CCalculationPool {
+public:
+    explicit CCalculationPool(const StaticParameters& sp = StaticParameters());
+    ~CCalculationPool();
+    CCalculationPool(const CCalculationPool&) = delete;
+    CCalculationPool& operator=(const CCalculationPool&) = delete;
+
+    void SetParameterFile(const std::string& ymlPath) { m_paraFile = ymlPath; }
+    void SetGrayCodeFile(const std::string& path, const std::string& name) { m_codePath = path; m_codeName = name; }
+    // frame sets per upload / launch / download chunk and stream slots per GPU (before Init)
+    void SetPipeline(int framesPerChunk, int slots) { m_chunk = framesPerChunk; m_slots = slots; }
+
+    bool Init(const std::vector<int>& devices);     // twice => false, like CCalculation::Init (CCalculation.cpp:80-83)
+    int Devices() const;
+    // [lo, hi) of the n frame sets GPU `member` computes (slc_shard_range)
+    bool ShardRange(int n, int member, int& lo, int& hi) const;
+    // stacks: u8 [n][2G+N][H][W]; xyzw: f32 [n][H][W][4]; mask: u8 [n][H][W].  Host memory, ideally pinned.
+    bool CalculateFirstBatch(const uint8_t* stacks, int n, float* xyzw, uint8_t* mask);
+    // the same with a result format (SLC_RESULT_DEPTH / SLC_RESULT_POINTS: fewer bytes back over PCIe)
+    bool CalculateFirstBatch(const uint8_t* stacks, int n, const slc_result& out);
+    slc_pool* Handle() { return pool_; }
+
+private:
+    StaticParameters sp_;
+    slc_pool* pool_ = nullptr;
+    std::string m_paraFile = "parameters.yml";
+    std::string m_codePath = "Patterns/", m_codeName = "vGrayCode.txt";
+    int m_chunk = 2, m_slots = 4;
+};
+
 // Helpers shared by the classes and usable on their own.
 bool ReadCalibrationYaml(const std::string& path, double cam[9], double pro[9], double R[9], double T[3]);
 bool ReadGrayCodeFile(const std::string& file, int grayCodeSize, std::vector<int16_t>& gray2bin);

@@ -34,7 +34,16 @@
  *             (CDecodePhase.cpp:59-62; CCalculation.cpp:552-557).
  *   xyzw    : float  [n_stacks][H][W][4] = (x, y, z, U) -- m_xMat/m_yMat/m_zMat
  *             (CCalculation.cpp:118-120) packed, w = decoded projector column
- *             (m_ProjectorU, :115) rounded to f32.  Invalid pixel => x=y=z=0.
+ *             (m_ProjectorU, :115) rounded ONCE to f32 (0 where the [EXT] modulation
+ *             test rejects the pixel).  Invalid pixel => x=y=z=0.
+ *             Precision of w as an unwrapped phase 2*pi*U/T: half an f32 ulp of U
+ *             times 2*pi/T, i.e. <= 1e-4 rad (the north-star bar) for every column
+ *             inside the projector raster iff  ulp_f32(PW - 1)/2 * 2*pi/T <= 1e-4:
+ *             PW <= 4096 with T >= 8, PW <= 2048 with T >= 4, PW <= 1024 with
+ *             T >= 2 -- all BASELINE geometries (worst: 4096 / T = 8, 9.6e-5 rad).
+ *             Outside that range (e.g. PW 4096 with T = 4: 1.9e-4 rad; PW 65536 with
+ *             T = 2: 6.1e-3 rad) f32 cannot hold the bar; the exact value is the
+ *             proj_u parity plane (f64, bit-exact for every geometry).
  *   mask    : uint8  [n_stacks][H][W], 1 = modulation_ok && U != 0 &&
  *             fov_min <= z <= fov_max (CCalculation.cpp:678-682,701-704).
  *   parity planes (optional): kbin int16, corr int8, phase_pix float,
@@ -358,6 +367,14 @@ int slc_pointcloud_compact_device(slc_context *ctx, const float *d_xyzw, const u
                                   float *d_xyz, int64_t capacity_points, int64_t *points, void *cuda_stream);
 int slc_pointcloud_compact_host(slc_context *ctx, const float *h_xyzw, const uint8_t *h_mask, int32_t order,
                                 float *h_xyz, int64_t capacity_points, int64_t *points);
+/* The same for n_maps maps in ONE asynchronous launch (e.g. every frame of a dynamic sequence):
+ * d_points [n_maps][point_stride][3], d_n_points [n_maps] and the optional d_mask_bits [n_maps][(H*W+7)/8]
+ * stay on the device; nothing is read back, the call does not synchronise.  A map with more valid pixels
+ * than point_stride keeps the first point_stride of them (d_n_points still counts them all).  Needs a
+ * camera width that is a multiple of 8. */
+int slc_compact_points_device(slc_context *ctx, const float *d_xyzw, const uint8_t *d_mask, int32_t n_maps, int32_t order,
+                              float *d_points, int64_t point_stride, uint8_t *d_mask_bits, int64_t *d_n_points,
+                              void *cuda_stream);
 /* Parity hook for the number formatting alone: n doubles -> n slots of 16 chars (zero padded) and
  * their lengths, exactly as the text kernel formats them. */
 int slc_format_g6_host(slc_context *ctx, const double *h_values, int64_t n, uint32_t flags, char *h_text16,

@@ -551,6 +551,12 @@ static void hot_loops(const slo_config *cfg, const slo_calib *cal,
     if (phase_raw) memcpy(phase_raw, w->phase, npx * sizeof(double)); /* parity output only */
     /* the combine stage edits vPhaseMat in place (CCalculation.cpp:574-583) */
     combine_stage(cfg, w->gray, w->phase, w->U, corr, w->proj);
+    /* [EXT] a pixel the modulation test rejects has no projector column: ProjectorU = 0, the
+     * reference's own "no value" sentinel (CCalculation.cpp:678), so that Result(), FillCoordinate(i)
+     * and the dynamic frames -- which only test U == 0 -- skip it as well */
+    if (use_mod)
+        for (size_t q = 0; q < npx; q++)
+            if (!w->mod_ok[q]) w->U[q] = 0.0;
     coordinate_stage(cfg, cal, w->A, w->B, w->cC, w->cD, w->U,
                      use_mod ? w->mod_ok : NULL, w->x, w->y, w->z, mask);
 }

@@ -171,6 +171,7 @@ def load_library():
     L.slc_pointcloud_text_host.argtypes = [vp, vp, C.c_uint32, vp, C.c_int64, i64p, i64p]
     L.slc_pointcloud_compact_device.argtypes = [vp, vp, vp, i32, vp, C.c_int64, i64p, vp]
     L.slc_pointcloud_compact_host.argtypes = [vp, vp, vp, i32, vp, C.c_int64, i64p]
+    L.slc_compact_points_device.argtypes = [vp, vp, vp, i32, i32, vp, C.c_int64, vp, vp, vp]
     L.slc_format_g6_host.argtypes = [vp, vp, C.c_int64, C.c_uint32, vp, vp]
     L.slc_time_reconstruct_device.argtypes = [vp, vp, i32, vp, vp, i32, C.POINTER(C.c_float)]
     L.slc_launch_count.argtypes = [vp]
@@ -557,6 +558,13 @@ class Reconstructor:
         self._check(self.lib.slc_pointcloud_compact_device(self.h, d_xyzw, d_mask, order, d_xyz, capacity_points,
                                                            C.byref(n), stream))
         return int(n.value)
+
+    def compact_points_device(self, d_xyzw: int, d_mask: int, n_maps: int, d_points: int, point_stride: int,
+                              d_n_points: int, order: int = SLC_ORDER_ROW_MAJOR, d_mask_bits: int | None = None,
+                              stream: int | None = None):
+        """n_maps maps -> packed point lists in one asynchronous launch; everything stays on the device."""
+        self._check(self.lib.slc_compact_points_device(self.h, d_xyzw, d_mask, n_maps, order, d_points, point_stride,
+                                                       d_mask_bits, d_n_points, stream))
 
     def format_g6(self, values: np.ndarray, flags: int = 0) -> list[bytes]:
         """Device number formatting (printf "%g") of each value."""

@@ -1384,7 +1384,7 @@ int compact_run(slc_context* ctx, int order, const float* d_xyzw, const uint8_t*
     SLC_CUDA(ctx, cudaStreamSynchronize(st));
     if (points) *points = (int64_t)totals[0];
     if ((int64_t)totals[0] > capacity_points)
-        return fail(ctx, SLC_ERR_INVALID_ARG, "point cloud has %lld points, buffer holds %lld", (long long)totals[0],
+        return fail(ctx, SLC_ERR_INVALID_ARG, "point cloud needs room for %lld points, buffer holds %lld", (long long)totals[0],
                     (long long)capacity_points);
     return SLC_OK;
 }
@@ -1433,6 +1433,31 @@ int slc_pointcloud_compact_device(slc_context* ctx, const float* d_xyzw, const u
     SLC_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
     cudaStream_t st = cuda_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : ctx->stream;
     return compact_run(ctx, order, d_xyzw, d_mask, d_xyz, capacity_points, points, st);
+}
+
+int slc_compact_points_device(slc_context* ctx, const float* d_xyzw, const uint8_t* d_mask, int32_t n_maps, int32_t order,
+                              float* d_points, int64_t point_stride, uint8_t* d_mask_bits, int64_t* d_n_points,
+                              void* cuda_stream)
+{
+    if (!ctx) return SLC_ERR_INVALID_ARG;
+    if (n_maps < 0) return fail(ctx, SLC_ERR_INVALID_ARG, "n_maps < 0");
+    if (n_maps == 0) return SLC_OK;
+    if (!d_xyzw || !d_mask || !d_points || !d_n_points || point_stride < 0)
+        return fail(ctx, SLC_ERR_INVALID_ARG, "NULL buffer or negative point_stride");
+    if (order != SLC_ORDER_ROW_MAJOR && order != SLC_ORDER_REFERENCE)
+        return fail(ctx, SLC_ERR_INVALID_ARG, "order %d is neither SLC_ORDER_ROW_MAJOR nor SLC_ORDER_REFERENCE", order);
+    if (!slc::compact_supported(ctx->kp.W, ctx->kp.H, d_mask, d_xyzw))
+        return fail(ctx, SLC_ERR_INVALID_ARG, "batched compaction needs a camera width that is a multiple of 8, a height below 65536, "
+                                              "16-byte aligned xyzw and 8-byte aligned mask");
+    SLC_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+    cudaStream_t st = cuda_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : ctx->stream;
+    int rc = ensure_cstate(ctx, n_maps, st);
+    if (rc != SLC_OK) return rc;
+    SLC_CUDA(ctx, slc::launch_compact(ctx->kp.W, ctx->kp.H, n_maps, order, d_xyzw, d_mask, d_points, (long long)point_stride,
+                                      d_mask_bits, (long long)bits_bytes(ctx), reinterpret_cast<unsigned long long*>(d_n_points),
+                                      static_cast<unsigned long long*>(ctx->d_cstate), ++ctx->cstate_epoch, st));
+    ctx->launches += (n_maps + 65534) / 65535;
+    return SLC_OK;
 }
 
 int slc_pointcloud_compact_host(slc_context* ctx, const float* h_xyzw, const uint8_t* h_mask, int32_t order,

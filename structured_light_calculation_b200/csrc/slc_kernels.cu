@@ -68,12 +68,16 @@ template <> struct Slot<1> {
 // MODE 2: everything decided at run time (parity planes, custom LUT, SLC_FLAG_Z_FP64, modulation)
 template <int MODE, bool Z64>
 __device__ __forceinline__ float solve_pixel(const KParams& p, const RowConst& rc, int kbin, float s, float c,
-                                             float uf, PixelResult& r)
+                                             float uf, PixelResult& r, bool& mod_ok)
 {
     const float pix = phase_to_pix(fast_atan2_deg(s, c), p.Tf);
-    bool mod_ok = true;
+    mod_ok = true;
     if (MODE == 1 || (MODE == 2 && p.use_mod)) mod_ok = __fadd_rn(__fmul_rn(s, s), __fmul_rn(c, c)) >= p.thr2;
     unwrap_and_triangulate<MODE == 2, Z64>(p, rc, kbin, pix, mod_ok, uf, r);
+    // [EXT] a pixel the modulation test rejects has no projector column: U = 0, the reference's own
+    // "no value" sentinel (CCalculation.cpp:678), in w and in the proj_u plane -- so that Result(),
+    // FillCoordinate(i) and the dynamic frames, which only test U == 0, skip it too
+    if (MODE == 1 || (MODE == 2 && p.use_mod)) r.w = mod_ok ? r.w : 0.f;
     return pix;
 }
 
@@ -230,8 +234,9 @@ reconstruct_vec_kernel(const __grid_constant__ KParams p)
                 const float uf = u0f + (float)i;
                 PixelResult r;
                 float pix;
-                if (z64) pix = solve_pixel<MODE, true>(p, rc, kbin, sv[i], cv[i], uf, r);
-                else pix = solve_pixel<MODE, false>(p, rc, kbin, sv[i], cv[i], uf, r);
+                bool mod_ok;
+                if (z64) pix = solve_pixel<MODE, true>(p, rc, kbin, sv[i], cv[i], uf, r, mod_ok);
+                else pix = solve_pixel<MODE, false>(p, rc, kbin, sv[i], cv[i], uf, r, mod_ok);
                 // pixels awaiting the f64 re-solve park (gint, pix) in their tile slot
                 if constexpr (OUT == 0) trow[i] = make_float4(r.need64 ? r.gint : r.x, r.need64 ? pix : r.y, r.z, r.w);
                 else trow[i] = make_float2(r.need64 ? r.gint : r.z, pix);
@@ -242,7 +247,7 @@ reconstruct_vec_kernel(const __grid_constant__ KParams p)
                     if (p.kbin) p.kbin[o] = (int16_t)kbin;
                     if (p.corr) p.corr[o] = (int8_t)r.corr;
                     if (p.phase_pix) p.phase_pix[o] = pix;
-                    if (p.proj_u) p.proj_u[o] = __dadd_rn((double)r.gint, (double)pix);
+                    if (p.proj_u) p.proj_u[o] = mod_ok ? __dadd_rn((double)r.gint, (double)pix) : 0.0;
                 }
             }
         }
@@ -372,7 +377,7 @@ reconstruct_scalar_kernel(const __grid_constant__ KParams p)
     const RowConst rc = make_row_const(p, v);
     if (p.z_fp64) unwrap_and_triangulate<true, true>(p, rc, kbin, pix, mod_ok, (float)u, r);
     else unwrap_and_triangulate<true, false>(p, rc, kbin, pix, mod_ok, (float)u, r);
-    float4 outv = make_float4(r.x, r.y, r.z, r.w);
+    float4 outv = make_float4(r.x, r.y, r.z, mod_ok ? r.w : 0.f);   // [EXT] rejected by the modulation test: U = 0
     int ok = r.valid ? 1 : 0;
     if (r.need64) outv = resolve_f64(p, r.gint, pix, u, v, &ok);
     if (p.depth) {
@@ -390,7 +395,7 @@ reconstruct_scalar_kernel(const __grid_constant__ KParams p)
         if (p.kbin) p.kbin[idx] = (int16_t)kbin;
         if (p.corr) p.corr[idx] = (int8_t)r.corr;
         if (p.phase_pix) p.phase_pix[idx] = pix;
-        if (p.proj_u) p.proj_u[idx] = __dadd_rn((double)r.gint, (double)pix);
+        if (p.proj_u) p.proj_u[idx] = mod_ok ? __dadd_rn((double)r.gint, (double)pix) : 0.0;
     }
 }
 

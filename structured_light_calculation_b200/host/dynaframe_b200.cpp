@@ -633,4 +633,79 @@ Mat CCalculation::GetY() const { return channel_as_f64(m_xyzw, 1); }
 Mat CCalculation::GetZ() const { return channel_as_f64(m_xyzw, 2); }
 Mat CCalculation::GetProjectorU() const { return m_projU.clone(); }
 
+// ---- CCalculationPool -------------------------------------------------------------------
+CCalculationPool::CCalculationPool(const StaticParameters& sp) : sp_(sp) {}
+
+CCalculationPool::~CCalculationPool()
+{
+    if (pool_) slc_pool_destroy(pool_);
+}
+
+bool CCalculationPool::Init(const std::vector<int>& devices)
+{
+    if (pool_ != nullptr) return false;                             // CCalculation.cpp:80-83
+    if (devices.empty()) { ErrorHandling("CCalculationPool::Init()->no device listed."); return false; }
+    slc_config cfg = make_cfg(sp_, sp_.PROJECTOR_RESLINE, sp_.GRAY_V_NUMDIGIT, sp_.PHASE_NUMDIGIT);
+    cfg.max_batch = m_chunk;
+    cfg.num_slots = m_slots;
+    std::vector<int32_t> devs(devices.begin(), devices.end());
+    if (slc_pool_create(&cfg, devs.data(), (int32_t)devs.size(), &pool_) != SLC_OK) {
+        ErrorHandling(std::string("CCalculationPool::Init()->") + slc_pool_last_error(nullptr));
+        pool_ = nullptr;
+        return false;
+    }
+    auto fail = [&](const std::string& msg) {
+        ErrorHandling(msg);
+        slc_pool_destroy(pool_);
+        pool_ = nullptr;
+        return false;
+    };
+    // :124-132 calibration, replicated to every GPU
+    double cam[9], pro[9], R[9], T[3];
+    if (!ReadCalibrationYaml(sp_.DATA_PATH + m_paraFile, cam, pro, R, T))
+        return fail("CCalculationPool::Init() OpenFile Error:" + sp_.DATA_PATH + m_paraFile);
+    if (slc_pool_set_calibration(pool_, cam, pro, R, T) != SLC_OK)
+        return fail(std::string("CCalculationPool::Init()->") + slc_pool_last_error(pool_));
+    // CDecodeGray.cpp:113-125 Gray code table
+    if (!m_codeName.empty()) {
+        const int n = 1 << sp_.GRAY_V_NUMDIGIT;
+        std::vector<int16_t> lut;
+        if (!ReadGrayCodeFile(m_codePath + m_codeName, n, lut)) return fail("Gray Decode->Open file error.");
+        if (slc_pool_set_gray_lut(pool_, lut.data(), n) != SLC_OK)
+            return fail(std::string("Gray Decode->") + slc_pool_last_error(pool_));
+    }
+    return true;
+}
+
+int CCalculationPool::Devices() const { return slc_pool_size(pool_); }
+
+bool CCalculationPool::ShardRange(int n, int member, int& lo, int& hi) const
+{
+    int64_t a = 0, b = 0;
+    if (!pool_ || slc_shard_range(n, member, slc_pool_size(pool_), &a, &b) != SLC_OK) return false;
+    lo = (int)a;
+    hi = (int)b;
+    return true;
+}
+
+bool CCalculationPool::CalculateFirstBatch(const uint8_t* stacks, int n, const slc_result& out)
+{
+    if (pool_ == nullptr) { ErrorHandling("CCalculationPool::CalculateFirstBatch()->Init first."); return false; }   // :176-181
+    if (slc_pool_reconstruct_host(pool_, stacks, n, &out) != SLC_OK) {
+        ErrorHandling(std::string("CCalculationPool::CalculateFirstBatch()->") + slc_pool_last_error(pool_));
+        return false;
+    }
+    return true;
+}
+
+bool CCalculationPool::CalculateFirstBatch(const uint8_t* stacks, int n, float* xyzw, uint8_t* mask)
+{
+    slc_result r;
+    std::memset(&r, 0, sizeof(r));
+    r.format = SLC_RESULT_XYZW;
+    r.xyzw = xyzw;
+    r.mask = mask;
+    return CalculateFirstBatch(stacks, n, r);
+}
+
 }  // namespace dynaframe

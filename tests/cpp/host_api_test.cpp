@@ -157,6 +157,47 @@ int main(int argc, char** argv)
             std::printf("file-backed sensor ok\n");
         }
     }
+    {   // several GPUs behind the same protocol (here: two members on device 0): n frame sets in one call,
+        // contiguous shards, results identical to CCalculation's
+        CCalculationPool pool(sp);
+        CHECK(!pool.CalculateFirstBatch(planes.data(), 1, nullptr, nullptr));      // before Init
+        pool.SetParameterFile("parameters.yml");
+        pool.SetGrayCodeFile(dir + "/", "vGrayCode.txt");
+        pool.SetPipeline(1, 2);
+        CHECK(pool.Init({0, 0}));
+        CHECK(!pool.Init({0}));                                                    // twice
+        CHECK(pool.Devices() == 2);
+        int lo = -1, hi = -1;
+        CHECK(pool.ShardRange(3, 0, lo, hi) && lo == 0 && hi == 2);
+        CHECK(pool.ShardRange(3, 1, lo, hi) && lo == 2 && hi == 3);
+        const int n = 3;
+        const size_t sb = planes.size();
+        uint8_t* in = static_cast<uint8_t*>(slc_host_alloc(n * sb));
+        float* xyzw = static_cast<float*>(slc_host_alloc(n * npx * 16));
+        uint8_t* mask = static_cast<uint8_t*>(slc_host_alloc(n * npx));
+        CHECK(in && xyzw && mask);
+        for (int i = 0; i < n; i++) std::memcpy(in + i * sb, planes.data(), sb);
+        CHECK(pool.CalculateFirstBatch(in, n, xyzw, mask));
+        for (int i = 0; i < n; i++) {
+            CHECK(std::memcmp(xyzw + (size_t)i * npx * 4, calc.PointMap().ptr(), npx * 16) == 0);
+            CHECK(std::memcmp(mask + (size_t)i * npx, calc.ValidMask().ptr(), npx) == 0);
+        }
+        // depth-only result: z plane + one validity bit per pixel
+        float* depth = static_cast<float*>(slc_host_alloc(n * npx * 4));
+        uint8_t* bits = static_cast<uint8_t*>(slc_host_alloc(n * ((npx + 7) / 8) + 4));
+        slc_result r;
+        std::memset(&r, 0, sizeof(r));
+        r.format = SLC_RESULT_DEPTH;
+        r.depth = depth;
+        r.mask_bits = bits;
+        CHECK(pool.CalculateFirstBatch(in, n, r));
+        for (size_t q = 0; q < npx; q++) {
+            CHECK(depth[2 * npx + q] == calc.PointMap().at<float>((int)(q / W), 4 * (int)(q % W) + 2));
+            CHECK(((bits[2 * ((npx + 7) / 8) + (q >> 3)] >> (q & 7)) & 1) == calc.ValidMask().at<uint8_t>((int)(q / W), (int)(q % W)));
+        }
+        slc_host_free(in); slc_host_free(xyzw); slc_host_free(mask); slc_host_free(depth); slc_host_free(bits);
+        std::printf("pool ok\n");
+    }
     std::printf("host_api_test ok\n");
     return 0;
 }

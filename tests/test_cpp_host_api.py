@@ -58,7 +58,7 @@ def test_cpp_host_api_matches_oracle(tmp_path, built_library, oracle, base_calib
     res = subprocess.run([exe, str(d), str(W), str(H), str(PW), str(G), str(N)], stdout=subprocess.PIPE,
                          stderr=subprocess.STDOUT, text=True)
     assert res.returncode == 0, res.stdout
-    assert "host_api_test ok" in res.stdout and "file-backed sensor ok" in res.stdout
+    assert "host_api_test ok" in res.stdout and "file-backed sensor ok" in res.stdout and "pool ok" in res.stdout
     want = oracle_run(oracle, cfg, cal, planes)
     gray = np.fromfile(d / "gray.f64", np.float64).reshape(H, W)
     phase = np.fromfile(d / "phase.f64", np.float64).reshape(H, W)

@@ -166,3 +166,27 @@ def test_pointcloud_and_ingest_error_paths(built_library, base_calibration):
     # the context is still usable after every failure
     assert rec.pointcloud_compact_device(d_xyzw.data_ptr(), d_mask.data_ptr(), d_xyz.data_ptr(), 2048) == int(got["mask"].sum())
     rec.close()
+
+
+def test_modulation_rejected_pixels_have_no_projector_column(built_library, oracle, base_calibration):
+    """[EXT] modulation mask on: a rejected pixel carries U = 0 (the reference's own "no value" sentinel,
+    CCalculation.cpp:678) in w and in the proj_u plane, so everything downstream that only tests U == 0 --
+    Result()'s text cloud, FillCoordinate(i) on the plane -- agrees with the validity mask."""
+    from structured_light_calculation_b200.configs import StackConfig
+    cfg = StackConfig(272, 128, 2048, 8, 8, modulation_min=8.0)
+    cal, scene, planes = make_case(cfg, base_calibration, noise=1.0, seed=23)
+    want = oracle_run(oracle, cfg, cal, planes)
+    rejected = want["mod_ok"] == 0
+    assert rejected.any() and not rejected.all()
+    assert not want["proj_u"][rejected].any()
+    rec = _rec(cfg, cal)
+    got = rec.reconstruct(planes, parity=True)
+    assert np.array_equal(got["proj_u"][0], want["proj_u"]) and np.array_equal(got["mask"][0], want["mask"])
+    assert not got["proj_u"][0][rejected].any() and not got["xyzw"][0][rejected].any()
+    fast = rec.reconstruct(planes)                               # MODE 1 (no parity planes): same w
+    assert np.array_equal(fast["xyzw"], got["xyzw"])
+    text, npts = rec.pointcloud_text(got["proj_u"][0])
+    assert npts == int(got["mask"][0].sum()) == text.count(b"\n")
+    xyzw, mask = rec.triangulate(got["proj_u"][0])
+    assert np.array_equal(mask, got["mask"][0])
+    rec.close()
