@@ -937,7 +937,8 @@ def main():
     ap.add_argument("--batch", type=int, default=256, help="frame sets per step (device-resident batch)")
     ap.add_argument("--pool", type=int, default=4, help="distinct rendered stacks tiled into the batch")
     ap.add_argument("--e2e-stacks", type=int, default=24, help="frame sets per end-to-end step")
-    ap.add_argument("--e2e-chunk", type=int, default=2, help="frame sets per upload/launch/download chunk")
+    ap.add_argument("--e2e-chunk", type=int, default=1, help="frame sets per upload/launch/download chunk "
+                    "(1: the shortest pipeline ramp; measured 982 / 939 / 900 frame sets/s with 1 / 2 / 4 on one box)")
     ap.add_argument("--e2e-slots", type=int, default=4)
     ap.add_argument("--e2e-mem", default="pinned", choices=["pinned", "wc", "huge"],
                     help="host memory of the end-to-end input ring: cudaHostAlloc, write-combined, 2 MB pages")
@@ -1115,7 +1116,8 @@ def main():
                                       "order + bit mask), " + slots_note, world, ceiling)
     e2e_compact["points"]["valid_fraction"] = n_pts / (E * cfg.pixels)
 
-    # ---- one process, a feeder thread per GPU (slc_pool): rank 0 drives every GPU, the other ranks wait ----
+    # ---- one process, a feeder thread per GPU (slc_pool): rank 0 drives every GPU, the other ranks wait.
+    #      Frame sets are handed out on demand, so GPUs behind a faster host link take more of them. ----
     e2e_pool = None
     if world > 1:
         D.barrier()
@@ -1126,21 +1128,31 @@ def main():
             p_in = capi.PinnedArray((PE, cfg.planes, cfg.height, cfg.width), np.uint8, memflag)
             for i in range(PE):
                 p_in.array[i] = stacks[i % len(stacks)]
-            pb, pres = capi.alloc_result(cfg, PE, capi.SLC_RESULT_XYZW, pinned=True)
-            for _ in range(2):
-                pool.reconstruct_into_ex(p_in, PE, pres)
-            t0 = time.perf_counter()
-            for _ in range(e2e_steps):
-                pool.reconstruct_into_ex(p_in, PE, pres)
-            ps = time.perf_counter() - t0
-            same = bool(np.array_equal(pb["mask"].array[E], h_mask.array[0]) and
-                        np.array_equal(pb["xyzw"].array[PE - E], h_xyzw.array[0]))
-            e2e_pool = e2e_entry(PE * e2e_steps / ps, E * cfg.stack_bytes, E * cfg.pixels * 17, E, e2e_steps, ps,
-                                 f"capi.Pool.reconstruct_into_ex -> slc_pool_reconstruct_host: ONE process, {world} feeder "
-                                 f"threads (the other ranks idle at a barrier), " + slots_note, world, ceiling)
-            e2e_pool["equals_per_rank_result"] = same
+
+            def pool_run(fmt, d2h_per_set, what):
+                pb, pres = capi.alloc_result(cfg, PE, fmt, pinned=True)
+                for _ in range(2):
+                    pool.reconstruct_into_ex(p_in, PE, pres)
+                t0 = time.perf_counter()
+                for _ in range(e2e_steps):
+                    pool.reconstruct_into_ex(p_in, PE, pres)
+                ps = time.perf_counter() - t0
+                ent = e2e_entry(PE * e2e_steps / ps, E * cfg.stack_bytes, E * d2h_per_set, E, e2e_steps, ps,
+                                f"capi.Pool.reconstruct_into_ex -> slc_pool_reconstruct_host ({what}): ONE process, {world} feeder "
+                                f"threads, frame sets handed out on demand (the other ranks idle at a barrier), " + slots_note,
+                                world, ceiling)
+                ent["frame_sets_taken_per_gpu_last_call"] = pool.last_shares()
+                return pb, ent
+
+            pb, e2e_pool = pool_run(capi.SLC_RESULT_XYZW, cfg.pixels * 17, "xyzw + mask")
+            e2e_pool["equals_per_rank_result"] = bool(np.array_equal(pb["mask"].array[E], h_mask.array[0]) and
+                                                      np.array_equal(pb["xyzw"].array[PE - E], h_xyzw.array[0]))
+            del pb
+            pbd, ent = pool_run(capi.SLC_RESULT_DEPTH, cfg.pixels * 4 + capi.bits_bytes(cfg.pixels), "depth + bit mask")
+            ent["equals_per_rank_result"] = bool(np.array_equal(pbd["depth"].array[PE - E], bufs_d["depth"].array[0]))
+            e2e_pool["depth"] = ent
             pool.close()
-            del p_in, pb
+            del p_in, pbd
         D.barrier()
 
     os.sched_setaffinity(0, orig_affinity)   # the CPU baseline below may use every core again

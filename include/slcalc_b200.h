@@ -231,14 +231,23 @@ int slc_reconstruct_device_ex(slc_context *ctx, const uint8_t *d_stack, int32_t 
                               const slc_result *d_out, void *cuda_stream);
 int slc_reconstruct_host_ex(slc_context *ctx, const uint8_t *h_stack, int32_t n_stacks,
                             const slc_result *h_out);
+/* slc_submit_host with a result format (up to max_batch frame sets on a free slot; slc_wait completes it,
+ * and for SLC_RESULT_POINTS is also where the point lists are fetched, once their counts are known). */
+int slc_submit_host_ex(slc_context *ctx, int32_t slot, const uint8_t *h_stack, int32_t n_stacks,
+                       const slc_result *h_out);
 
 /* ---- several GPUs behind one call --------------------------- */
 /* replaces: the frame loop of CCalculation::CalculateOther (CCalculation.cpp:221) seen as independent
  * frame sets, i.e. what main.cpp:42-45 would shard.  A pool owns one context per listed device (a device
  * may be listed more than once) and one feeder thread per context; calibration and Gray table are
- * replicated.  Frame sets are split into contiguous shards (slc_shard_range) and every feeder runs the
- * pinned multi-slot upload / kernel / download pipeline of its context on its shard; there is no
- * data-path collective.  cfg->device is ignored. */
+ * replicated.  slc_pool_reconstruct_host hands frame sets out ON DEMAND, max_batch at a time: each feeder
+ * keeps the stream slots of its context full (slc_submit_host_ex / slc_wait) and takes the next chunk as
+ * soon as a slot frees up, so a GPU behind a faster host link takes more of the batch (on the pool's
+ * 8-GPU hosts four of the GPUs share an uplink and move 2/3 of what the other four do,
+ * profiles/r02_hostlink_probe.txt) and the pipeline never drains between chunks.  Results land at the index
+ * of their frame set whoever computed it.  slc_pool_reconstruct_device takes caller-made shards
+ * (slc_shard_range gives the contiguous equal split).  There is no data-path collective.  cfg->device is
+ * ignored. */
 typedef struct slc_pool slc_pool;
 int slc_pool_create(const slc_config *cfg, const int32_t *devices, int32_t n_devices, slc_pool **out);
 void slc_pool_destroy(slc_pool *pool);
@@ -250,9 +259,11 @@ int slc_pool_set_calibration(slc_pool *pool, const double cam[9], const double p
 int slc_pool_set_gray_lut(slc_pool *pool, const int16_t *gray2bin, int32_t n);
 /* contiguous block [*lo, *hi) of n_items for shard `index` of `n_shards`; sizes differ by at most one */
 int slc_shard_range(int64_t n_items, int32_t index, int32_t n_shards, int64_t *lo, int64_t *hi);
-/* n_stacks frame sets in host memory -> results in host memory, all members at once; blocks. */
+/* n_stacks frame sets in host memory -> results in host memory, all members at once; blocks.
+ * slc_pool_last_shares(): how many frame sets each member took in the last call. */
 int slc_pool_reconstruct_host(slc_pool *pool, const uint8_t *h_stack, int32_t n_stacks,
                               const slc_result *h_out);
+int slc_pool_last_shares(const slc_pool *pool, int32_t *frame_sets_per_member, int32_t n_members);
 /* Device-resident shards: member i runs n_stacks[i] frame sets from d_stack[i] into d_out[i] (device
  * pointers on that member's GPU) and the call returns when every GPU has finished. */
 int slc_pool_reconstruct_device(slc_pool *pool, const uint8_t *const *d_stack, const int32_t *n_stacks,

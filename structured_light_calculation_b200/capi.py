@@ -152,6 +152,8 @@ def load_library():
     L.slc_pool_set_gray_lut.argtypes = [vp, vp, i32]
     L.slc_shard_range.argtypes = [C.c_int64, i32, i32, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     L.slc_pool_reconstruct_host.argtypes = [vp, vp, i32, C.POINTER(SlcResult)]
+    L.slc_pool_last_shares.argtypes = [vp, C.POINTER(i32), i32]
+    L.slc_submit_host_ex.argtypes = [vp, i32, vp, i32, C.POINTER(SlcResult)]
     L.slc_pool_reconstruct_device.argtypes = [vp, C.POINTER(vp), C.POINTER(i32), C.POINTER(SlcResult)]
     L.slc_decode_gray_host.argtypes = [vp, vp, vp, vp]
     L.slc_decode_phase_host.argtypes = [vp, vp, vp, vp]
@@ -415,6 +417,9 @@ class Reconstructor:
     def submit(self, slot: int, h_stack, n_stacks: int, h_xyzw, h_mask):
         self._check(self.lib.slc_submit_host(self.h, slot, _ptr(h_stack), n_stacks, _ptr(h_xyzw), _ptr(h_mask)))
 
+    def submit_ex(self, slot: int, h_stack, n_stacks: int, result: SlcResult):
+        self._check(self.lib.slc_submit_host_ex(self.h, slot, _ptr(h_stack), n_stacks, C.byref(result)))
+
     def wait(self, slot: int):
         self._check(self.lib.slc_wait(self.h, slot))
 
@@ -643,6 +648,12 @@ class Pool:
 
     def reconstruct_into_ex(self, h_stack, n_stacks: int, result: SlcResult):
         self._check(self.lib.slc_pool_reconstruct_host(self.h, _ptr(h_stack), n_stacks, C.byref(result)))
+
+    def last_shares(self) -> list[int]:
+        """Frame sets each member took in the last reconstruct_into_ex call (handed out on demand)."""
+        out = (C.c_int32 * self.n)()
+        self._check(self.lib.slc_pool_last_shares(self.h, out, self.n))
+        return list(out)
 
     def reconstruct_device(self, d_stacks, n_stacks, results):
         """Per-member device shards: d_stacks[i] / results[i] live on member i's GPU."""

@@ -53,7 +53,7 @@ struct Slot {
     cudaEvent_t counts_ready = nullptr;
     unsigned epoch = 0;
     // a POINTS chunk whose counts are on their way: its point download is issued once they are known
-    struct { bool active = false; int n = 0; float* h_points = nullptr; int64_t* h_n_points = nullptr; } pending;
+    struct { bool active = false; int n = 0; float* h_points = nullptr; int64_t* h_n_points = nullptr; int64_t stride = 0; } pending;
     bool busy = false;
 };
 
@@ -76,7 +76,8 @@ struct slc_context {
     void* d_scratch_aux = nullptr; size_t scratch_aux_bytes = 0;
     void* d_strips = nullptr;      size_t strips_bytes = 0;      // dynamic frames: (stripB, stripW) per frame
     void* d_dsums = nullptr;       size_t dsums_bytes = 0;       // dynamic frames: 3x3 sums of the nearer delta
-    void* d_pc_scratch = nullptr;  size_t pc_scratch_bytes = 0;  // point cloud: block sums
+    void* d_pc_scratch = nullptr;  size_t pc_scratch_bytes = 0;  // point cloud: block sums, totals, look-back words
+    unsigned pc_epoch = 0;                                       // launch epoch of the text kernel's look-back words
     void* d_pc_in = nullptr;       size_t pc_in_bytes = 0;       // point cloud: staging for the host entry points
     void* d_pc_out = nullptr;      size_t pc_out_bytes = 0;
     void* h_pc_totals = nullptr;                                   // point cloud: pinned (bytes, records) read-back
@@ -84,7 +85,7 @@ struct slc_context {
     void* h_bmp[kBmpSlots] = {};   size_t h_bmp_bytes[kBmpSlots] = {};   // ingest: raw file staging (pinned)
     cudaEvent_t bmp_done[kBmpSlots] = {};
     void* d_dyna = nullptr;        size_t dyna_bytes = 0;        // dynamic frames: staging for the host entry point
-    slc::LaunchPlan plans[3][2];                                 // [mode][output layout], chosen on first use
+    slc::LaunchPlan plans[3][2][2];                              // [mode][output layout][small launch], chosen on first use
     int pxt_override = 0;                                        // slc_set_pixels_per_thread
     void* d_cstate = nullptr;      size_t cstate_bytes = 0;      // POINTS on the device path: look-back state
     unsigned cstate_epoch = 0;
@@ -139,11 +140,26 @@ int ensure_parity(slc_context* ctx, Slot& s, const slc_parity_planes* want)
 
 size_t bits_bytes(const slc_context* c) { return ((size_t)c->kp.npx + 7) / 8; }
 
-// the kernel for (mode, output layout) of this context: chosen once, then only launched
-int plan_for(slc_context* ctx, int mode, int out, const slc::LaunchPlan** plan)
+// A launch below this many pixels does not fill the GPU for long enough to hide its ramp-up and tail:
+// the 4-pixels-per-thread shape (twice the threads, finer tail) is faster there and slower above
+// (profiles/r02_launch_size_curve*.txt: 1 / 4 / 8 / 256 frame sets of 1920x1200 run at 0.72 / 0.92 / 0.95 / 0.95
+// of the HBM peak with 4 pixels per thread and at 0.67 / 0.88 / 0.95 / 1.01 with 8).
+constexpr long long kSmallLaunchPixels = 16ll << 20;
+
+// the kernel for (mode, output layout, launch size class) of this context: chosen once, then only launched
+int plan_for(slc_context* ctx, int mode, int out, int n_stacks, const slc::LaunchPlan** plan)
 {
-    slc::LaunchPlan& pl = ctx->plans[mode][out];
-    if (!pl.valid) SLC_CUDA(ctx, slc::plan_reconstruct(ctx->kp, mode, out, ctx->pxt_override, &pl));
+    const int small = (ctx->pxt_override == 0 && (long long)n_stacks * ctx->kp.npx < kSmallLaunchPixels) ? 1 : 0;
+    slc::LaunchPlan& pl = ctx->plans[mode][out][small];
+    if (!pl.valid) {
+        SLC_CUDA(ctx, slc::plan_reconstruct(ctx->kp, mode, out, ctx->pxt_override, &pl));
+        if (small && pl.vec != nullptr && pl.pxt == 8) {
+            // only where the geometry has its own 4-pixel instance: a generic one would lose more than it gains
+            slc::LaunchPlan alt;
+            SLC_CUDA(ctx, slc::plan_reconstruct(ctx->kp, mode, out, 4, &alt));
+            if (alt.vec != nullptr && alt.pxt == 4 && alt.specialised == pl.specialised) pl = alt;
+        }
+    }
     *plan = &pl;
     return SLC_OK;
 }
@@ -168,7 +184,7 @@ int launch(slc_context* ctx, const uint8_t* d_stack, int n_stacks, float* d_xyzw
     p.lut = ctx->d_lut;
     const bool scalar = (ctx->cfg.flags & SLC_FLAG_SCALAR_KERNEL) != 0;
     const slc::LaunchPlan* plan = nullptr;
-    int rc = plan_for(ctx, slc::plan_mode(p), d_depth ? 1 : 0, &plan);
+    int rc = plan_for(ctx, slc::plan_mode(p), d_depth ? 1 : 0, n_stacks, &plan);
     if (rc != SLC_OK) return rc;
     SLC_CUDA(ctx, slc::launch_reconstruct(p, *plan, scalar, stream, nullptr));
     ctx->launches += (n_stacks + 65534) / 65535;
@@ -229,6 +245,9 @@ int enqueue_chunk(slc_context* ctx, Slot& s, const uint8_t* h_stack, int n, floa
 }  // namespace
 
 extern "C" {
+
+namespace { int finish_points(slc_context* ctx, Slot& s, bool* overflow); }   // result formats, below
+
 
 int slc_abi_version(void) { return SLC_ABI_VERSION; }
 
@@ -406,7 +425,7 @@ int slc_get_info(const slc_context* cctx, slc_info* out)
     p.mask = ctx->slots[0].d_mask;
     p.lut = ctx->d_lut;
     const slc::LaunchPlan* plan = nullptr;
-    int rc = plan_for(ctx, slc::plan_mode(p), 0, &plan);
+    int rc = plan_for(ctx, slc::plan_mode(p), 0, 1 << 20, &plan);   // the shape of a large launch
     if (rc != SLC_OK) return rc;
     SLC_CUDA(ctx, slc::launch_reconstruct(p, *plan, (ctx->cfg.flags & SLC_FLAG_SCALAR_KERNEL) != 0, nullptr, &li));
     out->kernel_variant = li.variant;
@@ -659,8 +678,17 @@ int slc_wait(slc_context* ctx, int32_t slot)
     if (!ctx) return SLC_ERR_INVALID_ARG;
     if (slot < 0 || slot >= (int)ctx->slots.size()) return fail(ctx, SLC_ERR_INVALID_ARG, "slot %d out of range", slot);
     SLC_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
-    SLC_CUDA(ctx, cudaStreamSynchronize(ctx->slots[slot].stream));
-    ctx->slots[slot].busy = false;
+    Slot& s = ctx->slots[slot];
+    bool overflow = false;
+    const int64_t stride = s.pending.stride;
+    const int rc = finish_points(ctx, s, &overflow);     // SLC_RESULT_POINTS: the counts are known now, fetch the lists
+    const cudaError_t e = cudaStreamSynchronize(s.stream);
+    s.busy = false;
+    if (rc != SLC_OK) return rc;
+    if (e != cudaSuccess) return fail(ctx, SLC_ERR_CUDA, "cudaStreamSynchronize failed: %s", cudaGetErrorString(e));
+    if (overflow)
+        return fail(ctx, SLC_ERR_INVALID_ARG, "a frame set has more valid pixels than point_stride = %lld: its list was cut (n_points holds the full counts)",
+                    (long long)stride);
     return SLC_OK;
 }
 
@@ -715,10 +743,11 @@ int ensure_points(slc_context* ctx, Slot& s)
 
 // The counts of the slot's POINTS chunk are on their way (or there): once known, download exactly
 // 12 * count bytes per frame set.
-int finish_points(slc_context* ctx, Slot& s, int64_t point_stride, bool* overflow)
+int finish_points(slc_context* ctx, Slot& s, bool* overflow)
 {
     if (!s.pending.active) return SLC_OK;
     s.pending.active = false;
+    const int64_t point_stride = s.pending.stride;
     SLC_CUDA(ctx, cudaEventSynchronize(s.counts_ready));
     const size_t npx = (size_t)ctx->kp.npx;
     for (int i = 0; i < s.pending.n; i++) {
@@ -761,6 +790,7 @@ int enqueue_chunk_fmt(slc_context* ctx, Slot& s, const uint8_t* h_stack, int n, 
         s.pending.n = n;
         s.pending.h_points = o.points;
         s.pending.h_n_points = o.n_points;
+        s.pending.stride = o.point_stride;
     }
     s.busy = true;
     return SLC_OK;
@@ -824,6 +854,22 @@ int slc_reconstruct_device_ex(slc_context* ctx, const uint8_t* d_stack, int32_t 
     return SLC_OK;
 }
 
+int slc_submit_host_ex(slc_context* ctx, int32_t slot, const uint8_t* h_stack, int32_t n_stacks, const slc_result* h_out)
+{
+    int rc = check_ready(ctx, h_stack, h_out, h_out, n_stacks);
+    if (rc != SLC_OK) return rc;
+    rc = check_result(ctx, h_out, false);
+    if (rc != SLC_OK) return rc;
+    if (h_out->format == SLC_RESULT_XYZW) return slc_submit_host(ctx, slot, h_stack, n_stacks, h_out->xyzw, h_out->mask);
+    if (slot < 0 || slot >= (int)ctx->slots.size()) return fail(ctx, SLC_ERR_INVALID_ARG, "slot %d out of range", slot);
+    if (n_stacks < 1 || n_stacks > ctx->cfg.max_batch)
+        return fail(ctx, SLC_ERR_INVALID_ARG, "n_stacks %d outside 1..max_batch (%d)", n_stacks, ctx->cfg.max_batch);
+    Slot& s = ctx->slots[slot];
+    if (s.busy) return fail(ctx, SLC_ERR_STATE, "slot %d still in flight: call slc_wait first", slot);
+    SLC_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+    return enqueue_chunk_fmt(ctx, s, h_stack, n_stacks, *h_out);
+}
+
 int slc_reconstruct_host_ex(slc_context* ctx, const uint8_t* h_stack, int32_t n_stacks, const slc_result* h_out)
 {
     int rc = check_ready(ctx, h_stack, h_out, h_out, n_stacks);
@@ -843,13 +889,13 @@ int slc_reconstruct_host_ex(slc_context* ctx, const uint8_t* h_stack, int32_t n_
         const int n = (n_stacks - done) < chunk ? (n_stacks - done) : chunk;
         Slot& s = ctx->slots[slot];
         // the chunk this slot ran S chunks ago: its counts are known by now, queue its point download
-        if (points) rc = finish_points(ctx, s, h_out->point_stride, &overflow);
+        if (points) rc = finish_points(ctx, s, &overflow);
         if (rc == SLC_OK)
             rc = enqueue_chunk_fmt(ctx, s, h_stack + (size_t)done * stack_bytes(ctx), n, result_at(ctx, *h_out, (size_t)done));
         slot = (slot + 1) % S;
     }
     for (int k = 0; k < S && points; k++) {       // oldest first
-        const int rc2 = finish_points(ctx, ctx->slots[(slot + k) % S], h_out->point_stride, &overflow);
+        const int rc2 = finish_points(ctx, ctx->slots[(slot + k) % S], &overflow);
         if (rc == SLC_OK) rc = rc2;
     }
     for (Slot& s : ctx->slots) {
@@ -1329,6 +1375,18 @@ static int load_bmp_planes_impl(slc_context* ctx, const char* const* paths, int3
 /* ---- point-cloud output ------------------------------------------------ */
 namespace {
 
+// block sums / totals / look-back words of the point-cloud kernels; zeroed when (re)allocated
+int ensure_pc_scratch(slc_context* ctx, cudaStream_t st)
+{
+    const size_t want = slc::pointcloud_scratch_bytes(ctx->kp.npx);
+    if (ctx->pc_scratch_bytes >= want) return SLC_OK;
+    int rc = ensure_scratch(ctx, &ctx->d_pc_scratch, &ctx->pc_scratch_bytes, want);
+    if (rc != SLC_OK) return rc;
+    SLC_CUDA(ctx, cudaMemsetAsync(ctx->d_pc_scratch, 0, want, st));
+    ctx->pc_epoch = 0;
+    return SLC_OK;
+}
+
 int pointcloud_run(slc_context* ctx, int mode, int order, uint32_t flags, const double* d_proj_u, const float* d_xyzw,
                    const uint8_t* d_mask, void* d_out, int64_t capacity_bytes, int64_t* bytes, int64_t* records,
                    cudaStream_t st)
@@ -1338,12 +1396,13 @@ int pointcloud_run(slc_context* ctx, int mode, int order, uint32_t flags, const 
     if (order != SLC_ORDER_ROW_MAJOR && order != SLC_ORDER_REFERENCE)
         return fail(ctx, SLC_ERR_INVALID_ARG, "order %d is neither SLC_ORDER_ROW_MAJOR nor SLC_ORDER_REFERENCE", order);
     if (reinterpret_cast<uintptr_t>(d_out) & 15) return fail(ctx, SLC_ERR_INVALID_ARG, "output buffer must be 16-byte aligned");
-    int rc = ensure_scratch(ctx, &ctx->d_pc_scratch, &ctx->pc_scratch_bytes, slc::pointcloud_scratch_bytes(ctx->kp.npx));
+    int rc = ensure_pc_scratch(ctx, st);
     if (rc != SLC_OK) return rc;
     const unsigned long long* d_totals = nullptr;
+    if (mode == 0) ctx->pc_epoch = ctx->pc_epoch % 3u + 1u;
     SLC_CUDA(ctx, slc::launch_pointcloud(ctx->kp, mode, order, flags, d_proj_u, d_xyzw, d_mask, d_out,
-                                         (unsigned long long)capacity_bytes, ctx->d_pc_scratch, &d_totals, st));
-    ctx->launches += 2;
+                                         (unsigned long long)capacity_bytes, ctx->d_pc_scratch, ctx->pc_epoch, &d_totals, st));
+    ctx->launches += mode == 0 ? 1 : 2;
     // the counts come back through a pinned word pair (a pageable destination costs a staged copy per call)
     if (!ctx->h_pc_totals) SLC_CUDA(ctx, cudaHostAlloc(&ctx->h_pc_totals, 2 * sizeof(unsigned long long), cudaHostAllocDefault));
     unsigned long long* totals = static_cast<unsigned long long*>(ctx->h_pc_totals);
@@ -1372,7 +1431,7 @@ int compact_run(slc_context* ctx, int order, const float* d_xyzw, const uint8_t*
     if (order != SLC_ORDER_ROW_MAJOR && order != SLC_ORDER_REFERENCE)
         return fail(ctx, SLC_ERR_INVALID_ARG, "order %d is neither SLC_ORDER_ROW_MAJOR nor SLC_ORDER_REFERENCE", order);
     int rc = ensure_cstate(ctx, 1, st);
-    if (rc == SLC_OK) rc = ensure_scratch(ctx, &ctx->d_pc_scratch, &ctx->pc_scratch_bytes, slc::pointcloud_scratch_bytes(ctx->kp.npx));
+    if (rc == SLC_OK) rc = ensure_pc_scratch(ctx, st);
     if (rc != SLC_OK) return rc;
     unsigned long long* d_count = static_cast<unsigned long long*>(ctx->d_pc_scratch);
     SLC_CUDA(ctx, slc::launch_compact(ctx->kp.W, ctx->kp.H, 1, order, d_xyzw, d_mask, d_xyz, (long long)capacity_points, nullptr, 0,
@@ -1565,8 +1624,9 @@ int slc_set_pixels_per_thread(slc_context* ctx, int32_t pxt)
     if (!ctx) return SLC_ERR_INVALID_ARG;
     if (pxt != 0 && pxt != 4 && pxt != 8 && pxt != 16) return fail(ctx, SLC_ERR_INVALID_ARG, "pixels per thread must be 0, 4, 8 or 16");
     ctx->pxt_override = pxt;
-    for (auto& row : ctx->plans)
-        for (auto& pl : row) pl = slc::LaunchPlan{};      // chosen again on the next launch
+    for (auto& a : ctx->plans)
+        for (auto& b : a)
+            for (auto& pl : b) pl = slc::LaunchPlan{};    // chosen again on the next launch
     return SLC_OK;
 }
 

@@ -64,9 +64,11 @@ cudaError_t launch_dyna_fused(KParams p, const signed char* d_strips, int n_fram
 
 // point-cloud output (slc_pointcloud.cu)
 size_t pointcloud_scratch_bytes(long long npx);
+// d_scratch: pointcloud_scratch_bytes() bytes, ZEROED when allocated; text_epoch: 1, 2, 3, 1, ... advancing with every
+// mode-0 launch on this scratch (the look-back words of the text kernel carry it)
 cudaError_t launch_pointcloud(const KParams& p, int mode, int order, unsigned flags, const double* d_proj_u,
                               const float* d_xyzw, const uint8_t* d_mask, void* d_out, unsigned long long capacity,
-                              void* d_scratch, const unsigned long long** d_totals, cudaStream_t stream);
+                              void* d_scratch, unsigned text_epoch, const unsigned long long** d_totals, cudaStream_t stream);
 cudaError_t launch_format_g6(const double* d_values, long long n, unsigned flags, char* d_text, uint8_t* d_len,
                              cudaStream_t stream);
 

@@ -3,19 +3,18 @@
 //
 // The reference walks the image u outer / v inner, skips pixels whose z is outside
 // [FOV_MIN_DISTANCE, FOV_MAX_DISTANCE] and writes "x y z\n" with ostream << double, i.e.
-// printf("%g") with precision 6.  Here that is a variable-length record emission:
-//   pass 1  pc_emit_kernel<MODE, false>  everything that needs f64, once per number: x, y, z and their six
-//                                        exactly rounded digits + decimal exponent (decode_g6), kept as
-//                                        three 32-bit codes + the line length per record (one uint4);
-//                                        lengths summed per block
-//   pass 2  pc_emit_kernel<MODE, true>   each block sums the counts of the blocks before it, scans the
-//                                        lengths, writes the characters of every record (emit_g6: integer
-//                                        work only) straight into its place in a shared-memory chunk laid
-//                                        out at the output's own 16-byte phase, and writes the chunk as uint4
-// MODE 0 records are text lines formatted from f64 x, y, z -- recomputed from the f64
-// ProjectorU plane in the reference's operation order (:686-687, :761-767), so the text is
-// byte-identical to what the reference's doubles print; MODE 1 records are packed float3 xyz
-// of the valid pixels of a float4 map (binary cloud / PLY body).
+// printf("%g") with precision 6.  Here that is a variable-length record emission in ONE launch
+// (pc_text_kernel), a chained scan over tiles of 2048 records in output order:
+//   phase A  everything that needs f64, once per number: x, y, z from the f64 ProjectorU plane in the
+//            reference's operation order (:686-687, :761-767) and their six exactly rounded digits +
+//            decimal exponent (decode_g6), kept in SHARED memory as three 32-bit codes + the line length
+//            per record; the tile's byte / line totals are published and the totals of the tiles before it
+//            summed (decoupled look-back; counts, flag and launch epoch travel in one 64-bit word)
+//   phase B  the characters of every record (emit_g6_fast: integer work only) go straight into their
+//            place in a shared-memory chunk laid out at the output's own 16-byte phase, written as uint4.
+// (Until round 2 this was two launches with a 16 B/px scratch round trip between them.)  The text is
+// byte-identical to what the reference's doubles print.  pc_emit_kernel<1, *> -- packed float3 xyz of the
+// valid pixels of a float4 map in two passes -- remains for the geometries slc_compact.cu does not take.
 #include "slc_kernels.h"
 
 namespace slc {
@@ -376,6 +375,130 @@ pc_emit_kernel(const __grid_constant__ KParams p, const PcArgs a)
     }
 }
 
+// ---- the text cloud in one launch ---------------------------------------------------------------
+// look-back word: [63:62] flag (1 = this tile's totals, 2 = inclusive prefix), [61:60] launch epoch (1..3;
+// every launch rewrites every tile's word, so a stale word always carries the previous launch's epoch),
+// [59:26] bytes, [25:0] lines -- the two counts add without meeting while a frame stays below 2^34 bytes
+// and 2^26 lines (67 M pixels).
+constexpr unsigned long long kTxAggregate = 1ull << 62, kTxInclusive = 2ull << 62, kTxCounts = (1ull << 60) - 1ull;
+
+__device__ __forceinline__ unsigned long long tx_ld(const unsigned long long* p)
+{
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void tx_st(unsigned long long* p, unsigned long long v)
+{
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+
+// exclusive prefix (packed bytes | lines) of the tiles before `tile`; every thread of warp 0 calls it
+__device__ __forceinline__ unsigned long long tx_lookback(unsigned long long* state, int tile, unsigned long long mine,
+                                                          unsigned epoch)
+{
+    const int lane = threadIdx.x & 31;
+    const unsigned long long tag = (unsigned long long)epoch << 60;
+    if (tile == 0) {
+        if (lane == 0) tx_st(state, kTxInclusive | tag | mine);
+        return 0ull;
+    }
+    if (lane == 0) tx_st(state + tile, kTxAggregate | tag | mine);
+    unsigned long long prefix = 0ull;
+    for (int j = tile - 1;; j -= 32) {
+        const int idx = j - lane;
+        unsigned long long w;
+        bool ready;
+        do {
+            w = (idx >= 0) ? tx_ld(state + idx) : (kTxInclusive | tag);
+            ready = (((w >> 60) & 3ull) == (unsigned long long)epoch) && ((w >> 62) != 0ull);
+        } while (!__all_sync(0xFFFFFFFFu, ready));
+        const unsigned incl = __ballot_sync(0xFFFFFFFFu, (w >> 62) == 2ull);
+        const int stop = incl ? (__ffs((int)incl) - 1) : 31;
+        unsigned long long v = (lane <= stop) ? (w & kTxCounts) : 0ull;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, d);
+        prefix += v;
+        if (incl) break;
+    }
+    if (lane == 0) tx_st(state + tile, kTxInclusive | tag | (prefix + mine));
+    return prefix;
+}
+
+__global__ void __launch_bounds__(kPcThreads)
+pc_text_kernel(const __grid_constant__ KParams p, const PcArgs a, unsigned long long* __restrict__ state, unsigned epoch)
+{
+    __shared__ uint4 s_rec[kPcChunk];
+    __shared__ __align__(16) unsigned char s_txt[kPcThreads * kPcMaxLine + 32];
+    __shared__ int s_warp[kPcThreads / 32];
+    __shared__ unsigned long long s_red[kPcThreads / 32];
+    __shared__ unsigned long long s_prefix;
+    const int t = threadIdx.x, tile = (int)blockIdx.x;
+    const long long base = (long long)tile * kPcChunk;
+    const bool crlf = (a.flags & 1u) != 0u, exp3 = (a.flags & 2u) != 0u;
+
+    // ---- phase A: the codes of the tile's records, in output order (u outer, v inner) ----
+    unsigned long long mine = 0ull;                     // bytes << 26 | lines, this thread's records
+#pragma unroll 2
+    for (int it = 0; it < kPcIters; it++) {
+        const long long i = base + (long long)it * kPcThreads + t;
+        uint4 rec = make_uint4(0u, 0u, 0u, 0u);
+        if (i < a.npx) {
+            // npx < 2^31 (slc_create): 32-bit division, not the 64-bit emulation
+            const unsigned ii = (unsigned)i;
+            unsigned u, v;
+            if (a.order == 1) { u = ii / (unsigned)a.H; v = ii - u * (unsigned)a.H; }
+            else { v = ii / (unsigned)a.W; u = ii - v * (unsigned)a.W; }
+            rec = text_line_codes(p, a.proj_u[(long long)v * a.W + u], (int)u, (int)v, exp3, crlf);
+        }
+        s_rec[it * kPcThreads + t] = rec;
+        const unsigned len = rec.w & 63u;
+        mine += ((unsigned long long)len << 26) + (len ? 1ull : 0ull);
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) mine += __shfl_down_sync(0xFFFFFFFFu, mine, d);
+    if ((t & 31) == 0) s_red[t >> 5] = mine;
+    __syncthreads();
+    if (t < 32) {
+        unsigned long long tot = 0ull;
+#pragma unroll
+        for (int w = 0; w < kPcThreads / 32; w++) tot += s_red[w];
+        const unsigned long long before = tx_lookback(state, tile, tot, epoch);
+        if (t == 0) {
+            s_prefix = before;
+            if (tile == (int)gridDim.x - 1) {
+                const unsigned long long all = before + tot;
+                a.block_sums[0] = all >> 26;                     // bytes of the whole text
+                a.block_sums[1] = all & ((1ull << 26) - 1ull);   // lines
+            }
+        }
+    }
+    __syncthreads();
+    unsigned long long gofs = s_prefix >> 26;
+
+    // ---- phase B: characters, 256 records at a time, staged at the output's own 16-byte phase ----
+    for (int it = 0; it < kPcIters; it++) {
+        const uint4 rec = s_rec[it * kPcThreads + t];
+        const int len = (int)(rec.w & 63u);
+        int total;
+        const int excl = block_exclusive_scan(len, s_warp, &total);
+        const unsigned align = (unsigned)(gofs & 15ull);
+        if (gofs + (unsigned long long)total <= a.capacity) {
+            if (len) text_line_emit(rec, reinterpret_cast<char*>(&s_txt[align + excl]), exp3, crlf);
+            __syncthreads();
+            unsigned char* g = a.out + (gofs - align);         // 16-byte aligned
+            const int end = (int)align + total;
+            const int body0 = align ? 16 : 0, body1 = end & ~15;
+            for (int j = (int)align + t; j < min(16, end) && align; j += kPcThreads) g[j] = s_txt[j];
+            for (int j = body0 + 16 * t; j < body1; j += 16 * kPcThreads)
+                *reinterpret_cast<uint4*>(g + j) = *reinterpret_cast<const uint4*>(&s_txt[j]);
+            for (int j = max(body1, body0) + t; j < end; j += kPcThreads) g[j] = s_txt[j];
+            __syncthreads();
+        }
+        gofs += (unsigned long long)total;
+    }
+}
+
 __global__ void format_g6_kernel(const double* __restrict__ v, long long n, unsigned flags, char* __restrict__ text,
                                  uint8_t* __restrict__ len)
 {
@@ -397,14 +520,14 @@ static size_t pointcloud_sums_bytes(long long npx)
 
 size_t pointcloud_scratch_bytes(long long npx)
 {
-    return pointcloud_sums_bytes(npx) + 16 * (size_t)npx;  // block sums | one uint4 (three number codes, length) per pixel
+    return 2 * pointcloud_sums_bytes(npx);   // block sums + totals (two-pass float3 emitter) | look-back words (text)
 }
 
 // mode 0: text lines from d_proj_u; mode 1: float3 of the valid pixels of (d_xyzw, d_mask).
 // d_totals (inside d_scratch, 2 x u64: bytes, records) is valid once the stream has drained.
 cudaError_t launch_pointcloud(const KParams& p, int mode, int order, unsigned flags, const double* d_proj_u,
                               const float* d_xyzw, const uint8_t* d_mask, void* d_out, unsigned long long capacity,
-                              void* d_scratch, const unsigned long long** d_totals, cudaStream_t stream)
+                              void* d_scratch, unsigned text_epoch, const unsigned long long** d_totals, cudaStream_t stream)
 {
     if ((reinterpret_cast<uintptr_t>(d_out) & 15) != 0) return cudaErrorMisalignedAddress;
     const int blocks = (int)((p.npx + kPcChunk - 1) / kPcChunk);
@@ -415,14 +538,20 @@ cudaError_t launch_pointcloud(const KParams& p, int mode, int order, unsigned fl
     a.mask = d_mask;
     a.flags = flags;
     a.block_sums = static_cast<unsigned long long*>(d_scratch);
-    a.rec = reinterpret_cast<uint4*>(static_cast<uint8_t*>(d_scratch) + pointcloud_sums_bytes(p.npx));
+    a.rec = nullptr;
     a.out = static_cast<unsigned char*>(d_out);
     a.capacity = capacity;
-    if (mode == 0) pc_emit_kernel<0, false><<<blocks, kPcThreads, 0, stream>>>(p, a);
-    else pc_emit_kernel<1, false><<<blocks, kPcThreads, 0, stream>>>(p, a);
-    if (mode == 0) pc_emit_kernel<0, true><<<blocks, kPcThreads, 0, stream>>>(p, a);
-    else pc_emit_kernel<1, true><<<blocks, kPcThreads, 0, stream>>>(p, a);
-    *d_totals = a.block_sums + 2 * blocks;
+    if (mode == 0) {
+        // one launch: the totals land in the first two words of the scratch, the look-back words behind the sums
+        if (p.npx >= (1ll << 26)) return cudaErrorInvalidValue;    // line count field of the look-back word
+        unsigned long long* state = reinterpret_cast<unsigned long long*>(static_cast<uint8_t*>(d_scratch) + pointcloud_sums_bytes(p.npx));
+        pc_text_kernel<<<blocks, kPcThreads, 0, stream>>>(p, a, state, text_epoch);
+        *d_totals = a.block_sums;
+    } else {
+        pc_emit_kernel<1, false><<<blocks, kPcThreads, 0, stream>>>(p, a);
+        pc_emit_kernel<1, true><<<blocks, kPcThreads, 0, stream>>>(p, a);
+        *d_totals = a.block_sums + 2 * blocks;
+    }
     return cudaGetLastError();
 }
 

@@ -9,6 +9,7 @@
 // CCalculation.cpp:221, which a reference user would have to thread by hand.
 #include "../../include/slcalc_b200.h"
 
+#include <atomic>
 #include <condition_variable>
 #include <cstdarg>
 #include <cstdio>
@@ -29,6 +30,8 @@ struct slc_pool {
     int remaining = 0;
     bool quit = false;
     std::vector<int> status;
+    std::vector<int> shares;              // frame sets each member took in the last host call
+    int chunk = 1, slots = 1;             // max_batch / num_slots of every member
     std::string err;
 };
 
@@ -111,6 +114,9 @@ int slc_pool_create(const slc_config* cfg, const int32_t* devices, int32_t n_dev
     if (!pool) return pool_fail(nullptr, SLC_ERR_OUT_OF_MEMORY, "host allocation failed");
     try {
         pool->status.assign((size_t)n_devices, SLC_OK);
+        pool->shares.assign((size_t)n_devices, 0);
+        pool->chunk = cfg->max_batch;
+        pool->slots = cfg->num_slots;
         for (int i = 0; i < n_devices; i++) {
             slc_config c = *cfg;
             c.device = devices[i];
@@ -181,28 +187,61 @@ int slc_pool_reconstruct_host(slc_pool* pool, const uint8_t* h_stack, int32_t n_
 {
     if (!pool) return SLC_ERR_INVALID_ARG;
     if (n_stacks < 0) return pool_fail(pool, SLC_ERR_INVALID_ARG, "n_stacks < 0");
+    for (int& v : pool->shares) v = 0;
     if (n_stacks == 0) return SLC_OK;
     if (!h_stack || !h_out) return pool_fail(pool, SLC_ERR_INVALID_ARG, "NULL buffer");
     slc_info info;
     int st = slc_get_info(pool->ctx[0], &info);
     if (st != SLC_OK) return pool_fail(pool, st, "member 0: %s", slc_last_error(pool->ctx[0]));
     const size_t npx = (size_t)info.pixels, sb = (size_t)info.stack_bytes, bb = (npx + 7) / 8;
-    const int n = (int)pool->ctx.size();
+    const int chunk = pool->chunk, slots = pool->slots;
     const slc_result r = *h_out;
-    return run_all(pool, [=](int i) -> int {
-        int64_t lo = 0, hi = 0;
-        slc_shard_range(n_stacks, i, n, &lo, &hi);
-        if (hi == lo) return SLC_OK;
-        slc_result o = r;      // this member's shard of every plane
-        const size_t d = (size_t)lo;
-        if (r.xyzw) o.xyzw = r.xyzw + d * npx * 4;
-        if (r.mask) o.mask = r.mask + d * npx;
-        if (r.depth) o.depth = r.depth + d * npx;
-        if (r.mask_bits) o.mask_bits = r.mask_bits + d * bb;
-        if (r.points) o.points = r.points + d * (size_t)r.point_stride * 3;
-        if (r.n_points) o.n_points = r.n_points + d;
-        return slc_reconstruct_host_ex(pool->ctx[(size_t)i], h_stack + d * sb, (int32_t)(hi - lo), &o);
+    std::atomic<int> next{0};             // first frame set nobody has taken yet
+    std::atomic<bool> stop{false};        // a member failed: the others stop taking work
+    return run_all(pool, [&, npx, sb, bb, chunk, slots, r](int i) -> int {
+        slc_context* c = pool->ctx[(size_t)i];
+        std::vector<char> busy((size_t)slots, 0);
+        int rc = SLC_OK, slot = 0, taken = 0;
+        while (rc == SLC_OK && !stop.load(std::memory_order_relaxed)) {
+            if (busy[(size_t)slot]) {                       // the chunk this slot ran `slots` chunks ago
+                rc = slc_wait(c, slot);
+                busy[(size_t)slot] = 0;
+                if (rc != SLC_OK) break;
+            }
+            const int lo = next.fetch_add(chunk, std::memory_order_relaxed);
+            if (lo >= n_stacks) break;
+            const int n = (n_stacks - lo) < chunk ? (n_stacks - lo) : chunk;
+            slc_result o = r;                               // the planes of frame sets lo .. lo + n - 1
+            const size_t d = (size_t)lo;
+            if (r.xyzw) o.xyzw = r.xyzw + d * npx * 4;
+            if (r.mask) o.mask = r.mask + d * npx;
+            if (r.depth) o.depth = r.depth + d * npx;
+            if (r.mask_bits) o.mask_bits = r.mask_bits + d * bb;
+            if (r.points) o.points = r.points + d * (size_t)r.point_stride * 3;
+            if (r.n_points) o.n_points = r.n_points + d;
+            rc = slc_submit_host_ex(c, slot, h_stack + d * sb, n, &o);
+            if (rc != SLC_OK) break;
+            busy[(size_t)slot] = 1;
+            taken += n;
+            slot = (slot + 1) % slots;
+        }
+        if (rc != SLC_OK) stop.store(true, std::memory_order_relaxed);
+        for (int k = 0; k < slots; k++) {                   // drain, oldest first
+            const int q = (slot + k) % slots;
+            if (!busy[(size_t)q]) continue;
+            const int rc2 = slc_wait(c, q);
+            if (rc == SLC_OK) rc = rc2;
+        }
+        pool->shares[(size_t)i] = taken;
+        return rc;
     });
+}
+
+int slc_pool_last_shares(const slc_pool* pool, int32_t* frame_sets_per_member, int32_t n_members)
+{
+    if (!pool || !frame_sets_per_member || n_members != (int)pool->ctx.size()) return SLC_ERR_INVALID_ARG;
+    for (int i = 0; i < n_members; i++) frame_sets_per_member[i] = pool->shares[(size_t)i];
+    return SLC_OK;
 }
 
 int slc_pool_reconstruct_device(slc_pool* pool, const uint8_t* const* d_stack, const int32_t* n_stacks,

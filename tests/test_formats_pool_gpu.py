@@ -201,6 +201,7 @@ def test_pool_equals_single_context(built_library, base_calibration, fmt_name):
             for a in many.values():
                 a[...] = 0
             pool.reconstruct_into_ex(stacks, n, res)
+            assert sum(pool.last_shares()) == n          # handed out on demand, every frame set exactly once
             for k in many:
                 if k == "points":
                     for i in range(n):
