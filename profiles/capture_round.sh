@@ -30,6 +30,9 @@ echo "== launch-size curve"
 timeout 300 python profiles/launch_size_curve.py --out $out/${tag}_launch_size_curve.txt > /dev/null 2>&1; cat $out/${tag}_launch_size_curve.txt
 timeout 300 python profiles/launch_size_curve.py --format depth --out $out/${tag}_launch_size_curve_depth.txt > /dev/null 2>&1; cat $out/${tag}_launch_size_curve_depth.txt
 
+echo "== geometry sweep"
+timeout 600 python profiles/sweep_geometry.py > $out/${tag}_sweep_geometry.txt 2>&1; cat $out/${tag}_sweep_geometry.txt
+
 echo "== ncu launch lists"
 NCU="ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --csv"
 $NCU -c 60 --log-file $out/${tag}_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-next-rows --sustained-seconds 0 > $out/${tag}_ncu_main.log 2>&1
@@ -41,6 +44,6 @@ echo "== ncu --set full (one capture per kernel)"
 FULL="ncu --set full --clock-control none --import-source on"
 $FULL -k regex:reconstruct_vec_kernel -s 3 -c 2 -o $out/${tag}_prof_main -f python bench.py --steps 1 --warmup 3 --batch 8 --no-cpu-baseline --no-next-rows --sustained-seconds 0 > $out/${tag}_ncu_full_main.log 2>&1
 $FULL -k regex:"compact_cols_kernel|compact_rows_kernel" -s 2 -c 2 -o $out/${tag}_prof_compact -f python bench.py --path pointcloud --steps 1 --warmup 1 > $out/${tag}_ncu_full_compact.log 2>&1
-$FULL -k regex:pc_emit_kernel -s 4 -c 2 -o $out/${tag}_prof_pc -f python bench.py --path pointcloud --steps 1 --warmup 1 > $out/${tag}_ncu_full_pc.log 2>&1
+$FULL -k regex:pc_text_kernel -s 2 -c 2 -o $out/${tag}_prof_pc -f python bench.py --path pointcloud --steps 1 --warmup 1 > $out/${tag}_ncu_full_pc.log 2>&1
 $FULL -k regex:"strip_regression21_kernel|dyna_fused_kernel" -s 2 -c 2 -o $out/${tag}_prof_dyn -f python bench.py --path dynamic --steps 1 --warmup 1 --dyna-frames 30 > $out/${tag}_ncu_full_dyn.log 2>&1
 ls -la $out/${tag}_* | awk '{print $5, $9}'

@@ -202,11 +202,25 @@ int check_ready(slc_context* ctx, const void* a, const void* b, const void* c, i
     return SLC_OK;
 }
 
+// device staging of a slot (max_batch frame sets), on first use
+int ensure_slot(slc_context* ctx, Slot& s)
+{
+    const size_t nb = (size_t)ctx->cfg.max_batch;
+    if (!s.d_stack) SLC_CUDA(ctx, cudaMalloc(&s.d_stack, stack_bytes(ctx) * nb));
+    if (!s.d_xyzw) SLC_CUDA(ctx, cudaMalloc(&s.d_xyzw, xyzw_bytes(ctx) * nb));
+    if (!s.d_mask) SLC_CUDA(ctx, cudaMalloc(&s.d_mask, mask_bytes(ctx) * nb));
+    return SLC_OK;
+}
+
 // Enqueue upload + kernel + download of one chunk on a slot.
 int enqueue_chunk(slc_context* ctx, Slot& s, const uint8_t* h_stack, int n, float* h_xyzw, uint8_t* h_mask,
                   const slc_parity_planes* h_par, size_t par_offset_px)
 {
     const size_t npx = (size_t)ctx->kp.npx;
+    {
+        const int rc = ensure_slot(ctx, s);
+        if (rc != SLC_OK) return rc;
+    }
     SLC_CUDA(ctx, cudaMemcpyAsync(s.d_stack, h_stack, stack_bytes(ctx) * n, cudaMemcpyHostToDevice, s.stream));
     slc_parity_planes dpar{};
     const slc_parity_planes* dparp = nullptr;
@@ -365,12 +379,10 @@ int slc_create(const slc_config* cfg, slc_context** out)
     ctx->sm_count = prop.multiProcessorCount;
     SLC_CREATE_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     ctx->slots.resize(cfg->num_slots);
-    for (Slot& s : ctx->slots) {
-        SLC_CREATE_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
-        SLC_CREATE_CUDA(cudaMalloc(&s.d_stack, stack_bytes(ctx) * cfg->max_batch));
-        SLC_CREATE_CUDA(cudaMalloc(&s.d_xyzw, xyzw_bytes(ctx) * cfg->max_batch));
-        SLC_CREATE_CUDA(cudaMalloc(&s.d_mask, mask_bytes(ctx) * cfg->max_batch));
-    }
+    // the slots' device buffers (stack + xyzw + mask, max_batch frame sets each) are allocated by the
+    // first host-path call that needs them: a context that only serves the stand-alone decoder objects,
+    // device-resident callers or the point-cloud / ingest entry points stays a few streams large
+    for (Slot& s : ctx->slots) SLC_CREATE_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
 #undef SLC_CREATE_CUDA
     *out = ctx;
     return SLC_OK;
@@ -420,9 +432,10 @@ int slc_get_info(const slc_context* cctx, slc_info* out)
     li.query_only = true;
     KParams p = ctx->kp;
     p.n_stacks = 1;
-    p.stack = ctx->slots[0].d_stack;
-    p.xyzw = reinterpret_cast<float4*>(ctx->slots[0].d_xyzw);
-    p.mask = ctx->slots[0].d_mask;
+    // the shape the kernel takes for buffers aligned the way cudaMalloc aligns them
+    p.stack = reinterpret_cast<const uint8_t*>(uintptr_t{256});
+    p.xyzw = reinterpret_cast<float4*>(uintptr_t{256});
+    p.mask = reinterpret_cast<uint8_t*>(uintptr_t{256});
     p.lut = ctx->d_lut;
     const slc::LaunchPlan* plan = nullptr;
     int rc = plan_for(ctx, slc::plan_mode(p), 0, 1 << 20, &plan);   // the shape of a large launch
@@ -766,6 +779,10 @@ int finish_points(slc_context* ctx, Slot& s, bool* overflow)
 int enqueue_chunk_fmt(slc_context* ctx, Slot& s, const uint8_t* h_stack, int n, const slc_result& o)
 {
     const size_t npx = (size_t)ctx->kp.npx, bb = bits_bytes(ctx);
+    {
+        const int rc = ensure_slot(ctx, s);
+        if (rc != SLC_OK) return rc;
+    }
     SLC_CUDA(ctx, cudaMemcpyAsync(s.d_stack, h_stack, stack_bytes(ctx) * n, cudaMemcpyHostToDevice, s.stream));
     if (o.format == SLC_RESULT_DEPTH) {
         // the slot's xyzw / mask buffers hold the (smaller) depth plane / bit mask
@@ -1024,7 +1041,9 @@ int slc_dyna_track_device(slc_context* ctx, const uint8_t* d_frames, int32_t n_f
                           const double* d_u0, float* d_xyzw, uint8_t* d_mask, float* d_delta_z,
                           const slc_dyna_parity* d_parity, void* cuda_stream)
 {
-    int rc = check_ready(ctx, d_frames, d_xyzw, d_mask, n_frames);
+    // a single frame writes no map (only its strips): the outputs may be NULL then
+    int rc = check_ready(ctx, d_frames, n_frames > 1 ? static_cast<const void*>(d_xyzw) : d_frames,
+                         n_frames > 1 ? static_cast<const void*>(d_mask) : d_frames, n_frames);
     if (rc != SLC_OK) return rc;
     if (!d_u0) return fail(ctx, SLC_ERR_INVALID_ARG, "NULL ProjectorU[0]");
     if (n_frames < 1 || n_frames > 65535) return fail(ctx, SLC_ERR_INVALID_ARG, "n_frames %d outside 1..65535", n_frames);
@@ -1066,9 +1085,16 @@ int slc_dyna_track_host(slc_context* ctx, const uint8_t* h_frames, int32_t n_fra
                         const double* h_u0, float* h_xyzw, uint8_t* h_mask, float* h_delta_z,
                         const slc_dyna_parity* h_parity)
 {
-    int rc = check_ready(ctx, h_frames, h_xyzw, h_mask, n_frames);
+    int rc = check_ready(ctx, h_frames, n_frames > 1 ? static_cast<const void*>(h_xyzw) : h_frames,
+                         n_frames > 1 ? static_cast<const void*>(h_mask) : h_frames, n_frames);
     if (rc != SLC_OK) return rc;
     if (!h_u0 || n_frames < 1) return fail(ctx, SLC_ERR_INVALID_ARG, "NULL ProjectorU[0] or n_frames < 1");
+    // everything slc_dyna_track_device would reject is rejected here, before a byte is uploaded
+    if (n_frames > 65535) return fail(ctx, SLC_ERR_INVALID_ARG, "n_frames %d outside 1..65535", n_frames);
+    if (window < 3 || window > 33 || (window & 1) == 0)
+        return fail(ctx, SLC_ERR_INVALID_ARG, "window %d must be odd and in 3..33 (RECO_WINDOW_SIZE)", window);
+    if (ctx->kp.W <= window || ctx->kp.H <= window)
+        return fail(ctx, SLC_ERR_INVALID_ARG, "camera %dx%d smaller than the %d-pixel window", ctx->kp.W, ctx->kp.H, window);
     SLC_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
     const size_t npx = (size_t)ctx->kp.npx;
     const size_t nf = (size_t)n_frames, no = nf - 1;

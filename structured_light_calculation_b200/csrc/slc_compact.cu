@@ -266,19 +266,23 @@ compact_cols_kernel(const CompactArgs a)
     const int lr = t >> 3, lc = t & 7;
     const int ec = t >> 5, er = t & 31;
     float* out = a.points + (long long)stack * a.point_stride * 3;
-    for (int v0 = 0; v0 < H; v0 += kColChunk) {
-        float4 q[4];
-        bool ok[4];
+    float4 q[4];
+    bool ok[4];
+    auto load_chunk = [&](int v0) {                     // issue the chunk's global loads (valid pixels only)
 #pragma unroll
         for (int k = 0; k < 4; k++) {
             const int v = v0 + lr + 32 * k;
             ok[k] = v < H && ((s_rowbits[v] >> lc) & 1u);
             if (ok[k]) q[k] = __ldcs(xyzw + (long long)v * W + u0 + lc);
         }
+    };
+    load_chunk(0);
+    for (int v0 = 0; v0 < H; v0 += kColChunk) {
 #pragma unroll
         for (int k = 0; k < 4; k++)
             if (ok[k]) s_q[lc * (kColChunk + 1) + lr + 32 * k] = q[k];
         __syncthreads();
+        if (v0 + kColChunk < H) load_chunk(v0 + kColChunk);   // in flight while this chunk is emitted
 #pragma unroll
         for (int k = 0; k < 4; k++) {
             const int v = v0 + er + 32 * k;

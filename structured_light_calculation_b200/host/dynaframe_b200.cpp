@@ -44,6 +44,7 @@ void Mat::create(int rows_, int cols_, int type__)
     if (bytes && posix_memalign(&p, 64, bytes) != 0) p = nullptr;
     owner_.reset(static_cast<uint8_t*>(p), [](uint8_t* q) { free(q); });
     data_ = owner_.get();
+    if (bytes && !data_) { rows = cols = 0; step_ = 0; }     // allocation failed: the Mat is empty(), not a null map of size rows x cols
 }
 
 void Mat::copyTo(Mat& dst) const
@@ -520,16 +521,18 @@ bool CCalculation::CalculateOther()
         if (!copy_plane(img, sp_, frames + (size_t)i * npx, "CCalculation::StripRegression")) { slc_host_free(frames); return false; }
     }
     const size_t no = (size_t)n - 1;
-    // one pinned block holds every map of the sequence (xyzw | deltaZ | ProjectorU | mask per frame);
-    // the per-frame Mats are headers onto it, so the download is the only copy
-    const size_t per = npx * (16 + 4 + 8 + 1);
+    // one pinned block holds every map of the sequence, planes in descending alignment
+    // (xyzw 16 B | ProjectorU 8 B | deltaZ 4 B | mask 1 B) so that every plane starts aligned for its
+    // element type whatever the parity of the pixel count; the per-frame Mats are headers onto it, so
+    // the download is the only copy
+    const size_t per = npx * (16 + 8 + 4 + 1);
     if (m_dynBlock) { slc_host_free(m_dynBlock); m_dynBlock = nullptr; }
     m_dynXyzw.clear(); m_dynMask.clear(); m_dynDeltaZ.clear(); m_dynProjU.clear();
     m_dynBlock = static_cast<uint8_t*>(slc_host_alloc(no * per));
     if (!m_dynBlock) { slc_host_free(frames); ErrorHandling("CCalculation::CalculateOther()->pinned allocation failed."); return false; }
     float* xyzw = reinterpret_cast<float*>(m_dynBlock);
-    float* dz = reinterpret_cast<float*>(m_dynBlock + no * npx * 16);
-    double* pu = reinterpret_cast<double*>(m_dynBlock + no * npx * 20);
+    double* pu = reinterpret_cast<double*>(m_dynBlock + no * npx * 16);
+    float* dz = reinterpret_cast<float*>(m_dynBlock + no * npx * 24);
     uint8_t* mask = m_dynBlock + no * npx * 28;
     // StripRegression + FillOtherDeltaProU + FillCoordinate for every frame: two launches
     slc_dyna_parity par;
