@@ -201,7 +201,9 @@ int slc_wait(slc_context *ctx, int32_t slot);
  *                      (SLC_ORDER_ROW_MAJOR, or SLC_ORDER_REFERENCE = the order Result() walks),
  *                      n_points [n], + mask_bits                                    12 B/valid px + 0.125 B/px
  * mask_bits: u8 [n][(H*W+7)/8], bit (i & 7) of byte (i >> 3) = pixel i valid (numpy packbits,
- * bitorder "little"); 4-byte aligned, total size padded to a multiple of 4 bytes. */
+ * bitorder "little"); 4-byte aligned, total size padded to a multiple of 4 bytes.
+ * SLC_RESULT_POINTS needs a camera width that is a multiple of 8 and a height of at most 12000 (the
+ * chained-scan kernels of slc_compact.cu); the other formats take any geometry. */
 #define SLC_RESULT_XYZW   0
 #define SLC_RESULT_DEPTH  1
 #define SLC_RESULT_POINTS 2

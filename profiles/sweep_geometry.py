@@ -4,6 +4,7 @@ fraction of the measured HBM copy peak (algorithmic bytes 2G+N+17 per pixel).  R
 import json
 import os
 import sys
+import time
 
 import numpy as np
 import torch
@@ -39,10 +40,15 @@ for W, H, PW, G, N in cases:
     d_xyzw = torch.empty((F, H, W, 4), dtype=torch.float32, device=dev)
     d_mask = torch.empty((F, H, W), dtype=torch.uint8, device=dev)
     rec.time_device(d_in.data_ptr(), F, d_xyzw.data_ptr(), d_mask.data_ptr(), 1 if os.environ.get("SWEEP_QUICK") else 3)
-    ms = rec.time_device(d_in.data_ptr(), F, d_xyzw.data_ptr(), d_mask.data_ptr(), 1 if os.environ.get("SWEEP_QUICK") else 10)
+    # the fastest of three short bursts: a sweep of 16 cases runs into the power cap, and which case meets the
+    # dip differs from run to run (round 1: 1280x1040 at 0.854; the first round-2 run: the 1920x1200 rows)
+    runs = [rec.time_device(d_in.data_ptr(), F, d_xyzw.data_ptr(), d_mask.data_ptr(), 1 if os.environ.get("SWEEP_QUICK") else 6)
+            for _ in range(1 if os.environ.get("SWEEP_QUICK") else 3)]
+    ms = min(runs)
     gbs = (cfg.planes + 17) * cfg.pixels * F / (ms * 1e-3) / 1e9
     print(f"{W}x{H} G={G} N={N} P={cfg.planes}: {F / (ms * 1e-3):9.0f} frame sets/s  {gbs:7.0f} GB/s  {gbs / peak:.3f} of peak  "
-          f"(batch {F}, {ms:.3f} ms)")
+          f"(batch {F}, best of {len(runs)} bursts {ms:.3f} ms, slowest {max(runs):.3f} ms, variant {rec.info().kernel_variant})")
+    time.sleep(0.5)
     rec.close()
     del d_in, d_xyzw, d_mask
     torch.cuda.empty_cache()

@@ -727,8 +727,8 @@ int check_result(slc_context* ctx, const slc_result* r, bool device_path)
             return fail(ctx, SLC_ERR_INVALID_ARG, "order %d is neither SLC_ORDER_ROW_MAJOR nor SLC_ORDER_REFERENCE", r->order);
         if (device_path && (!r->xyzw || !r->mask))
             return fail(ctx, SLC_ERR_INVALID_ARG, "SLC_RESULT_POINTS on the device path needs xyzw and mask (the maps the points are taken from)");
-        if (ctx->kp.W % 8 != 0 || ctx->kp.H >= 65536)
-            return fail(ctx, SLC_ERR_INVALID_ARG, "SLC_RESULT_POINTS needs a camera width that is a multiple of 8 and a height below 65536");
+        if (ctx->kp.W % 8 != 0 || ctx->kp.H > 12000)
+            return fail(ctx, SLC_ERR_INVALID_ARG, "SLC_RESULT_POINTS needs a camera width that is a multiple of 8 and a height of at most 12000");
         break;
     default:
         return fail(ctx, SLC_ERR_INVALID_ARG, "unknown result format %d", r->format);

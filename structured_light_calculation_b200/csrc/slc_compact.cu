@@ -181,35 +181,47 @@ compact_rows_kernel(const CompactArgs a)
 }
 
 // ---- SLC_ORDER_REFERENCE: tile = 8 adjacent columns x H rows --------------------------------
-// dynamic shared memory: H bytes (one validity byte per row of the tile)
+// dynamic shared memory: H validity bytes (one per row of the tile: bit c = column c valid), then
+// H x 8 u16: the rank of pixel (row, column) inside its column
+__host__ __device__ inline size_t cols_rank_offset(int H) { return ((size_t)H + 15) & ~(size_t)15; }
+__host__ __device__ inline size_t cols_smem_bytes(int H) { return cols_rank_offset(H) + (size_t)H * 16; }
+
 __global__ void __launch_bounds__(kCThreads)
 compact_cols_kernel(const CompactArgs a)
 {
-    extern __shared__ unsigned char s_rowbits[];
+    extern __shared__ __align__(16) unsigned char s_dyn[];
     __shared__ float4 s_q[kColTileW * (kColChunk + 1)];
-    __shared__ unsigned short s_rank[kCThreads][kColTileW];   // rank (inside its column) of a thread's first row
     __shared__ unsigned s_warp4[4][kCThreads / 32];
     __shared__ unsigned s_colbase[kColTileW];
     const int t = threadIdx.x, tile = blockIdx.x, stack = blockIdx.y;
     const int H = a.H, W = a.W, u0 = tile * kColTileW;
+    unsigned char* s_rowbits = s_dyn;
+    unsigned short* s_rowrank = reinterpret_cast<unsigned short*>(s_dyn + cols_rank_offset(H));
     const uint8_t* mask = a.mask + (long long)stack * a.npx;
     const float4* xyzw = a.xyzw + (long long)stack * a.npx;
     const int R = (H + kCThreads - 1) / kCThreads;            // rows per thread, contiguous
 
     // phase A: one validity byte per row (8 columns), per-thread column counts, block scan per column
-    unsigned c01 = 0, c23 = 0, c45 = 0, c67 = 0;              // two 16-bit counters per word
+    unsigned cnt[4] = {0u, 0u, 0u, 0u};                       // two 16-bit counters per word: columns (0,1) (2,3) (4,5) (6,7)
+    auto spread = [](unsigned bits, unsigned (&d)[4]) {       // bit c -> +1 in the 16-bit lane of column c
+        d[0] = (bits & 1u) | ((bits & 2u) << 15);
+        d[1] = ((bits >> 2) & 1u) | ((bits & 8u) << 13);
+        d[2] = ((bits >> 4) & 1u) | ((bits & 32u) << 11);
+        d[3] = ((bits >> 6) & 1u) | ((bits & 128u) << 9);
+    };
     const int vbeg = t * R, vend = min(H, vbeg + R);
     for (int v = vbeg; v < vend; v++) {
-        const unsigned bits = nonzero_bits8(*reinterpret_cast<const uint2*>(mask + (long long)v * W + u0));
+        const unsigned px = (unsigned)v * (unsigned)W + (unsigned)u0;
+        const unsigned bits = nonzero_bits8(*reinterpret_cast<const uint2*>(mask + px));
         s_rowbits[v] = (unsigned char)bits;
-        if (a.mask_bits != nullptr) a.mask_bits[(long long)stack * a.bits_stride + (((long long)v * W + u0) >> 3)] = (uint8_t)bits;
-        c01 += (bits & 1u) | ((bits & 2u) << 15);
-        c23 += ((bits >> 2) & 1u) | ((bits & 8u) << 13);
-        c45 += ((bits >> 4) & 1u) | ((bits & 32u) << 11);
-        c67 += ((bits >> 6) & 1u) | ((bits & 128u) << 9);
+        if (a.mask_bits != nullptr) a.mask_bits[(long long)stack * a.bits_stride + (px >> 3)] = (uint8_t)bits;
+        unsigned d[4];
+        spread(bits, d);
+#pragma unroll
+        for (int k = 0; k < 4; k++) cnt[k] += d[k];
     }
     // exclusive scan over threads of the four packed words (16-bit lanes cannot overflow: sums <= H < 65536)
-    unsigned cnt[4] = {c01, c23, c45, c67}, excl[4], tot[4];
+    unsigned excl[4], tot[4];
     {
         const int lane = t & 31, warp = t >> 5;
         unsigned inc[4];
@@ -241,10 +253,16 @@ compact_cols_kernel(const CompactArgs a)
             tot[k] = sum;
         }
     }
+    // the rank of every pixel of this thread's rows inside its column: one 16-byte store per row
+    {
+        unsigned run[4] = {excl[0], excl[1], excl[2], excl[3]};
+        for (int v = vbeg; v < vend; v++) {
+            *reinterpret_cast<uint4*>(s_rowrank + 8 * v) = make_uint4(run[0], run[1], run[2], run[3]);
+            unsigned d[4];
+            spread(s_rowbits[v], d);
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
-        s_rank[t][2 * k] = (unsigned short)(excl[k] & 0xFFFFu);
-        s_rank[t][2 * k + 1] = (unsigned short)(excl[k] >> 16);
+            for (int k = 0; k < 4; k++) run[k] += d[k];
+        }
     }
     // column totals -> exclusive prefix over the 8 columns, tile total
     unsigned colcnt[kColTileW];
@@ -266,6 +284,8 @@ compact_cols_kernel(const CompactArgs a)
     const int lr = t >> 3, lc = t & 7;
     const int ec = t >> 5, er = t & 31;
     float* out = a.points + (long long)stack * a.point_stride * 3;
+    const unsigned colbase = s_colbase[ec];
+    const unsigned room = (unsigned)min((long long)0xFFFFFFFFll, a.point_stride);   // npx < 2^31: 32-bit indices
     float4 q[4];
     bool ok[4];
     auto load_chunk = [&](int v0) {                     // issue the chunk's global loads (valid pixels only)
@@ -273,7 +293,7 @@ compact_cols_kernel(const CompactArgs a)
         for (int k = 0; k < 4; k++) {
             const int v = v0 + lr + 32 * k;
             ok[k] = v < H && ((s_rowbits[v] >> lc) & 1u);
-            if (ok[k]) q[k] = __ldcs(xyzw + (long long)v * W + u0 + lc);
+            if (ok[k]) q[k] = __ldcs(xyzw + ((unsigned)v * (unsigned)W + (unsigned)(u0 + lc)));
         }
     };
     load_chunk(0);
@@ -287,14 +307,10 @@ compact_cols_kernel(const CompactArgs a)
         for (int k = 0; k < 4; k++) {
             const int v = v0 + er + 32 * k;
             if (v < H && ((s_rowbits[v] >> ec) & 1u)) {
-                // rank inside the column: the owner thread's first-row rank + the valid rows between
-                const int owner = v / R;
-                unsigned rank = s_rank[owner][ec];
-                for (int vv = owner * R; vv < v; vv++) rank += (s_rowbits[vv] >> ec) & 1u;
-                const long long idx = (long long)s_colbase[ec] + rank;
-                if (idx < a.point_stride) {
+                const unsigned idx = colbase + s_rowrank[8 * v + ec];
+                if (idx < room) {
                     const float4 p = s_q[ec * (kColChunk + 1) + er + 32 * k];
-                    float* d = out + idx * 3;
+                    float* d = out + 3ull * idx;
                     __stcs(d, p.x); __stcs(d + 1, p.y); __stcs(d + 2, p.z);
                 }
             }
@@ -307,7 +323,8 @@ compact_cols_kernel(const CompactArgs a)
 
 bool compact_supported(int W, int H, const void* d_mask, const void* d_xyzw)
 {
-    return (W % 8 == 0) && H < 65536 && ((reinterpret_cast<uintptr_t>(d_mask) & 7) == 0) &&
+    // reference order keeps 17 bytes of shared memory per image row
+    return (W % 8 == 0) && H < 65536 && cols_smem_bytes(H) <= 200 * 1024 && ((reinterpret_cast<uintptr_t>(d_mask) & 7) == 0) &&
            ((reinterpret_cast<uintptr_t>(d_xyzw) & 15) == 0);
 }
 
@@ -350,7 +367,7 @@ cudaError_t launch_compact(int W, int H, int n_stacks, int order, const float* d
         b.counts = a.counts + done;
         b.state = a.state + (size_t)done * a.tiles;
         if (order == 1) {
-            const size_t smem = ((size_t)H + 15) & ~(size_t)15;
+            const size_t smem = cols_smem_bytes(H);
             if (smem > 48 * 1024) {
                 const cudaError_t e = cudaFuncSetAttribute(compact_cols_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
                 if (e != cudaSuccess) return e;

@@ -190,14 +190,14 @@ reconstruct_vec_kernel(const __grid_constant__ KParams p)
 #pragma unroll
                 for (int k = 0; k < N_T / 2; k++) phase_pair(k);
             } else {
-#pragma unroll 4
-                for (int k = 0; k < half; k++) phase_pair(k);   // run-time step count: eight plane loads in flight
+#pragma unroll 2
+                for (int k = 0; k < half; k++) phase_pair(k);
             }
         } else {
             // [EXT] odd N: plain sums
 #pragma unroll
             for (int i = 0; i < PXT; i++) { sv[i] = 0.f; cv[i] = 0.f; }
-#pragma unroll 4
+#pragma unroll 3
             for (int k = 0; k < N; k++) {
                 uint32_t qa[NW];
                 VecLoad<PXT>::load(plane(2 * G + k), qa);
