@@ -425,58 +425,44 @@ __device__ __forceinline__ unsigned long long tx_lookback(unsigned long long* st
     return prefix;
 }
 
-// Tile: 1024 records in output order, four CONSECUTIVE records per thread.  A thread's lines are
-// therefore contiguous in the text, one block scan gives every line its place, and the whole tile
-// is staged once: four barriers per tile (the first version scanned and staged 256 records at a
-// time: 32 barriers per 2048 records, a quarter of all stall samples).
-constexpr int kTxPer = 4;                          // records per thread
-constexpr int kTxTile = kPcThreads * kTxPer;       // records per block
-
-// text_line_codes out of line: one copy of the f64 solve + three digit decodes in the kernel
-// instead of one per unrolled record (the inlined kernel was 10.9 k instructions, more than the
-// instruction cache holds: 13 % of the stall samples were instruction fetch)
-static __device__ __noinline__ uint4 text_line_codes_ool(const KParams& p, double U, int u, int v, unsigned flags)
-{
-    return text_line_codes(p, U, u, v, (flags & 2u) != 0u, (flags & 1u) != 0u);
-}
-
-__global__ void __launch_bounds__(kPcThreads, 4)
+__global__ void __launch_bounds__(kPcThreads)
 pc_text_kernel(const __grid_constant__ KParams p, const PcArgs a, unsigned long long* __restrict__ state, unsigned epoch)
 {
-    __shared__ __align__(16) unsigned char s_txt[kTxTile * kPcMaxLine + 32];
+    __shared__ uint4 s_rec[kPcChunk];
+    __shared__ __align__(16) unsigned char s_txt[kPcThreads * kPcMaxLine + 32];
     __shared__ int s_warp[kPcThreads / 32];
+    __shared__ unsigned long long s_red[kPcThreads / 32];
     __shared__ unsigned long long s_prefix;
     const int t = threadIdx.x, tile = (int)blockIdx.x;
+    const long long base = (long long)tile * kPcChunk;
     const bool crlf = (a.flags & 1u) != 0u, exp3 = (a.flags & 2u) != 0u;
 
-    // ---- phase A: the codes of this thread's four records, in output order (u outer, v inner) ----
-    const long long i0 = (long long)tile * kTxTile + (long long)t * kTxPer;
-    uint4 rec[kTxPer];
-    int mine = 0;                                       // bytes << 12 | lines of this thread's records
-    {
-        // npx < 2^31 (slc_create): 32-bit division, once per thread
-        unsigned u = 0, v = 0;
-        if (i0 < a.npx) {
-            const unsigned ii = (unsigned)i0;
+    // ---- phase A: the codes of the tile's records, in output order (u outer, v inner) ----
+    unsigned long long mine = 0ull;                     // bytes << 26 | lines, this thread's records
+#pragma unroll 2
+    for (int it = 0; it < kPcIters; it++) {
+        const long long i = base + (long long)it * kPcThreads + t;
+        uint4 rec = make_uint4(0u, 0u, 0u, 0u);
+        if (i < a.npx) {
+            // npx < 2^31 (slc_create): 32-bit division, not the 64-bit emulation
+            const unsigned ii = (unsigned)i;
+            unsigned u, v;
             if (a.order == 1) { u = ii / (unsigned)a.H; v = ii - u * (unsigned)a.H; }
             else { v = ii / (unsigned)a.W; u = ii - v * (unsigned)a.W; }
+            rec = text_line_codes(p, a.proj_u[(long long)v * a.W + u], (int)u, (int)v, exp3, crlf);
         }
-#pragma unroll 1
-        for (int k = 0; k < kTxPer; k++) {
-            uint4 r = make_uint4(0u, 0u, 0u, 0u);
-            if (i0 + k < a.npx) r = text_line_codes_ool(p, a.proj_u[(long long)v * a.W + u], (int)u, (int)v, a.flags);
-            // registers, not local memory: the index is a compile-time constant in each arm
-            if (k == 0) rec[0] = r; else if (k == 1) rec[1] = r; else if (k == 2) rec[2] = r; else rec[3] = r;
-            const int len = (int)(r.w & 63u);
-            mine += (len << 12) + (len ? 1 : 0);
-            if (a.order == 1) { if (++v == (unsigned)a.H) { v = 0; u++; } }
-            else { if (++u == (unsigned)a.W) { u = 0; v++; } }
-        }
+        s_rec[it * kPcThreads + t] = rec;
+        const unsigned len = rec.w & 63u;
+        mine += ((unsigned long long)len << 26) + (len ? 1ull : 0ull);
     }
-    int total;
-    const int excl = block_exclusive_scan(mine, s_warp, &total);     // both counts in one scan: no field can carry
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) mine += __shfl_down_sync(0xFFFFFFFFu, mine, d);
+    if ((t & 31) == 0) s_red[t >> 5] = mine;
+    __syncthreads();
     if (t < 32) {
-        const unsigned long long tot = ((unsigned long long)(total >> 12) << 26) | (unsigned long long)(total & 0xFFF);
+        unsigned long long tot = 0ull;
+#pragma unroll
+        for (int w = 0; w < kPcThreads / 32; w++) tot += s_red[w];
         const unsigned long long before = tx_lookback(state, tile, tot, epoch);
         if (t == 0) {
             s_prefix = before;
@@ -488,28 +474,29 @@ pc_text_kernel(const __grid_constant__ KParams p, const PcArgs a, unsigned long 
         }
     }
     __syncthreads();
-    const unsigned long long gofs = s_prefix >> 26;
-    const int bytes = total >> 12;
-    if (gofs + (unsigned long long)bytes > a.capacity) return;   // the totals above still report the size needed
+    unsigned long long gofs = s_prefix >> 26;
 
-    // ---- phase B: this thread's lines, back to back, at the output's own 16-byte phase ----
-    const unsigned align = (unsigned)(gofs & 15ull);
-    char* dst = reinterpret_cast<char*>(&s_txt[align + (unsigned)(excl >> 12)]);
-#pragma unroll 1
-    for (int k = 0; k < kTxPer; k++) {                  // one copy of the emitter in the kernel (instruction cache)
-        const uint4 r = (k == 0) ? rec[0] : (k == 1) ? rec[1] : (k == 2) ? rec[2] : rec[3];
-        const int len = (int)(r.w & 63u);
-        if (len) text_line_emit(r, dst, exp3, crlf);
-        dst += len;
+    // ---- phase B: characters, 256 records at a time, staged at the output's own 16-byte phase ----
+    for (int it = 0; it < kPcIters; it++) {
+        const uint4 rec = s_rec[it * kPcThreads + t];
+        const int len = (int)(rec.w & 63u);
+        int total;
+        const int excl = block_exclusive_scan(len, s_warp, &total);
+        const unsigned align = (unsigned)(gofs & 15ull);
+        if (gofs + (unsigned long long)total <= a.capacity) {
+            if (len) text_line_emit(rec, reinterpret_cast<char*>(&s_txt[align + excl]), exp3, crlf);
+            __syncthreads();
+            unsigned char* g = a.out + (gofs - align);         // 16-byte aligned
+            const int end = (int)align + total;
+            const int body0 = align ? 16 : 0, body1 = end & ~15;
+            for (int j = (int)align + t; j < min(16, end) && align; j += kPcThreads) g[j] = s_txt[j];
+            for (int j = body0 + 16 * t; j < body1; j += 16 * kPcThreads)
+                *reinterpret_cast<uint4*>(g + j) = *reinterpret_cast<const uint4*>(&s_txt[j]);
+            for (int j = max(body1, body0) + t; j < end; j += kPcThreads) g[j] = s_txt[j];
+            __syncthreads();
+        }
+        gofs += (unsigned long long)total;
     }
-    __syncthreads();
-    unsigned char* g = a.out + (gofs - align);                   // 16-byte aligned
-    const int end = (int)align + bytes;
-    const int body0 = align ? 16 : 0, body1 = end & ~15;
-    for (int j = (int)align + t; j < min(16, end) && align; j += kPcThreads) g[j] = s_txt[j];
-    for (int j = body0 + 16 * t; j < body1; j += 16 * kPcThreads)
-        *reinterpret_cast<uint4*>(g + j) = *reinterpret_cast<const uint4*>(&s_txt[j]);
-    for (int j = max(body1, body0) + t; j < end; j += kPcThreads) g[j] = s_txt[j];
 }
 
 __global__ void format_g6_kernel(const double* __restrict__ v, long long n, unsigned flags, char* __restrict__ text,
@@ -533,8 +520,7 @@ static size_t pointcloud_sums_bytes(long long npx)
 
 size_t pointcloud_scratch_bytes(long long npx)
 {
-    // block sums + totals (two-pass float3 emitter) | look-back words of the text kernel (one per 1024 records)
-    return pointcloud_sums_bytes(npx) + (((size_t)((npx + kTxTile - 1) / kTxTile) * sizeof(unsigned long long) + 255) & ~(size_t)255);
+    return 2 * pointcloud_sums_bytes(npx);   // block sums + totals (two-pass float3 emitter) | look-back words (text)
 }
 
 // mode 0: text lines from d_proj_u; mode 1: float3 of the valid pixels of (d_xyzw, d_mask).
@@ -559,8 +545,7 @@ cudaError_t launch_pointcloud(const KParams& p, int mode, int order, unsigned fl
         // one launch: the totals land in the first two words of the scratch, the look-back words behind the sums
         if (p.npx >= (1ll << 26)) return cudaErrorInvalidValue;    // line count field of the look-back word
         unsigned long long* state = reinterpret_cast<unsigned long long*>(static_cast<uint8_t*>(d_scratch) + pointcloud_sums_bytes(p.npx));
-        const int tiles = (int)((p.npx + kTxTile - 1) / kTxTile);
-        pc_text_kernel<<<tiles, kPcThreads, 0, stream>>>(p, a, state, text_epoch);
+        pc_text_kernel<<<blocks, kPcThreads, 0, stream>>>(p, a, state, text_epoch);
         *d_totals = a.block_sums;
     } else {
         pc_emit_kernel<1, false><<<blocks, kPcThreads, 0, stream>>>(p, a);
