@@ -379,6 +379,17 @@ def run_dynamic(args, emit=True):
     e2e_s = D.max_over_ranks(time.perf_counter() - t0, dev)
     e2e_value = world * e2e_reps * (E - 1) / e2e_s
     out = {"xyzw": h_xyzw.array, "mask": h_mask.array}
+    # the same with the depth-only result (z + one bit per pixel instead of 21 B/px back over the link)
+    bufs_d, res_d = capi.alloc_result(cfg, E - 1, capi.SLC_RESULT_DEPTH, pinned=True)
+    rec.dyna_track_into_ex(h_frames, E, h_u0, res_d, window)
+    D.barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_reps):
+        rec.dyna_track_into_ex(h_frames, E, h_u0, res_d, window)
+    e2e_depth_s = D.max_over_ranks(time.perf_counter() - t0, dev)
+    e2e_depth_value = world * e2e_reps * (E - 1) / e2e_depth_s
+    depth_ok = bool(np.array_equal(bufs_d["depth"].array, h_xyzw.array[..., 2]) and
+                    np.array_equal(capi.unpack_mask_bits(bufs_d["mask_bits"], E - 1, npx), h_mask.array.reshape(E - 1, npx)))
 
     if rank == 0:
         ocfg = O.make_config(cfg.width, cfg.height, cfg.projector_width, cfg.gray_digits, cfg.phase_steps)
@@ -404,6 +415,10 @@ def run_dynamic(args, emit=True):
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": args.dyna_e2e_frames * npx,
                     "d2h_bytes_per_step": (args.dyna_e2e_frames - 1) * npx * 21,
                     "api": "capi.Reconstructor.dyna_track_into -> slc_dyna_track_host, pinned host buffers"},
+            "e2e_compact": {"depth": {"value": e2e_depth_value, "unit": "frames/s", "h2d_bytes_per_step": args.dyna_e2e_frames * npx,
+                                      "d2h_bytes_per_step": (args.dyna_e2e_frames - 1) * (npx * 4 + capi.bits_bytes(npx)),
+                                      "api": "slc_dyna_track_host_ex SLC_RESULT_DEPTH (z + bit mask per frame)",
+                                      "checked_bit_equal_to_full_map": depth_ok}},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "peak_kind": f"of {peak_kind}",
@@ -922,6 +937,8 @@ def next_rows(args):
                          "workload": ln["config"]["workload"], "wall_s": time.perf_counter() - t0}
             if name == "pointcloud":
                 out[name]["binary_cloud"] = ln.get("binary_cloud")
+            if name == "dynamic":
+                out[name]["e2e_depth_value"] = ln["e2e_compact"]["depth"]["value"]
         except Exception as e:      # a next row must never take the headline line down
             out[name] = {"error": repr(e)}
     return out

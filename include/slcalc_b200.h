@@ -320,6 +320,13 @@ int slc_dyna_track_host(slc_context *ctx, const uint8_t *h_frames, int32_t n_fra
                         const double *h_u0, float *h_xyzw, uint8_t *h_mask, float *h_delta_z,
                         const slc_dyna_parity *h_parity);
 
+/* slc_dyna_track_host with a result format for the n_frames-1 maps (slc_result, above): the host path of the
+ * dynamic frames is bound by the 21 B/px it sends back, and SLC_RESULT_DEPTH (z + one bit per pixel; deltaZ is
+ * z[f] - z[f-1]) or SLC_RESULT_POINTS (the valid points of every frame, as Result() would print them) are a
+ * fifth / about two thirds of that.  Each format is a bit-for-bit selection of the xyzw + mask maps. */
+int slc_dyna_track_host_ex(slc_context *ctx, const uint8_t *h_frames, int32_t n_frames, int32_t window,
+                           const double *h_u0, const slc_result *h_out);
+
 /* ---- input ingest ("next" row: CSensor::LoadDatas) ------------------------- */
 /* What the reference's imread(file, CV_LOAD_IMAGE_GRAYSCALE) (CSensorV.cpp:111-114) yields for a
  * .bmp: uncompressed 8-bit paletted, 24-bit BGR or 32-bit BGRA, bottom-up or top-down. */

@@ -162,6 +162,7 @@ def load_library():
     L.slc_triangulate_uv_host.argtypes = [vp, vp, vp, vp, vp]
     L.slc_dyna_track_device.argtypes = [vp, vp, i32, i32, vp, vp, vp, vp, C.POINTER(SlcDynaParity), vp]
     L.slc_dyna_track_host.argtypes = [vp, vp, i32, i32, vp, vp, vp, vp, C.POINTER(SlcDynaParity)]
+    L.slc_dyna_track_host_ex.argtypes = [vp, vp, i32, i32, vp, C.POINTER(SlcResult)]
     L.slc_eval_phase_host.argtypes = [vp, vp, vp, C.c_int64, vp, vp]
     i64p = C.POINTER(C.c_int64)
     L.slc_bmp_parse.argtypes = [vp, C.c_int64, C.POINTER(SlcBmpInfo)]
@@ -492,6 +493,10 @@ class Reconstructor:
         xyzw f32 [n-1][H][W][4], mask u8 [n-1][H][W], delta_z f32 [n-1][H][W] out."""
         self._check(self.lib.slc_dyna_track_host(self.h, _ptr(h_frames), n_frames, window, _ptr(h_u0), _ptr(h_xyzw),
                                                  _ptr(h_mask), _ptr(h_delta_z), None))
+
+    def dyna_track_into_ex(self, h_frames, n_frames: int, h_u0, result: SlcResult, window: int = 21):
+        """CalculateOther with a result format for the n_frames - 1 maps (slc_dyna_track_host_ex)."""
+        self._check(self.lib.slc_dyna_track_host_ex(self.h, _ptr(h_frames), n_frames, window, _ptr(h_u0), C.byref(result)))
 
     def dyna_track_device(self, d_frames: int, n_frames: int, d_u0: int, d_xyzw: int, d_mask: int,
                           d_delta_z: int | None = None, window: int = 21, stream: int | None = None):

@@ -1136,6 +1136,85 @@ int slc_dyna_track_host(slc_context* ctx, const uint8_t* h_frames, int32_t n_fra
     return SLC_OK;
 }
 
+int slc_dyna_track_host_ex(slc_context* ctx, const uint8_t* h_frames, int32_t n_frames, int32_t window,
+                           const double* h_u0, const slc_result* h_out)
+{
+    if (!ctx) return SLC_ERR_INVALID_ARG;
+    if (!h_out) return fail(ctx, SLC_ERR_INVALID_ARG, "NULL slc_result");
+    if (h_out->format == SLC_RESULT_XYZW)
+        return slc_dyna_track_host(ctx, h_frames, n_frames, window, h_u0, h_out->xyzw, h_out->mask, nullptr, nullptr);
+    int rc = check_ready(ctx, h_frames, h_frames, h_frames, n_frames);
+    if (rc != SLC_OK) return rc;
+    if (!h_u0 || n_frames < 1 || n_frames > 65535) return fail(ctx, SLC_ERR_INVALID_ARG, "NULL ProjectorU[0] or n_frames outside 1..65535");
+    if (window < 3 || window > 33 || (window & 1) == 0)
+        return fail(ctx, SLC_ERR_INVALID_ARG, "window %d must be odd and in 3..33 (RECO_WINDOW_SIZE)", window);
+    if (ctx->kp.W <= window || ctx->kp.H <= window)
+        return fail(ctx, SLC_ERR_INVALID_ARG, "camera %dx%d smaller than the %d-pixel window", ctx->kp.W, ctx->kp.H, window);
+    if (n_frames == 1) return SLC_OK;                         // a single frame has no dynamic map
+    rc = check_result(ctx, h_out, false);
+    if (rc != SLC_OK) return rc;
+    SLC_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+    const size_t npx = (size_t)ctx->kp.npx, nf = (size_t)n_frames, no = nf - 1, bb = bits_bytes(ctx);
+    const bool points = h_out->format == SLC_RESULT_POINTS;
+    // one staging block: frames | u0 | xyzw | mask | strips | depth or points | bits | counts
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
+    const size_t o_fr = take(nf * npx), o_u0 = take(npx * 8), o_xyzw = take(no * npx * 16), o_mask = take(no * npx),
+                 o_st = take(nf * npx * 2), o_val = take(points ? no * npx * 12 : no * npx * 4), o_bits = take(no * bb + 4),
+                 o_cnt = take(no * sizeof(unsigned long long));
+    rc = ensure_scratch(ctx, &ctx->d_dyna, &ctx->dyna_bytes, off);
+    if (rc != SLC_OK) return rc;
+    char* base = static_cast<char*>(ctx->d_dyna);
+    cudaStream_t st = ctx->stream;
+    SLC_CUDA(ctx, cudaMemcpyAsync(base + o_fr, h_frames, nf * npx, cudaMemcpyHostToDevice, st));
+    SLC_CUDA(ctx, cudaMemcpyAsync(base + o_u0, h_u0, npx * 8, cudaMemcpyHostToDevice, st));
+    slc_dyna_parity dpar{};
+    dpar.strips = reinterpret_cast<int8_t*>(base + o_st);
+    float* d_xyzw = reinterpret_cast<float*>(base + o_xyzw);
+    uint8_t* d_mask = reinterpret_cast<uint8_t*>(base + o_mask);
+    uint8_t* d_bits = reinterpret_cast<uint8_t*>(base + o_bits);
+    rc = slc_dyna_track_device(ctx, reinterpret_cast<uint8_t*>(base + o_fr), n_frames, window,
+                               reinterpret_cast<double*>(base + o_u0), d_xyzw, d_mask, nullptr, &dpar, st);
+    if (rc != SLC_OK) return rc;
+    if (!points) {
+        float* d_depth = reinterpret_cast<float*>(base + o_val);
+        SLC_CUDA(ctx, slc::launch_pack_depth(d_xyzw, d_mask, (long long)npx, (int)no, d_depth, d_bits, (long long)bb, st));
+        ctx->launches++;
+        SLC_CUDA(ctx, cudaMemcpyAsync(h_out->depth, d_depth, no * npx * 4, cudaMemcpyDeviceToHost, st));
+        SLC_CUDA(ctx, cudaMemcpyAsync(h_out->mask_bits, d_bits, no * bb, cudaMemcpyDeviceToHost, st));
+        SLC_CUDA(ctx, cudaStreamSynchronize(st));
+        return SLC_OK;
+    }
+    // POINTS: one chained-scan launch over every map of the sequence, the counts first, then exactly 12 * count bytes per map
+    float* d_points = reinterpret_cast<float*>(base + o_val);
+    unsigned long long* d_counts = reinterpret_cast<unsigned long long*>(base + o_cnt);
+    rc = ensure_cstate(ctx, (int)no, st);
+    if (rc != SLC_OK) return rc;
+    SLC_CUDA(ctx, slc::launch_compact(ctx->kp.W, ctx->kp.H, (int)no, h_out->order, d_xyzw, d_mask, d_points, (long long)npx,
+                                      h_out->mask_bits ? d_bits : nullptr, (long long)bb, d_counts,
+                                      static_cast<unsigned long long*>(ctx->d_cstate), ++ctx->cstate_epoch, st));
+    ctx->launches++;
+    SLC_CUDA(ctx, cudaMemcpyAsync(h_out->n_points, d_counts, no * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    if (h_out->mask_bits) SLC_CUDA(ctx, cudaMemcpyAsync(h_out->mask_bits, d_bits, no * bb, cudaMemcpyDeviceToHost, st));
+    if (h_out->xyzw) SLC_CUDA(ctx, cudaMemcpyAsync(h_out->xyzw, d_xyzw, no * npx * 16, cudaMemcpyDeviceToHost, st));
+    if (h_out->mask) SLC_CUDA(ctx, cudaMemcpyAsync(h_out->mask, d_mask, no * npx, cudaMemcpyDeviceToHost, st));
+    SLC_CUDA(ctx, cudaStreamSynchronize(st));                 // n_points is in host memory now
+    bool overflow = false;
+    for (size_t f = 0; f < no; f++) {
+        const int64_t cnt = h_out->n_points[f];
+        if (cnt > h_out->point_stride) overflow = true;
+        const int64_t m = cnt < h_out->point_stride ? cnt : h_out->point_stride;
+        if (m > 0)
+            SLC_CUDA(ctx, cudaMemcpyAsync(h_out->points + f * (size_t)h_out->point_stride * 3, d_points + f * npx * 3,
+                                          (size_t)m * 12, cudaMemcpyDeviceToHost, st));
+    }
+    SLC_CUDA(ctx, cudaStreamSynchronize(st));
+    if (overflow)
+        return fail(ctx, SLC_ERR_INVALID_ARG, "a frame has more valid pixels than point_stride = %lld: its list was cut (n_points holds the full counts)",
+                    (long long)h_out->point_stride);
+    return SLC_OK;
+}
+
 /* ---- input ingest ------------------------------------------------------ */
 namespace {
 

@@ -319,7 +319,48 @@ compact_cols_kernel(const CompactArgs a)
     }
 }
 
+// ---- SLC_RESULT_DEPTH from finished maps: z plane + one validity bit per pixel ----------------
+// (the first-frame kernel writes this layout itself; the dynamic frames, whose kernel walks a
+// sequence, get it from their maps.)  A thread owns 8 consecutive pixels of one map.
+__global__ void __launch_bounds__(kCThreads)
+pack_depth_kernel(const float4* __restrict__ xyzw, const uint8_t* __restrict__ mask, long long npx,
+                  float* __restrict__ depth, uint8_t* __restrict__ bits, long long bits_stride)
+{
+    const long long map = blockIdx.y;
+    const long long p0 = ((long long)blockIdx.x * kCThreads + threadIdx.x) * 8;
+    if (p0 >= npx) return;
+    const float4* src = xyzw + map * npx + p0;
+    const uint8_t* m = mask + map * npx + p0;
+    float* dst = depth + map * npx + p0;
+    unsigned b = 0u;
+    const int n = (int)((npx - p0) < 8 ? (npx - p0) : 8);
+    float z[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++)
+        if (j < n) { z[j] = __ldcs(src + j).z; b |= (m[j] != 0 ? 1u : 0u) << j; }
+#pragma unroll
+    for (int j = 0; j < 8; j++)
+        if (j < n) __stcs(dst + j, z[j]);
+    bits[map * bits_stride + (p0 >> 3)] = (uint8_t)b;
+}
+
 }  // namespace
+
+cudaError_t launch_pack_depth(const float* d_xyzw, const uint8_t* d_mask, long long npx, int n_maps, float* d_depth,
+                              uint8_t* d_bits, long long bits_stride, cudaStream_t stream)
+{
+    if (n_maps <= 0) return cudaSuccess;
+    const long long groups = (npx + 7) / 8;
+    for (int done = 0; done < n_maps; done += 65535) {
+        const int n = (n_maps - done) < 65535 ? (n_maps - done) : 65535;
+        pack_depth_kernel<<<dim3((unsigned)((groups + kCThreads - 1) / kCThreads), (unsigned)n), kCThreads, 0, stream>>>(
+            reinterpret_cast<const float4*>(d_xyzw) + (size_t)done * npx, d_mask + (size_t)done * npx, npx,
+            d_depth + (size_t)done * npx, d_bits + (size_t)done * bits_stride, bits_stride);
+        const cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+}
 
 bool compact_supported(int W, int H, const void* d_mask, const void* d_xyzw)
 {

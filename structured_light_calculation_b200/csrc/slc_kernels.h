@@ -81,6 +81,10 @@ cudaError_t launch_compact(int W, int H, int n_stacks, int order, const float* d
                            unsigned long long* d_counts, unsigned long long* d_state, unsigned epoch,
                            cudaStream_t stream);
 
+// z plane + validity bits of finished (xyzw, mask) maps: the SLC_RESULT_DEPTH layout for the dynamic frames
+cudaError_t launch_pack_depth(const float* d_xyzw, const uint8_t* d_mask, long long npx, int n_maps, float* d_depth,
+                              uint8_t* d_bits, long long bits_stride, cudaStream_t stream);
+
 // input ingest (slc_ingest.cu)
 cudaError_t launch_bmp_unpack(const uint8_t* d_pixels, int width, int height, int bpp, int top_down, int row_stride,
                               int identity, const uint8_t* gray256, uint8_t* d_plane, cudaStream_t stream);

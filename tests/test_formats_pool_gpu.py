@@ -274,3 +274,37 @@ def test_two_contexts_from_two_host_threads(built_library, base_calibration):
     for rec, _, _ in cases:
         rec.close()
     assert not errors, errors
+
+
+@pytest.mark.parametrize("W,H", [(320, 128), (200, 75)])
+def test_dynamic_frames_result_formats(built_library, base_calibration, W, H):
+    """slc_dyna_track_host_ex: depth + bits / valid points of every dynamic frame == selections of the full maps
+    (any width for DEPTH; POINTS needs a width that is a multiple of 8)."""
+    from structured_light_calculation_b200 import capi, synth
+    cfg = _cfg("reference_default", W, H)
+    cal, scene, planes = make_case(cfg, base_calibration, noise=1.0, seed=41)
+    frames = synth.render_dyna_frames(cfg, cal, 5, stripe_period=14.0, z_step=0.4, noise_sigma=1.5)
+    rec = capi.Reconstructor(cfg, device=0, max_batch=1, num_slots=1)
+    rec.set_calibration(cal)
+    u0 = rec.reconstruct(planes, parity=True)["proj_u"][0]
+    full = rec.dyna_track(frames, u0, window=21)
+    n, npx = 4, cfg.pixels
+    assert full["mask"].any()
+    bufs, res = capi.alloc_result(cfg, n, capi.SLC_RESULT_DEPTH)
+    rec.dyna_track_into_ex(frames, 5, u0, res, window=21)
+    assert bits_equal(bufs["depth"], np.ascontiguousarray(full["xyzw"][..., 2]))
+    assert np.array_equal(capi.unpack_mask_bits(bufs["mask_bits"], n, npx), full["mask"].reshape(n, npx))
+    for order in (capi.SLC_ORDER_ROW_MAJOR, capi.SLC_ORDER_REFERENCE):
+        bufs, res = capi.alloc_result(cfg, n, capi.SLC_RESULT_POINTS, order)
+        if W % 8:
+            with pytest.raises(capi.SlcError):
+                rec.dyna_track_into_ex(frames, 5, u0, res, window=21)
+            continue
+        rec.dyna_track_into_ex(frames, 5, u0, res, window=21)
+        for i in range(n):
+            want = _select(full, i, order)
+            assert int(bufs["n_points"][i]) == len(want)
+            assert bits_equal(np.ascontiguousarray(bufs["points"][i, : len(want)]), np.ascontiguousarray(want))
+    # a single frame has no dynamic map: nothing is written, nothing fails
+    rec.dyna_track_into_ex(frames, 1, u0, res, window=21)
+    rec.close()
