@@ -13,7 +13,7 @@
 //   phase B  the characters of every record (emit_g6_fast: integer work only) go straight into their
 //            place in a shared-memory chunk laid out at the output's own 16-byte phase, written as uint4.
 // (Until round 2 this was two launches with a 16 B/px scratch round trip between them.)  The text is
-// byte-identical to what the reference's doubles print.  pc_emit_kernel<1, *> -- packed float3 xyz of the
+// byte-identical to what the reference's doubles print.  pc_emit_kernel -- packed float3 xyz of the
 // valid pixels of a float4 map in two passes -- remains for the geometries slc_compact.cu does not take.
 #include "slc_kernels.h"
 
@@ -195,12 +195,11 @@ struct PcArgs {
     int W, H;
     long long npx;
     int order;                       // 0 row-major, 1 reference (u outer, v inner: CCalculation.cpp:336-338)
-    const double* proj_u;            // MODE 0
-    const float4* xyzw;              // MODE 1
-    const uint8_t* mask;             // MODE 1
+    const double* proj_u;            // text
+    const float4* xyzw;              // float3 records
+    const uint8_t* mask;             // float3 records
     unsigned flags;
     unsigned long long* block_sums;  // [2 * n_blocks + 2]: (bytes, records) per block, totals last
-    uint4* rec;                      // MODE 0: (x, y, z) as decode_g6 codes + the line length, written by pass 1 for pass 2
     unsigned char* out;
     unsigned long long capacity;     // bytes
 };
@@ -259,11 +258,14 @@ __device__ __forceinline__ int block_exclusive_scan(int v, int* s_warp, int* tot
     return base + inc - v;
 }
 
-template <int MODE, bool WRITE>
+// Packed float3 xyz of the valid pixels of a float4 map in two passes (count, then scan + emit): the
+// path of the geometries the chained-scan kernels of slc_compact.cu do not take (widths that are not a
+// multiple of 8).
+template <bool WRITE>
 __global__ void __launch_bounds__(kPcThreads)
-pc_emit_kernel(const __grid_constant__ KParams p, const PcArgs a)
+pc_emit_kernel(const PcArgs a)
 {
-    __shared__ __align__(16) unsigned char s_txt[WRITE ? kPcThreads * kPcMaxLine + 32 : 16];
+    __shared__ __align__(16) unsigned char s_txt[WRITE ? kPcThreads * 12 + 32 : 16];
     __shared__ int s_warp[kPcThreads / 32];
     const int t = threadIdx.x;
     const long long base = (long long)blockIdx.x * kPcChunk;
@@ -271,7 +273,7 @@ pc_emit_kernel(const __grid_constant__ KParams p, const PcArgs a)
     unsigned long long gofs = 0ull;
     if (WRITE) {
         // this block's offset = sum of the byte counts of all earlier blocks (a few thousand values
-        // sitting in L2; cheaper than a separate scan launch); the last block also publishes the totals
+        // sitting in L2); the last block also publishes the totals
         __shared__ unsigned long long s_part[3][kPcThreads / 32];
         const int nb = (int)gridDim.x, me = (int)blockIdx.x;
         const bool last = (me == nb - 1);
@@ -298,30 +300,19 @@ pc_emit_kernel(const __grid_constant__ KParams p, const PcArgs a)
             a.block_sums[2 * nb + 1] = tr;
         }
     }
-    const bool crlf = (a.flags & 1u) != 0u, exp3 = (a.flags & 2u) != 0u;
 
     for (int it = 0; it < kPcIters; it++) {
         const long long i = base + (long long)it * kPcThreads + t;
         int len = 0;
         long long px = 0;
-        uint4 rec = make_uint4(0u, 0u, 0u, 0u);
         if (i < a.npx) {
-            if (MODE == 0 && WRITE) {
-                rec = __ldcs(a.rec + i);                           // pass 2 never touches U or the calibration
-            } else {
-                // npx < 2^31 (slc_create): 32-bit division, not the 64-bit emulation
-                const unsigned ii = (unsigned)i;
-                unsigned u, v;
-                if (a.order == 1) { u = ii / (unsigned)a.H; v = ii - u * (unsigned)a.H; }
-                else { v = ii / (unsigned)a.W; u = ii - v * (unsigned)a.W; }
-                px = (long long)v * a.W + u;
-                if (MODE == 0) {
-                    // pass 1: everything that needs f64 -- x, y, z and their six exact digits -- once
-                    rec = text_line_codes(p, a.proj_u[px], (int)u, (int)v, exp3, crlf);
-                    __stcs(a.rec + i, rec);
-                }
-            }
-            len = (MODE == 0) ? (int)(rec.w & 63u) : ((a.mask[px] != 0) ? 12 : 0);
+            // npx < 2^31 (slc_create): 32-bit division, not the 64-bit emulation
+            const unsigned ii = (unsigned)i;
+            unsigned u, v;
+            if (a.order == 1) { u = ii / (unsigned)a.H; v = ii - u * (unsigned)a.H; }
+            else { v = ii / (unsigned)a.W; u = ii - v * (unsigned)a.W; }
+            px = (long long)v * a.W + u;
+            len = (a.mask[px] != 0) ? 12 : 0;
         }
         int total;
         const int excl = block_exclusive_scan(len, s_warp, &total);
@@ -330,17 +321,11 @@ pc_emit_kernel(const __grid_constant__ KParams p, const PcArgs a)
         if (WRITE) {
             const unsigned align = (unsigned)(gofs & 15ull);
             if (gofs + (unsigned long long)total <= a.capacity) {
-                unsigned char* dst = &s_txt[align + excl];
                 if (len) {
-                    if (MODE == 0) {
-                        // pass 2: the characters go straight into the line's place in the staged chunk
-                        text_line_emit(rec, reinterpret_cast<char*>(dst), exp3, crlf);
-                    } else {
-                        // 12-byte records: align + excl is a multiple of 4 (gofs is a multiple of 12 from a 16-aligned base)
-                        const float4 q = a.xyzw[px];
-                        float* d = reinterpret_cast<float*>(dst);
-                        d[0] = q.x; d[1] = q.y; d[2] = q.z;
-                    }
+                    // 12-byte records: align + excl is a multiple of 4 (gofs is a multiple of 12 from a 16-aligned base)
+                    const float4 q = a.xyzw[px];
+                    float* d = reinterpret_cast<float*>(&s_txt[align + excl]);
+                    d[0] = q.x; d[1] = q.y; d[2] = q.z;
                 }
                 __syncthreads();
                 unsigned char* g = a.out + (gofs - align);         // 16-byte aligned
@@ -538,7 +523,6 @@ cudaError_t launch_pointcloud(const KParams& p, int mode, int order, unsigned fl
     a.mask = d_mask;
     a.flags = flags;
     a.block_sums = static_cast<unsigned long long*>(d_scratch);
-    a.rec = nullptr;
     a.out = static_cast<unsigned char*>(d_out);
     a.capacity = capacity;
     if (mode == 0) {
@@ -548,8 +532,8 @@ cudaError_t launch_pointcloud(const KParams& p, int mode, int order, unsigned fl
         pc_text_kernel<<<blocks, kPcThreads, 0, stream>>>(p, a, state, text_epoch);
         *d_totals = a.block_sums;
     } else {
-        pc_emit_kernel<1, false><<<blocks, kPcThreads, 0, stream>>>(p, a);
-        pc_emit_kernel<1, true><<<blocks, kPcThreads, 0, stream>>>(p, a);
+        pc_emit_kernel<false><<<blocks, kPcThreads, 0, stream>>>(a);
+        pc_emit_kernel<true><<<blocks, kPcThreads, 0, stream>>>(a);
         *d_totals = a.block_sums + 2 * blocks;
     }
     return cudaGetLastError();
