@@ -509,7 +509,23 @@ def run_pointcloud(args, emit=True):
     c1.record(stream)
     torch.cuda.synchronize()
     compact_ms = c0.elapsed_time(c1) / (creps * B)
-    compact_launches = (rec.launch_count() - l1) // (creps + 3)
+    # the same lists in the maps' memory order (the other tile shape of slc_compact.cu)
+    r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    rec.compact_points_device(d_xyzw.data_ptr(), d_msk.data_ptr(), B, d_xyz.data_ptr(), npx, d_cnt.data_ptr(),
+                              capi.SLC_ORDER_ROW_MAJOR, None, stream.cuda_stream)
+    r0.record(stream)
+    for _ in range(creps):
+        rec.compact_points_device(d_xyzw.data_ptr(), d_msk.data_ptr(), B, d_xyz.data_ptr(), npx, d_cnt.data_ptr(),
+                                  capi.SLC_ORDER_ROW_MAJOR, None, stream.cuda_stream)
+    r1.record(stream)
+    torch.cuda.synchronize()
+    compact_rm_ms = r0.elapsed_time(r1) / (creps * B)
+    rm_ok = bool(np.array_equal(d_xyz[0, :int(d_cnt[0].item())].cpu().numpy(),
+                                first["xyzw"][0][..., :3][first["mask"][0].astype(bool)]))
+    rec.compact_points_device(d_xyzw.data_ptr(), d_msk.data_ptr(), B, d_xyz.data_ptr(), npx, d_cnt.data_ptr(),
+                              capi.SLC_ORDER_REFERENCE, None, stream.cuda_stream)      # the checks below read this order
+    torch.cuda.synchronize()
+    compact_launches = (rec.launch_count() - l1) // (2 * creps + 5)
     n_compact = int(d_cnt[B - 1].item())
     xyz_host = d_xyz[B - 1, :n_compact].cpu().numpy()
     m = first["mask"][0].T.astype(bool)                         # reference order: u outer, v inner
@@ -557,6 +573,9 @@ def run_pointcloud(args, emit=True):
                              "gb_per_s": (17 * npx + 12 * n_compact) / (compact_ms * 1e-3) / 1e9,
                              "roofline_frac": (17 * npx + 12 * n_compact) / (compact_ms * 1e-3) / 1e9 / peak,
                              "launches_per_call": compact_launches, "maps_per_launch": B,
+                             "row_major_us_per_frame": 1e3 * compact_rm_ms,
+                             "row_major_roofline_frac": (17 * npx + 12 * n_compact) / (compact_rm_ms * 1e-3) / 1e9 / peak,
+                             "row_major_checked": rm_ok,
                              "synchronous_call_us": 1e3 * compact_sync_ms,
                              "api": "slc_compact_points_device: float3 of the valid pixels in Result()'s order (u outer, v inner), "
                                     "one chained-scan launch for 16 maps, counts stay on the device; synchronous_call_us = one "
