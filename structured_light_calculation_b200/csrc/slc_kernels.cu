@@ -18,6 +18,7 @@
 #include "slc_kernels.h"
 
 #include <cstdio>
+#include <type_traits>
 
 namespace slc {
 
@@ -190,15 +191,25 @@ reconstruct_vec_kernel(const __grid_constant__ KParams p)
 #pragma unroll
                 for (int k = 0; k < N_T / 2; k++) phase_pair(k);
             } else {
+                // run-time step count: the usual ones (6, 8, 12 steps) get their loads issued up front like the
+                // compile-time instances; anything else loops two pairs at a time
+                auto pairs = [&](auto kc) {
+#pragma unroll
+                    for (int k = 0; k < decltype(kc)::value; k++) phase_pair(k);
+                };
+                if (half == 3) pairs(std::integral_constant<int, 3>{});
+                else if (half == 4) pairs(std::integral_constant<int, 4>{});
+                else if (half == 6) pairs(std::integral_constant<int, 6>{});
+                else {
 #pragma unroll 2
-                for (int k = 0; k < half; k++) phase_pair(k);
+                    for (int k = 0; k < half; k++) phase_pair(k);
+                }
             }
         } else {
             // [EXT] odd N: plain sums
 #pragma unroll
             for (int i = 0; i < PXT; i++) { sv[i] = 0.f; cv[i] = 0.f; }
-#pragma unroll 3
-            for (int k = 0; k < N; k++) {
+            auto phase_one = [&](int k) {
                 uint32_t qa[NW];
                 VecLoad<PXT>::load(plane(2 * G + k), qa);
                 const float ck = p.ck[k], sk = p.sk[k];
@@ -210,6 +221,16 @@ reconstruct_vec_kernel(const __grid_constant__ KParams p)
                         sv[4 * w + j] = __fmaf_rn(gk, ck, sv[4 * w + j]);
                         cv[4 * w + j] = __fmaf_rn(gk, sk, cv[4 * w + j]);
                     }
+            };
+            auto steps = [&](auto kc) {
+#pragma unroll
+                for (int k = 0; k < decltype(kc)::value; k++) phase_one(k);
+            };
+            if (N == 3) steps(std::integral_constant<int, 3>{});          // the usual odd step counts, loads up front
+            else if (N == 5) steps(std::integral_constant<int, 5>{});
+            else {
+#pragma unroll 3
+                for (int k = 0; k < N; k++) phase_one(k);
             }
         }
 
