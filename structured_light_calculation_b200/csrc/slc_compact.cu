@@ -409,7 +409,8 @@ cudaError_t launch_compact(int W, int H, int n_stacks, int order, const float* d
         b.state = a.state + (size_t)done * a.tiles;
         if (order == 1) {
             const size_t smem = cols_smem_bytes(H);
-            if (smem > 48 * 1024) {
+            if (smem > 24 * 1024) {
+                // static (17.7 KB) + dynamic shared memory beyond 48 KB needs the opt-in (images taller than ~1750 rows)
                 const cudaError_t e = cudaFuncSetAttribute(compact_cols_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
                 if (e != cudaSuccess) return e;
             }

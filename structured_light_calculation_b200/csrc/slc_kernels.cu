@@ -18,7 +18,6 @@
 #include "slc_kernels.h"
 
 #include <cstdio>
-#include <type_traits>
 
 namespace slc {
 
@@ -69,16 +68,13 @@ template <> struct Slot<1> {
 // MODE 2: everything decided at run time (parity planes, custom LUT, SLC_FLAG_Z_FP64, modulation)
 template <int MODE, bool Z64>
 __device__ __forceinline__ float solve_pixel(const KParams& p, const RowConst& rc, int kbin, float s, float c,
-                                             float uf, PixelResult& r, bool& mod_ok)
+                                             float uf, PixelResult& r)
 {
     const float pix = phase_to_pix(fast_atan2_deg(s, c), p.Tf);
-    mod_ok = true;
+    bool mod_ok = true;
     if (MODE == 1 || (MODE == 2 && p.use_mod)) mod_ok = __fadd_rn(__fmul_rn(s, s), __fmul_rn(c, c)) >= p.thr2;
-    unwrap_and_triangulate<MODE == 2, Z64>(p, rc, kbin, pix, mod_ok, uf, r);
-    // [EXT] a pixel the modulation test rejects has no projector column: U = 0, the reference's own
-    // "no value" sentinel (CCalculation.cpp:678), in w and in the proj_u plane -- so that Result(),
-    // FillCoordinate(i) and the dynamic frames, which only test U == 0, skip it too
-    if (MODE == 1 || (MODE == 2 && p.use_mod)) r.w = mod_ok ? r.w : 0.f;
+    // [EXT] a pixel the modulation test rejects has no projector column: w = 0 and proj_u = 0 (ZERO_W, r.has_u)
+    unwrap_and_triangulate<MODE == 2, Z64, MODE != 0>(p, rc, kbin, pix, mod_ok, uf, r);
     return pix;
 }
 
@@ -191,25 +187,15 @@ reconstruct_vec_kernel(const __grid_constant__ KParams p)
 #pragma unroll
                 for (int k = 0; k < N_T / 2; k++) phase_pair(k);
             } else {
-                // run-time step count: the usual ones (6, 8, 12 steps) get their loads issued up front like the
-                // compile-time instances; anything else loops two pairs at a time
-                auto pairs = [&](auto kc) {
-#pragma unroll
-                    for (int k = 0; k < decltype(kc)::value; k++) phase_pair(k);
-                };
-                if (half == 3) pairs(std::integral_constant<int, 3>{});
-                else if (half == 4) pairs(std::integral_constant<int, 4>{});
-                else if (half == 6) pairs(std::integral_constant<int, 6>{});
-                else {
 #pragma unroll 2
-                    for (int k = 0; k < half; k++) phase_pair(k);
-                }
+                for (int k = 0; k < half; k++) phase_pair(k);
             }
         } else {
             // [EXT] odd N: plain sums
 #pragma unroll
             for (int i = 0; i < PXT; i++) { sv[i] = 0.f; cv[i] = 0.f; }
-            auto phase_one = [&](int k) {
+#pragma unroll 3
+            for (int k = 0; k < N; k++) {
                 uint32_t qa[NW];
                 VecLoad<PXT>::load(plane(2 * G + k), qa);
                 const float ck = p.ck[k], sk = p.sk[k];
@@ -221,16 +207,6 @@ reconstruct_vec_kernel(const __grid_constant__ KParams p)
                         sv[4 * w + j] = __fmaf_rn(gk, ck, sv[4 * w + j]);
                         cv[4 * w + j] = __fmaf_rn(gk, sk, cv[4 * w + j]);
                     }
-            };
-            auto steps = [&](auto kc) {
-#pragma unroll
-                for (int k = 0; k < decltype(kc)::value; k++) phase_one(k);
-            };
-            if (N == 3) steps(std::integral_constant<int, 3>{});          // the usual odd step counts, loads up front
-            else if (N == 5) steps(std::integral_constant<int, 5>{});
-            else {
-#pragma unroll 3
-                for (int k = 0; k < N; k++) phase_one(k);
             }
         }
 
@@ -255,9 +231,8 @@ reconstruct_vec_kernel(const __grid_constant__ KParams p)
                 const float uf = u0f + (float)i;
                 PixelResult r;
                 float pix;
-                bool mod_ok;
-                if (z64) pix = solve_pixel<MODE, true>(p, rc, kbin, sv[i], cv[i], uf, r, mod_ok);
-                else pix = solve_pixel<MODE, false>(p, rc, kbin, sv[i], cv[i], uf, r, mod_ok);
+                if (z64) pix = solve_pixel<MODE, true>(p, rc, kbin, sv[i], cv[i], uf, r);
+                else pix = solve_pixel<MODE, false>(p, rc, kbin, sv[i], cv[i], uf, r);
                 // pixels awaiting the f64 re-solve park (gint, pix) in their tile slot
                 if constexpr (OUT == 0) trow[i] = make_float4(r.need64 ? r.gint : r.x, r.need64 ? pix : r.y, r.z, r.w);
                 else trow[i] = make_float2(r.need64 ? r.gint : r.z, pix);
@@ -268,7 +243,7 @@ reconstruct_vec_kernel(const __grid_constant__ KParams p)
                     if (p.kbin) p.kbin[o] = (int16_t)kbin;
                     if (p.corr) p.corr[o] = (int8_t)r.corr;
                     if (p.phase_pix) p.phase_pix[o] = pix;
-                    if (p.proj_u) p.proj_u[o] = mod_ok ? __dadd_rn((double)r.gint, (double)pix) : 0.0;
+                    if (p.proj_u) p.proj_u[o] = r.has_u ? __dadd_rn((double)r.gint, (double)pix) : 0.0;
                 }
             }
         }
@@ -396,9 +371,9 @@ reconstruct_scalar_kernel(const __grid_constant__ KParams p)
     if (p.use_mod) mod_ok = __fadd_rn(__fmul_rn(s, s), __fmul_rn(c, c)) >= p.thr2;
     PixelResult r;
     const RowConst rc = make_row_const(p, v);
-    if (p.z_fp64) unwrap_and_triangulate<true, true>(p, rc, kbin, pix, mod_ok, (float)u, r);
-    else unwrap_and_triangulate<true, false>(p, rc, kbin, pix, mod_ok, (float)u, r);
-    float4 outv = make_float4(r.x, r.y, r.z, mod_ok ? r.w : 0.f);   // [EXT] rejected by the modulation test: U = 0
+    if (p.z_fp64) unwrap_and_triangulate<true, true, true>(p, rc, kbin, pix, mod_ok, (float)u, r);
+    else unwrap_and_triangulate<true, false, true>(p, rc, kbin, pix, mod_ok, (float)u, r);
+    float4 outv = make_float4(r.x, r.y, r.z, r.w);                  // [EXT] rejected by the modulation test: w = 0
     int ok = r.valid ? 1 : 0;
     if (r.need64) outv = resolve_f64(p, r.gint, pix, u, v, &ok);
     if (p.depth) {
@@ -416,7 +391,7 @@ reconstruct_scalar_kernel(const __grid_constant__ KParams p)
         if (p.kbin) p.kbin[idx] = (int16_t)kbin;
         if (p.corr) p.corr[idx] = (int8_t)r.corr;
         if (p.phase_pix) p.phase_pix[idx] = pix;
-        if (p.proj_u) p.proj_u[idx] = mod_ok ? __dadd_rn((double)r.gint, (double)pix) : 0.0;
+        if (p.proj_u) p.proj_u[idx] = r.has_u ? __dadd_rn((double)r.gint, (double)pix) : 0.0;
     }
 }
 

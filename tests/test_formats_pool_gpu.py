@@ -308,3 +308,22 @@ def test_dynamic_frames_result_formats(built_library, base_calibration, W, H):
     # a single frame has no dynamic map: nothing is written, nothing fails
     rec.dyna_track_into_ex(frames, 1, u0, res, window=21)
     rec.close()
+
+
+@pytest.mark.parametrize("H", [2048, 3000])
+def test_points_format_on_tall_images(built_library, base_calibration, H):
+    """Result()'s order keeps 17 bytes of shared memory per image row: above ~1750 rows the kernel needs the
+    opt-in for more than 48 KB (BASELINE configs[2] and [4] are 2048 and 3000 rows tall)."""
+    from structured_light_calculation_b200 import capi
+    cfg = _cfg("config1", 64, H)
+    cal, stacks = _stacks(cfg, base_calibration, 2)
+    rec = capi.Reconstructor(cfg, device=0, max_batch=2, num_slots=1)
+    rec.set_calibration(cal)
+    full = rec.reconstruct(stacks)
+    for order in (capi.SLC_ORDER_REFERENCE, capi.SLC_ORDER_ROW_MAJOR):
+        p = rec.reconstruct_ex(stacks, capi.SLC_RESULT_POINTS, order)
+        for i in range(2):
+            want = _select(full, i, order)
+            assert int(p["n_points"][i]) == len(want) > 0
+            assert bits_equal(np.ascontiguousarray(p["points"][i, : len(want)]), np.ascontiguousarray(want))
+    rec.close()
