@@ -128,7 +128,7 @@ struct CompactArgs {
 __global__ void __launch_bounds__(kCThreads)
 compact_rows_kernel(const CompactArgs a)
 {
-    __shared__ __align__(16) float s_pts[kRowTile * 3];
+    __shared__ __align__(16) float s_pts[kRowTile * 3 + 4];
     __shared__ short s_rank[kRowTile];
     __shared__ unsigned s_warp[kCThreads / 32];
     __shared__ unsigned s_base;
@@ -160,7 +160,11 @@ compact_rows_kernel(const CompactArgs a)
         }
     }
     __syncthreads();
-    // phase B: float4 of the valid pixels, 512 contiguous bytes per warp load -> packed float3 in shared memory
+    // phase B: float4 of the valid pixels, 512 contiguous bytes per warp load -> packed float3 in shared memory,
+    // staged at the output's own 16-byte phase so that the body goes out as 16-byte stores
+    const long long base = (long long)s_base;
+    const long long g0 = ((long long)stack * a.point_stride + base) * 3;      // first float of this tile in `points`
+    const unsigned ph = (unsigned)(g0 & 3);                                   // (points is 16-byte aligned: cudaMalloc / slc_host_alloc)
     float4 q[8];
     int r[8];
 #pragma unroll
@@ -170,14 +174,21 @@ compact_rows_kernel(const CompactArgs a)
     }
 #pragma unroll
     for (int i = 0; i < 8; i++)
-        if (r[i] >= 0) { s_pts[3 * r[i]] = q[i].x; s_pts[3 * r[i] + 1] = q[i].y; s_pts[3 * r[i] + 2] = q[i].z; }
+        if (r[i] >= 0) { float* d = s_pts + ph + 3 * r[i]; d[0] = q[i].x; d[1] = q[i].y; d[2] = q[i].z; }
     __syncthreads();
-    const long long base = (long long)s_base;
     long long room = a.point_stride - base;                 // points that still fit this frame set's slice
     if (room <= 0) return;
     const unsigned n_out = (unsigned)(room < (long long)total ? room : (long long)total) * 3u;
-    float* dst = a.points + ((long long)stack * a.point_stride + base) * 3;
-    for (unsigned j = t; j < n_out; j += kCThreads) __stcs(dst + j, s_pts[j]);
+    float* dst = a.points + g0 - ph;                        // 16-byte aligned; float k of the tile sits at dst[ph + k]
+    const unsigned end = ph + n_out, body0 = ph ? 4u : 0u, body1 = end & ~3u;
+    if ((reinterpret_cast<uintptr_t>(a.points) & 15) == 0) {
+        for (unsigned j = ph + t; j < min(4u, end) && ph; j += kCThreads) __stcs(dst + j, s_pts[j]);
+        for (unsigned j = body0 + 4 * t; j < body1; j += 4 * kCThreads)
+            __stcs(reinterpret_cast<float4*>(dst + j), *reinterpret_cast<const float4*>(s_pts + j));
+        for (unsigned j = max(body1, body0) + t; j < end; j += kCThreads) __stcs(dst + j, s_pts[j]);
+    } else {
+        for (unsigned j = ph + t; j < end; j += kCThreads) __stcs(dst + j, s_pts[j]);
+    }
 }
 
 // ---- SLC_ORDER_REFERENCE: tile = 8 adjacent columns x H rows --------------------------------
