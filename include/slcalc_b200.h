@@ -262,7 +262,10 @@ int slc_pool_set_gray_lut(slc_pool *pool, const int16_t *gray2bin, int32_t n);
 /* contiguous block [*lo, *hi) of n_items for shard `index` of `n_shards`; sizes differ by at most one */
 int slc_shard_range(int64_t n_items, int32_t index, int32_t n_shards, int64_t *lo, int64_t *hi);
 /* n_stacks frame sets in host memory -> results in host memory, all members at once; blocks.
- * slc_pool_last_shares(): how many frame sets each member took in the last call. */
+ * A failure on one member (including a SLC_RESULT_POINTS frame set that does not fit point_stride) ends the
+ * call early: the other members finish the chunks they hold and take no more, the first failing member's
+ * status and message are returned.  slc_pool_last_shares(): how many frame sets each member took in the
+ * last call. */
 int slc_pool_reconstruct_host(slc_pool *pool, const uint8_t *h_stack, int32_t n_stacks,
                               const slc_result *h_out);
 int slc_pool_last_shares(const slc_pool *pool, int32_t *frame_sets_per_member, int32_t n_members);
