@@ -23,7 +23,9 @@ cases = [(1280, 1024, 1280, 6, 4), (1280, 1024, 1280, 7, 4), (1280, 1024, 1280, 
          (1920, 1200, 2560, 6, 4), (1920, 1200, 2560, 7, 4), (1920, 1200, 2560, 8, 4), (1920, 1200, 2560, 9, 4),
          (1280, 1040, 1280, 7, 4), (1296, 1024, 1280, 7, 4),
          (1280, 1024, 1280, 8, 3), (1280, 1024, 1280, 7, 6), (1280, 1024, 1280, 8, 5),     # <G, 0> instances
-         (1280, 1024, 4096, 11, 4), (1280, 1024, 1280, 4, 4), (1280, 1024, 4096, 12, 3)]
+         (1280, 1024, 4096, 11, 4), (1280, 1024, 1280, 4, 4), (1280, 1024, 4096, 12, 3),
+         (1280, 1024, 1280, 7, 3), (1920, 1200, 2560, 9, 3),                              # <G, 3> instances
+         (1920, 1200, 2560, 9, 5), (1920, 1200, 2560, 9, 6), (1920, 1200, 2560, 9, 8), (1920, 1200, 2560, 9, 12)]
 if os.environ.get("SWEEP_QUICK"):          # one small batch per Gray depth, for an ncu capture
     cases = cases[:4]
 for W, H, PW, G, N in cases:

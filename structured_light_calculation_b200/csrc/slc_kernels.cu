@@ -566,6 +566,13 @@ const VecEntry kVecTable[] = {
     SLC_VEC_TUNE(8, 10, 0),  SLC_VEC_TUNE(8, 0, 0),
     SLC_VEC_TUNE(16, 9, 4),  SLC_VEC_TUNE(16, 7, 4), SLC_VEC_TUNE(16, 8, 4), SLC_VEC_TUNE(16, 0, 0),
     SLC_VEC(4, 7, 4),   SLC_VEC(4, 8, 4),
+    // three-step phase shifting, the usual alternative to four steps, at the usual Gray depths
+    SLC_VEC(4, 7, 3),   SLC_VEC(4, 8, 3),   SLC_VEC(4, 9, 3),   SLC_VEC(4, 10, 3),
+    // ... and five / six steps (0.75 / 0.79 of the HBM peak through the <G, 0> instances, profiles/r02_sweep_geometry.txt)
+    SLC_VEC(4, 7, 5),   SLC_VEC(4, 8, 5),   SLC_VEC(4, 9, 5),   SLC_VEC(4, 10, 5),
+    SLC_VEC(4, 7, 6),   SLC_VEC(4, 8, 6),   SLC_VEC(4, 9, 6),   SLC_VEC(4, 10, 6),
+    // eight / twelve steps beside the two BASELINE pairs
+    SLC_VEC(8, 7, 8),   SLC_VEC(8, 9, 8),   SLC_VEC(8, 10, 8),  SLC_VEC(8, 8, 12),  SLC_VEC(8, 9, 12),
     SLC_VEC_TUNE(4, 9, 4),   SLC_VEC_TUNE(4, 6, 4), SLC_VEC_TUNE(4, 8, 8), SLC_VEC_TUNE(4, 10, 12),
     SLC_VEC(4, 5, 0),   SLC_VEC(4, 6, 0),   SLC_VEC(4, 7, 0),   SLC_VEC(4, 8, 0),   SLC_VEC(4, 9, 0),   SLC_VEC(4, 10, 0),
     // the remaining legal depths (CDecodeGray.cpp:39: 1..16), so that no geometry falls back to run-time loops
