@@ -1,12 +1,14 @@
 // slc_pool.cpp -- several GPUs behind one call (include/slcalc_b200.h "slc_pool").
 //
 // The frame sets of a DynaFrame sequence are independent in the north-star definition, so the
-// multi-GPU form of the path is a partition, not a collective: contiguous shards of frame sets,
-// one context + one feeder thread per GPU, calibration replicated.  This file is host C++ on
-// nothing but the public C ABI -- a feeder does exactly what a single-GPU caller would do with
-// its own context (slc_reconstruct_host_ex: pinned multi-slot upload / kernel / download).
-// What it replaces in the reference: the serial frame loop of main.cpp:42-45 /
-// CCalculation.cpp:221, which a reference user would have to thread by hand.
+// multi-GPU form of the path is a partition, not a collective: one context + one feeder thread
+// per GPU, calibration replicated, frame sets handed out ON DEMAND (max_batch at a time from one
+// atomic counter) so that every GPU keeps its upload / kernel / download slots full and a GPU
+// behind a faster host link takes more of the batch.  This file is host C++ on nothing but the
+// public C ABI -- a feeder does exactly what a single-GPU caller would do with its own context
+// (slc_submit_host_ex / slc_wait over the context's stream slots).  What it replaces in the
+// reference: the serial frame loop of main.cpp:42-45 / CCalculation.cpp:221, which a reference
+// user would have to thread by hand.
 #include "../../include/slcalc_b200.h"
 
 #include <atomic>
